@@ -1,0 +1,21 @@
+"""edge_diffusion_tts_b200 -- B200 (sm_100a) implementation of the few-step
+sampling path of Krabbens/edge-diffusion-tts behind the reference's own API.
+
+    from edge_diffusion_tts_b200 import CFG, DiffusionSchedule, EdgeDiffusionDecoder, EdgeInference
+
+Host code is Python/PyTorch (device memory, streams, torch.distributed); all
+arithmetic on the path is hand-written CUDA in ``lib/libedtts.so`` behind the C
+ABI of ``include/edtts.h``.  No CPU fallback, no Triton, no torch.compile.
+"""
+from .config import CFG, get_device, set_seed
+from .schedule import DiffusionSchedule
+from .vq import VectorQuantizer
+from .decoder import EdgeDiffusionDecoder
+from .encoder import SemanticEncoder
+from .inference import EdgeInference
+from .conv import DepthwiseSeparableConv
+from . import dist
+
+__version__ = "0.1.0"
+__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "VectorQuantizer", "EdgeDiffusionDecoder",
+           "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "dist"]

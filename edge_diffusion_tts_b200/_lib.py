@@ -1,0 +1,139 @@
+"""ctypes binding of libedtts.so (C ABI declared in include/edtts.h).
+
+There is no CPU fallback: if the shared library is missing or a tensor is not
+on a CUDA device the call raises.  Build the library with
+``python -c "import __graft_entry__ as g; g.build()"`` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libedtts.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+STEP_EPS, STEP_DDIM, STEP_DDPM = 0, 1, 2
+N_LAYERS = 4
+
+_f = C.c_void_p  # device pointers travel as void*
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, _f) for n in (
+        "norm1_norm_w", "norm1_proj_w", "norm1_proj_b", "attn_qkv_w", "attn_proj_w", "attn_proj_b", "norm2_w",
+        "q_proj_w", "kv_down_w", "kv_norm_w", "kv_up_w", "cross_out_w", "norm3_norm_w", "norm3_proj_w",
+        "norm3_proj_b", "ffn0_w", "ffn0_b", "ffn3_w", "ffn3_b")]
+
+
+class DecoderWeights(C.Structure):
+    _fields_ = [(n, _f) for n in (
+        "token_emb", "sem_proj_w", "sem_proj_b", "time1_w", "time1_b", "time3_w", "time3_b", "step_emb",
+        "in_proj_w", "in_proj_b", "pos_pe", "ctx_pe", "time_freqs", "final_norm_w", "final_norm_b", "out_proj_w",
+        "out_proj_b")] + [("layers", LayerWeights * N_LAYERS), ("codebook_size", C.c_int32),
+                          ("pos_rows", C.c_int32), ("ctx_rows", C.c_int32), ("reserved", C.c_int32),
+                          ("packed_bf16", _f)]
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("write_x_prev", C.c_int32), ("t", _f), ("t_prev", _f), ("alpha_bar", _f),
+                ("alphas", _f), ("betas", _f), ("posterior_var", _f), ("noise", _f), ("eps_out", _f),
+                ("x_prev_out", _f), ("x0_out", _f)]
+
+
+# name -> (restype, argtypes); must list every symbol of include/edtts.h
+_i32, _i64, _p = C.c_int32, C.c_int64, C.c_void_p
+SIGNATURES = {
+    "edtts_version": (C.c_int, []),
+    "edtts_last_error": (C.c_char_p, []),
+    "edtts_device_supported": (C.c_int, []),
+    "edtts_vq_argmin": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
+    "edtts_vq_workspace_bytes": (_i64, [_i32]),
+    "edtts_vq_gather_ste": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
+    "edtts_vq_bincount": (C.c_int, [_p, _p, _i64, _i32, _p]),
+    "edtts_encoder_proj": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+    "edtts_cond_prepare": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _i32, _p]),
+    "edtts_context_prepare": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "edtts_context_workspace_bytes": (_i64, [_i32, _i32]),
+    "edtts_decoder_step": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, C.POINTER(StepArgs), _p, _i64, _i32,
+                                      _i32, _i32, _i32, _p]),
+    "edtts_decoder_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "edtts_packed_bf16_bytes": (_i64, []),
+    "edtts_pack_weights_bf16": (C.c_int, [C.POINTER(DecoderWeights), _p, _p]),
+    "edtts_ddim_step": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_float, _p, _p, _i32, _i64, _p]),
+    "edtts_ddpm_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _p]),
+    "edtts_dsconv_forward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
+    "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "edtts_test_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
+    "edtts_test_attention": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+}
+
+_lib: Optional[C.CDLL] = None
+
+
+def load() -> C.CDLL:
+    """Load libedtts.so and bind every symbol; raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library drift apart
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().edtts_last_error().decode(errors="replace")
+        kind = {-1: ValueError, -4: NotImplementedError}.get(rc, RuntimeError)
+        raise kind(f"libedtts {what} failed ({rc}): {msg}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("edge_diffusion_tts_b200 runs on CUDA (B200) tensors only; got a CPU tensor "
+                           "(there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def f32(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"expected float32, got {t.dtype} (the path is fp32 at the API, SURVEY F11)")
+    return t.contiguous()
+
+
+def i64(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.int64:
+        t = t.long()
+    return t.contiguous()
+
+
+class Workspace:
+    """Grow-only device scratch owned by the caller side of the ABI."""
+
+    def __init__(self):
+        self._buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self._buf is None or self._buf.numel() < nbytes or self._buf.device != torch.device(device):
+            self._buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        return self._buf

@@ -1,0 +1,83 @@
+// Library-level entry points, error plumbing, encoder projection and the
+// single-kernel test hooks of the C ABI.
+#include <stdarg.h>
+#include <string.h>
+
+#define EDTTS_DECL_ONLY
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "attention_simt.cuh"
+#include "tc_path.cuh"
+
+namespace edtts {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return EDTTS_ECUDA;
+  }
+  return EDTTS_OK;
+}
+
+}  // namespace edtts
+
+using namespace edtts;
+
+extern "C" int edtts_version(void) { return 100; }
+extern "C" const char* edtts_last_error(void) { return g_err; }
+
+extern "C" int edtts_device_supported(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+// SemanticEncoder.proj (models/encoder.py:41-46): Linear(768,128) -> GELU ->
+// LayerNorm(128) -> Linear(128,128); the LayerNorm is the prologue of the second GEMM.
+extern "C" int edtts_encoder_proj(const float* h, const float* w0, const float* b0, const float* ln_w,
+                                  const float* ln_b, const float* w3, const float* b3, float* z_out, float* workspace,
+                                  int64_t rows, int32_t in_dim, void* stream) {
+  EDTTS_REQUIRE(h && w0 && b0 && ln_w && ln_b && w3 && b3 && z_out && workspace && rows > 0, EDTTS_EINVAL,
+                "encoder_proj: null argument");
+  const int D = EDTTS_SEMANTIC_DIM;
+  GemmArgs a;
+  a.A = h; a.rows = rows; a.K = in_dim; a.lda = in_dim; a.W = w0; a.N = D; a.bias = b0; a.out = workspace; a.ldo = D;
+  a.epi = EPI_GELU;
+  int rc = launch_gemm_simt(a, as_stream(stream));
+  if (rc) return rc;
+  GemmArgs b;
+  b.A = workspace; b.rows = rows; b.K = D; b.lda = D; b.W = w3; b.N = D; b.bias = b3; b.out = z_out; b.ldo = D;
+  b.pro = PRO_LN; b.norm_w = ln_w; b.norm_b = ln_b; b.norm_eps = 1e-5f;
+  return launch_gemm_simt(b, as_stream(stream));
+}
+
+extern "C" int edtts_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K,
+                                 int32_t N, int32_t precision, void* stream) {
+  EDTTS_REQUIRE(x && w && y && rows > 0, EDTTS_EINVAL, "test_linear: null argument");
+  if (precision == EDTTS_PREC_BF16) return tc_test_linear(x, w, bias, y, rows, K, N, as_stream(stream));
+  GemmArgs g;
+  g.A = x; g.rows = rows; g.K = K; g.lda = K; g.W = w; g.N = N; g.bias = bias; g.out = y; g.ldo = N;
+  return launch_gemm_simt(g, as_stream(stream));
+}
+
+extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const float* k, const float* v,
+                                    int32_t kv_stride, float* o, int32_t B, int32_t Tq, int32_t Tk, int32_t window,
+                                    int32_t precision, void* stream) {
+  EDTTS_REQUIRE(q && k && v && o && B > 0 && Tq > 0 && Tk > 0, EDTTS_EINVAL, "test_attention: null argument");
+  EDTTS_REQUIRE(precision == EDTTS_PREC_FP32, EDTTS_ENOTSUP, "test_attention: only fp32 is exposed");
+  AttnArgs a{q, q_stride, k, v, kv_stride, o, H, Tq, Tk, window, 1.0f / sqrtf((float)HD)};
+  return launch_attn_simt(a, B, as_stream(stream));
+}

@@ -1,0 +1,77 @@
+// Shared helpers for libedtts.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+
+#include "../../include/edtts.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libedtts is written for sm_100a (B200) only"
+#endif
+
+namespace edtts {
+
+constexpr int H = EDTTS_HIDDEN;        // 160
+constexpr int M = EDTTS_N_MELS;        // 80
+constexpr int NH = EDTTS_HEADS;        // 4
+constexpr int HD = EDTTS_HEAD_DIM;     // 40
+constexpr int RANK = EDTTS_KV_RANK;    // 80
+constexpr int FFN = EDTTS_FFN_HIDDEN;  // 320
+constexpr int NL = EDTTS_LAYERS;       // 4
+constexpr int WIN = EDTTS_WINDOW;      // 64
+
+// ---- error reporting across the C ABI -------------------------------------
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);          // cudaPeekAtLastError -> EDTTS_ECUDA
+
+#define EDTTS_REQUIRE(cond, code, ...)  \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::edtts::set_error(__VA_ARGS__);  \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- device math ------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {          // nn.GELU() default (exact erf)
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float silu(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// DDIM eta=0 / eta>0 update with torch's operation order and no FMA contraction
+// (schedule.py:179-202), so that it is bit-identical to the reference given the
+// same eps.  ab_t, ab_p are alpha_bar[t], alpha_bar[max(t_prev,0)] (or 1 if t_prev<0).
+__device__ __forceinline__ void ddim_update(float x, float e, float nz, float ab_t, float ab_p, float eta,
+                                            float& x_prev, float& x0) {
+  const float s1 = __fsqrt_rn(__fsub_rn(1.0f, ab_t));
+  float v = __fdiv_rn(__fsub_rn(x, __fmul_rn(s1, e)), __fsqrt_rn(ab_t));
+  v = fminf(fmaxf(v, -3.0f), 3.0f);
+  x0 = v;
+  const float om_p = __fsub_rn(1.0f, ab_p);
+  const float ratio = __fmul_rn(__fdiv_rn(om_p, __fsub_rn(1.0f, ab_t)), __fsub_rn(1.0f, __fdiv_rn(ab_t, ab_p)));
+  const float sigma = __fmul_rn(eta, __fsqrt_rn(ratio));
+  const float dir = __fmul_rn(__fsqrt_rn(__fsub_rn(om_p, __fmul_rn(sigma, sigma))), e);
+  x_prev = __fadd_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(ab_p), v), dir), __fmul_rn(sigma, nz));
+}
+
+// DDPM ancestral update (schedule.py:221-238), torch operation order.
+__device__ __forceinline__ float ddpm_update(float x, float e, float nz, float alpha, float alpha_bar, float beta,
+                                             float var, float nonzero) {
+  const float coef1 = __fdiv_rn(1.0f, __fsqrt_rn(alpha));
+  const float coef2 = __fdiv_rn(beta, __fsqrt_rn(__fsub_rn(1.0f, alpha_bar)));
+  const float mean = __fmul_rn(coef1, __fsub_rn(x, __fmul_rn(coef2, e)));
+  return __fadd_rn(mean, __fmul_rn(__fmul_rn(nonzero, __fsqrt_rn(var)), nz));
+}
+
+}  // namespace edtts

@@ -1,0 +1,118 @@
+// Stand-alone DiffusionSchedule update rules (schedule.py:157-238) -- used when a
+// caller drives DiffusionSchedule.get_ddim_step / ddpm_step directly; inside
+// generate_mel the same arithmetic runs fused in the last kernel of the step.
+// Pure streaming kernels: read x, eps (+noise), write x_prev (+x0); 128-bit
+// accesses, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace edtts {
+
+template <int VEC>
+__global__ void __launch_bounds__(256) ddim_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                   const float* __restrict__ noise, const float* __restrict__ alpha_bar,
+                                                   const int64_t* __restrict__ t, const int64_t* __restrict__ t_prev,
+                                                   float eta, float* __restrict__ x_prev, float* __restrict__ x0,
+                                                   int64_t total, int64_t n) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total;
+       i += (int64_t)gridDim.x * blockDim.x * VEC) {
+    const int b = (int)(i / n);
+    const float ab_t = alpha_bar[t[b]];
+    const int64_t tp = t_prev[b];
+    const float ab_p = tp >= 0 ? alpha_bar[tp] : 1.0f;
+    float xv[VEC], ev[VEC], nv[VEC], xp[VEC], xz[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<float4*>(ev) = *reinterpret_cast<const float4*>(eps + i);
+      if (noise) *reinterpret_cast<float4*>(nv) = *reinterpret_cast<const float4*>(noise + i);
+    } else {
+      xv[0] = x[i];
+      ev[0] = eps[i];
+      if (noise) nv[0] = noise[i];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) ddim_update(xv[j], ev[j], noise ? nv[j] : 0.f, ab_t, ab_p, eta, xp[j], xz[j]);
+    if (VEC == 4) {
+      if (x_prev) *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
+      if (x0) *reinterpret_cast<float4*>(x0 + i) = *reinterpret_cast<float4*>(xz);
+    } else {
+      if (x_prev) x_prev[i] = xp[0];
+      if (x0) x0[i] = xz[0];
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) ddpm_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                   const float* __restrict__ noise, const float* __restrict__ alphas,
+                                                   const float* __restrict__ alpha_bar, const float* __restrict__ betas,
+                                                   const float* __restrict__ post_var, const int64_t* __restrict__ t,
+                                                   float* __restrict__ x_prev, int64_t total, int64_t n) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total;
+       i += (int64_t)gridDim.x * blockDim.x * VEC) {
+    const int b = (int)(i / n);
+    const int64_t tt = t[b];
+    const float al = alphas[tt], ab = alpha_bar[tt], be = betas[tt], pv = post_var[tt];
+    const float nzm = tt > 0 ? 1.0f : 0.0f;
+    float xv[VEC], ev[VEC], nv[VEC], xp[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<float4*>(ev) = *reinterpret_cast<const float4*>(eps + i);
+      *reinterpret_cast<float4*>(nv) = *reinterpret_cast<const float4*>(noise + i);
+    } else {
+      xv[0] = x[i];
+      ev[0] = eps[i];
+      nv[0] = noise[i];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) xp[j] = ddpm_update(xv[j], ev[j], nv[j], al, ab, be, pv, nzm);
+    if (VEC == 4) *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
+    else x_prev[i] = xp[0];
+  }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline unsigned stream_grid(int64_t work_items) {
+  const int64_t blocks = (work_items + 255) / 256;
+  const int64_t cap = 148 * 8;   // 8 resident 256-thread CTAs per SM
+  return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace edtts
+
+using namespace edtts;
+
+extern "C" int edtts_ddim_step(const float* x_t, const float* eps, const float* noise, const float* alpha_bar,
+                               const int64_t* t, const int64_t* t_prev, float eta, float* x_prev_out, float* x0_out,
+                               int32_t B, int64_t n, void* stream) {
+  EDTTS_REQUIRE(x_t && eps && alpha_bar && t && t_prev && (x_prev_out || x0_out) && B > 0 && n > 0, EDTTS_EINVAL,
+                "ddim_step: null argument");
+  EDTTS_REQUIRE(eta == 0.f || noise, EDTTS_EINVAL, "ddim_step: eta > 0 needs noise");
+  const int64_t total = (int64_t)B * n;
+  const bool vec = n % 4 == 0 && aligned16(x_t) && aligned16(eps) && (!noise || aligned16(noise)) &&
+                   (!x_prev_out || aligned16(x_prev_out)) && (!x0_out || aligned16(x0_out));
+  if (vec)
+    ddim_kernel<4><<<stream_grid(total / 4), 256, 0, as_stream(stream)>>>(x_t, eps, eta == 0.f ? nullptr : noise,
+                                                                          alpha_bar, t, t_prev, eta, x_prev_out, x0_out,
+                                                                          total, n);
+  else
+    ddim_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, eps, eta == 0.f ? nullptr : noise, alpha_bar,
+                                                                      t, t_prev, eta, x_prev_out, x0_out, total, n);
+  return check_launch("ddim_step");
+}
+
+extern "C" int edtts_ddpm_step(const float* x_t, const float* eps, const float* noise, const float* alphas,
+                               const float* alpha_bar, const float* betas, const float* posterior_var, const int64_t* t,
+                               float* x_prev_out, int32_t B, int64_t n, void* stream) {
+  EDTTS_REQUIRE(x_t && eps && noise && alphas && alpha_bar && betas && posterior_var && t && x_prev_out && B > 0 &&
+                    n > 0,
+                EDTTS_EINVAL, "ddpm_step: null argument");
+  const int64_t total = (int64_t)B * n;
+  const bool vec = n % 4 == 0 && aligned16(x_t) && aligned16(eps) && aligned16(noise) && aligned16(x_prev_out);
+  if (vec)
+    ddpm_kernel<4><<<stream_grid(total / 4), 256, 0, as_stream(stream)>>>(x_t, eps, noise, alphas, alpha_bar, betas,
+                                                                          posterior_var, t, x_prev_out, total, n);
+  else
+    ddpm_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, eps, noise, alphas, alpha_bar, betas,
+                                                                      posterior_var, t, x_prev_out, total, n);
+  return check_launch("ddpm_step");
+}

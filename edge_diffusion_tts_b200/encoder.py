@@ -1,0 +1,83 @@
+"""SemanticEncoder (models/encoder.py:14-131), thin: the trainable projection
+(Linear 768->128, GELU, LayerNorm, Linear 128->128) and the VectorQuantizer run
+as CUDA kernels; HuBERT stays the ``transformers`` module (frozen third-party
+feature extractor, out of scope -- BASELINE configs feed synthetic 768-d features
+through ``quantize_features`` / ``encode_features``)."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .vq import VectorQuantizer
+
+
+class SemanticEncoder(nn.Module):
+    def __init__(self, cfg, hubert: Optional[nn.Module] = None, load_hubert: bool = True):
+        super().__init__()
+        self.cfg = cfg
+        if getattr(cfg, "use_fsq", False):
+            raise NotImplementedError("FSQ quantiser is outside the accelerated path (SURVEY.md F5); set use_fsq=False")
+        if hubert is None and load_hubert:
+            from transformers import HubertModel                       # encoder.py:35 (needs the checkpoint)
+            hubert = HubertModel.from_pretrained(cfg.hubert_id)
+        self.hubert = hubert
+        if self.hubert is not None:
+            self.hubert.eval()
+            for p in self.hubert.parameters():
+                p.requires_grad = False
+        self.proj = nn.Sequential(nn.Linear(768, cfg.semantic_dim), nn.GELU(), nn.LayerNorm(cfg.semantic_dim),
+                                  nn.Linear(cfg.semantic_dim, cfg.semantic_dim))      # encoder.py:41-46
+        self.vq = VectorQuantizer(cfg.semantic_dim, cfg.codebook_size, commit=cfg.vq_commit)
+        self.codebook_size = cfg.codebook_size
+        self._ws = _lib.Workspace()
+
+    @torch.no_grad()
+    def extract_hubert(self, wav_16k: torch.Tensor) -> torch.Tensor:
+        """encoder.py:60-72."""
+        if self.hubert is None:
+            raise RuntimeError("SemanticEncoder was built without HuBERT; feed features to quantize_features()")
+        out = self.hubert(wav_16k, output_hidden_states=True)
+        return out.hidden_states[self.cfg.hubert_layer]
+
+    @torch.no_grad()
+    def project(self, h: torch.Tensor) -> torch.Tensor:
+        """``self.proj(h)`` (encoder.py:95) as two fused GEMM kernels: h [B,S,768] -> z [B,S,128]."""
+        lib = _lib.load()
+        h = _lib.f32(h)
+        B, S, Din = h.shape
+        D = self.cfg.semantic_dim
+        z = torch.empty(B, S, D, dtype=torch.float32, device=h.device)
+        if B * S == 0:
+            return z
+        ws = self._ws.get(B * S * D * 4, h.device)
+        p = self.proj
+        W = [_lib.f32(t.detach()) for t in (p[0].weight, p[0].bias, p[2].weight, p[2].bias, p[3].weight, p[3].bias)]
+        _lib.check(lib.edtts_encoder_proj(_lib.ptr(h), *[_lib.ptr(t) for t in W], _lib.ptr(z), _lib.ptr(ws), B * S,
+                                          Din, _lib.stream_ptr(h.device)), "encoder_proj")
+        return z
+
+    def quantize_features(self, h: torch.Tensor):
+        """Everything after HuBERT in ``forward`` (encoder.py:95-100) -> the 5-tuple."""
+        return self.vq(self.project(h.detach()))
+
+    def encode_features(self, h: torch.Tensor) -> torch.Tensor:
+        return self.vq.encode(self.project(h))
+
+    def forward(self, wav_16k: torch.Tensor):
+        """encoder.py:74-100: (z_q, idx, vq_loss, perplexity, used)."""
+        return self.quantize_features(self.extract_hubert(wav_16k))
+
+    def encode(self, wav_16k: torch.Tensor) -> torch.Tensor:
+        """encoder.py:102-115."""
+        with torch.no_grad():
+            return self.encode_features(self.extract_hubert(wav_16k))
+
+    def decode_tokens(self, idx: torch.Tensor) -> torch.Tensor:
+        """encoder.py:117-127."""
+        return self.vq.decode(idx)
+
+    def get_trainable_params(self) -> list:
+        return list(self.proj.parameters()) + list(self.vq.parameters())

@@ -1,0 +1,217 @@
+/*
+ * edtts.h -- C ABI of libedtts.so: the B200 (sm_100a) implementation of the
+ * edge-diffusion-tts few-step sampling path.
+ *
+ * The reference (Krabbens/edge-diffusion-tts) has no FFI layer: its boundary for
+ * this path is the Python class API.  Each entry point
+ * below replaces the body of one reference method; the host-side mirror in
+ * edge_diffusion_tts_b200/ binds them with ctypes (see INTEGRATION.md for the
+ * stub a reference maintainer would add).  Reference citations are relative to
+ * /root/reference/edge_diffusion_tts.
+ *
+ * Contract for every call:
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless
+ *     the name says host; the CALLER owns every buffer and the workspace;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); no
+ *     allocation, no device synchronisation, no host read-back => every call is
+ *     legal inside CUDA-graph capture;
+ *   - returns 0 on success, a negative EDTTS_E* code otherwise; the message is
+ *     available from edtts_last_error() (thread-local); C++ exceptions never
+ *     cross the ABI;
+ *   - all floating-point tensors are contiguous fp32, indices are int64
+ *     (torch.long), exactly as the reference passes them.
+ *
+ * The kernels are specialised for the reference's default CFG (config.py:97-111):
+ * n_mels 80, hidden 160, 4 layers, 4 heads (head_dim 40), ffn hidden 320,
+ * kv_lora_rank 80, attention window 64, semantic_dim 128, codebook 512.
+ */
+#ifndef EDTTS_H
+#define EDTTS_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EDTTS_N_MELS 80
+#define EDTTS_HIDDEN 160
+#define EDTTS_LAYERS 4
+#define EDTTS_HEADS 4
+#define EDTTS_HEAD_DIM 40
+#define EDTTS_KV_RANK 80
+#define EDTTS_FFN_HIDDEN 320
+#define EDTTS_WINDOW 64
+#define EDTTS_SEMANTIC_DIM 128
+#define EDTTS_STEP_EMB_ROWS 16
+
+#define EDTTS_OK 0
+#define EDTTS_EINVAL (-1)    /* bad argument (null pointer, unsupported size)      */
+#define EDTTS_ENOSPC (-2)    /* workspace too small                                */
+#define EDTTS_ECUDA (-3)     /* a CUDA runtime call / launch failed                */
+#define EDTTS_ENOTSUP (-4)   /* configuration outside the specialised kernel set   */
+
+/* arithmetic of the decoder contractions */
+#define EDTTS_PREC_FP32 0    /* CUDA-core FFMA, fp32 in / fp32 accumulate (parity path, 1e-4) */
+#define EDTTS_PREC_BF16 1    /* tcgen05 tensor cores, bf16 in / fp32 accumulate (1e-2 rel-L2)  */
+
+/* epilogue fused into the last kernel of a decoder step */
+#define EDTTS_STEP_EPS 0     /* write eps only           (decoder.py:109)          */
+#define EDTTS_STEP_DDIM 1    /* eps -> x_prev, x0        (schedule.py:179-202)     */
+#define EDTTS_STEP_DDPM 2    /* eps -> x_prev with noise (schedule.py:221-238)     */
+
+/* One DiffusionTransformerBlock (layers/transformer.py:71-160).  Names follow the
+ * reference state-dict keys `layers.<i>.<...>`. */
+typedef struct edtts_layer_weights {
+  const float* norm1_norm_w;   /* norm1.norm.weight            [160]       */
+  const float* norm1_proj_w;   /* norm1.proj.weight            [320,160]   */
+  const float* norm1_proj_b;   /* norm1.proj.bias              [320]       */
+  const float* attn_qkv_w;     /* attn.qkv.weight              [480,160]   */
+  const float* attn_proj_w;    /* attn.proj.weight             [160,160]   */
+  const float* attn_proj_b;    /* attn.proj.bias               [160]       */
+  const float* norm2_w;        /* norm2.weight                 [160]       */
+  const float* q_proj_w;       /* cross_attn.q_proj.weight     [160,160]   */
+  const float* kv_down_w;      /* cross_attn.kv_down_proj.weight [80,160]  */
+  const float* kv_norm_w;      /* cross_attn.kv_norm.weight    [80]        */
+  const float* kv_up_w;        /* cross_attn.kv_up_proj.weight [320,80]    */
+  const float* cross_out_w;    /* cross_attn.out_proj.weight   [160,160]   */
+  const float* norm3_norm_w;   /* norm3.norm.weight            [160]       */
+  const float* norm3_proj_w;   /* norm3.proj.weight            [320,160]   */
+  const float* norm3_proj_b;   /* norm3.proj.bias              [320]       */
+  const float* ffn0_w;         /* ffn.net.0.weight             [640,160]   */
+  const float* ffn0_b;         /* ffn.net.0.bias               [640]       */
+  const float* ffn3_w;         /* ffn.net.3.weight             [160,320]   */
+  const float* ffn3_b;         /* ffn.net.3.bias               [160]       */
+} edtts_layer_weights;
+
+/* EdgeDiffusionDecoder parameters (models/decoder.py:17-64), device pointers. */
+typedef struct edtts_decoder_weights {
+  const float* token_emb;      /* token_emb.weight   [codebook,160]                 */
+  const float* sem_proj_w;     /* sem_proj.weight    [160,128]                      */
+  const float* sem_proj_b;     /* sem_proj.bias      [160]                          */
+  const float* time1_w;        /* time_emb.1.weight  [160,160]                      */
+  const float* time1_b;        /* time_emb.1.bias    [160]                          */
+  const float* time3_w;        /* time_emb.3.weight  [160,160]                      */
+  const float* time3_b;        /* time_emb.3.bias    [160]                          */
+  const float* step_emb;       /* step_emb.weight    [16,160]                       */
+  const float* in_proj_w;      /* in_proj.weight     [160,80]                       */
+  const float* in_proj_b;      /* in_proj.bias       [160]                          */
+  const float* pos_pe;         /* pos_emb.pe         [pos_rows,160]  (host may extend rows, F7) */
+  const float* ctx_pe;         /* context_pos_emb.pe [ctx_rows,160]                 */
+  const float* time_freqs;     /* exp(arange(80) * -ln(1e4)/79), embeddings.py:38-41 [80] */
+  const float* final_norm_w;   /* final_norm.weight  [160]                          */
+  const float* final_norm_b;   /* final_norm.bias    [160]                          */
+  const float* out_proj_w;     /* out_proj.weight    [80,160]                       */
+  const float* out_proj_b;     /* out_proj.bias      [80]                           */
+  edtts_layer_weights layers[EDTTS_LAYERS];
+  int32_t codebook_size;       /* rows of token_emb                                  */
+  int32_t pos_rows;
+  int32_t ctx_rows;
+  int32_t reserved;
+  const void* packed_bf16;     /* image written by edtts_pack_weights_bf16 (or NULL)  */
+} edtts_decoder_weights;
+
+/* --- library ------------------------------------------------------------- */
+int edtts_version(void);
+const char* edtts_last_error(void);
+/* 1 if the device `stream` belongs to can run the kernels (sm_100), else 0. */
+int edtts_device_supported(void);
+
+/* --- VectorQuantizer (models/vq.py) --------------------------------------- */
+/* vq.py:75-82 / :153-159: idx[r] = argmin_k ||z_r - E_k||^2, first minimum.
+ * fp32 FFMA distances; near-ties are re-ranked in fp64 so the result equals the
+ * exact argmin.  workspace: edtts_vq_workspace_bytes(K) bytes. */
+int edtts_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, int64_t rows, int32_t dim,
+                    int32_t codebook_size, void* workspace, void* stream);
+int64_t edtts_vq_workspace_bytes(int32_t codebook_size);
+/* vq.py:83,98: z_q = z + (E[idx] - z)  (straight-through rounding included). */
+int edtts_vq_gather_ste(const float* z, const float* codebook, const int64_t* idx, float* zq_out, int64_t rows,
+                        int32_t dim, int32_t codebook_size, void* stream);
+/* vq.py:102: counts = bincount(idx, minlength=K) as int32 (zeroed by the call). */
+int edtts_vq_bincount(const int64_t* idx, int32_t* counts_out, int64_t rows, int32_t codebook_size, void* stream);
+
+/* --- SemanticEncoder.proj (models/encoder.py:41-46) ------------------------ */
+/* z = Linear(128,128)(LayerNorm(GELU(Linear(768,128)(h)))); workspace rows*128 floats. */
+int edtts_encoder_proj(const float* h, const float* w0, const float* b0, const float* ln_w, const float* ln_b,
+                       const float* w3, const float* b3, float* z_out, float* workspace, int64_t rows,
+                       int32_t in_dim, void* stream);
+
+/* --- EdgeDiffusionDecoder (models/decoder.py:66-109) ----------------------- */
+/* decoder.py:77-80 + transformer.py:64-66 for all 8 AdaLayerNorms:
+ *   cond[B,160]; mod[B, 2*LAYERS, 320] = (scale | shift) of norm1, norm3 per layer.
+ * t int64[B]; step_idx int64[B] or NULL. */
+int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t* t, const int64_t* step_idx, float* cond_out,
+                       float* mod_out, int32_t B, void* stream);
+/* decoder.py:83-93 + mla.py:144-153 for all layers (step-invariant):
+ *   kv_out[LAYERS][B*S][320] = (k | v), head-major inside each half.
+ * Exactly one of sem_idx (int64[B,S]) / sem_features (fp32[B,S,128]) is non-NULL. */
+int edtts_context_prepare(const edtts_decoder_weights* w, const int64_t* sem_idx, const float* sem_features,
+                          float* kv_out, void* workspace, int64_t workspace_bytes, int32_t B, int32_t S,
+                          int32_t precision, void* stream);
+int64_t edtts_context_workspace_bytes(int32_t B, int32_t S);
+
+/* Coefficients of the fused update, gathered on the device from the schedule
+ * tables (so the call stays graph-capturable): t, t_prev int64[B]. */
+typedef struct edtts_step_args {
+  int32_t mode;                 /* EDTTS_STEP_*                                          */
+  int32_t write_x_prev;         /* DDIM: 0 skips x_prev on the last step     */
+  const int64_t* t;             /* [B]                                                   */
+  const int64_t* t_prev;        /* [B] (DDIM)                                            */
+  const float* alpha_bar;       /* schedule.alpha_bar          [T]                       */
+  const float* alphas;          /* schedule.alphas             [T] (DDPM)                */
+  const float* betas;           /* schedule.betas              [T] (DDPM)                */
+  const float* posterior_var;   /* schedule.posterior_variance [T] (DDPM)                */
+  const float* noise;           /* [B,T,80] N(0,1) draws (DDPM)                          */
+  float* eps_out;               /* [B,T,80] or NULL                                      */
+  float* x_prev_out;            /* [B,T,80] or NULL                                      */
+  float* x0_out;                /* [B,T,80] or NULL (DDIM)                               */
+} edtts_step_args;
+
+/* One decoder evaluation (decoder.py:96-109) with the update rule fused into the
+ * last kernel.  x_t [B,T,80]; mod from edtts_cond_prepare; kv from
+ * edtts_context_prepare (S context tokens per utterance). */
+int edtts_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                       const edtts_step_args* args, void* workspace, int64_t workspace_bytes, int32_t B,
+                       int32_t T, int32_t S, int32_t precision, void* stream);
+int64_t edtts_decoder_workspace_bytes(int32_t B, int32_t T, int32_t S, int32_t precision);
+
+/* bf16 tensor-core path: repack the fp32 parameters into the shared-memory tile
+ * images the tcgen05 kernels bulk-copy (K-major core-matrix layout, bf16). */
+int64_t edtts_packed_bf16_bytes(void);
+int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* packed_out, void* stream);
+
+/* --- DiffusionSchedule update rules, standalone (schedule.py) -------------- */
+/* get_ddim_step (schedule.py:157-202): per-row t / t_prev gathered from alpha_bar.
+ * n = elements per batch row (T*80).  noise may be NULL when eta == 0. */
+int edtts_ddim_step(const float* x_t, const float* eps, const float* noise, const float* alpha_bar,
+                    const int64_t* t, const int64_t* t_prev, float eta, float* x_prev_out, float* x0_out,
+                    int32_t B, int64_t n, void* stream);
+/* ddpm_step (schedule.py:204-238). */
+int edtts_ddpm_step(const float* x_t, const float* eps, const float* noise, const float* alphas,
+                    const float* alpha_bar, const float* betas, const float* posterior_var, const int64_t* t,
+                    float* x_prev_out, int32_t B, int64_t n, void* stream);
+
+/* --- DepthwiseSeparableConv (layers/conv.py:10-64), operator level ---------- */
+/* x [B,C_in,T] -> y [B,C_out,T_out], T_out = (T + 2*(k/2) - k)/stride + 1:
+ * depthwise k taps (no bias) -> pointwise 1x1 (+bias) -> GroupNorm(min(8,C_out)) -> GELU.
+ * workspace: edtts_dsconv_workspace_bytes(B, C_out, T_out). */
+int edtts_dsconv_forward(const float* x, const float* dw_w, const float* pw_w, const float* pw_b,
+                         const float* gn_w, const float* gn_b, float* y_out, void* workspace,
+                         int64_t workspace_bytes, int32_t B, int32_t c_in, int32_t c_out, int32_t T,
+                         int32_t kernel_size, int32_t stride, void* stream);
+int64_t edtts_dsconv_workspace_bytes(int32_t B, int32_t c_out, int32_t t_out);
+
+/* --- unit-test hooks for single kernels (parity tests call them through the ABI) */
+/* y[rows,N] = x[rows,K] @ w[N,K]^T (+bias) in the given precision. */
+int edtts_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K,
+                      int32_t N, int32_t precision, void* stream);
+/* o[B,Tq,160] = attention(q,k,v) per head; window < 0 => full attention.
+ * q rows have stride q_stride floats, k/v rows kv_stride floats. */
+int edtts_test_attention(const float* q, int32_t q_stride, const float* k, const float* v, int32_t kv_stride,
+                         float* o, int32_t B, int32_t Tq, int32_t Tk, int32_t window, int32_t precision,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EDTTS_H */

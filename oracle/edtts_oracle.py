@@ -1,0 +1,371 @@
+"""CPU oracle for the edge-diffusion-tts few-step sampling path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``edge_diffusion_tts_b200/`` may import
+this file; only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs use it, and only as the checker /
+reported baseline -- never as the thing shipped.
+
+It is a *functional* restatement (state-dict in, tensors out) of the reference's
+PyTorch modules, written from SURVEY.md appendix A; every function cites the
+reference ``file:line`` it follows (paths relative to
+``/root/reference/edge_diffusion_tts``).  It uses the same ATen ops the
+reference uses (``F.linear``, ``F.scaled_dot_product_attention`` with the dense
+band mask, ``F.layer_norm`` ...) so that timing it on host cores is
+representative of the reference's own CPU path.
+
+Parity pinning: the reference ships no tests or golden vectors for this path
+("parity unpinned" by the reference itself).  The oracle is
+therefore pinned against the *reference run in the build container*:
+``oracle/make_golden.py`` imports the unmodified reference, loads the synthetic
+weights of ``oracle/synth.py`` into its modules and records outputs under
+``tests/golden/``; ``tests/test_oracle_golden.py`` checks this restatement
+against those fixtures everywhere, and ``tests/test_oracle_vs_reference.py``
+checks it against the live reference wherever ``/root/reference`` exists.
+
+All functions run in the dtype of the tensors they are given, so passing an
+fp64 state dict yields the fp64 restatement used to measure the fp32 noise
+floor.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+State = Dict[str, Tensor]
+
+# Hyper-parameters of the default CFG (config.py:97-111) that the path reads.
+N_MELS = 80
+HIDDEN = 160
+LAYERS = 4
+HEADS = 4
+HEAD_DIM = 40
+KV_RANK = 80
+FFN_HIDDEN = 320
+WINDOW = 64
+SEMANTIC_DIM = 128
+CODEBOOK = 512
+DIFF_STEPS = 1000
+
+
+# ----------------------------------------------------------------------------
+# schedule.py
+# ----------------------------------------------------------------------------
+def cosine_schedule(T: int = DIFF_STEPS, device: str = "cpu") -> State:
+    """Cosine schedule tables, fp32 (schedule.py:36-59).  beta_start/beta_end
+    are ignored by the reference, so they are not parameters."""
+    s = 0.008
+    x = torch.linspace(0, T, T + 1, device=device)
+    ac = torch.cos(((x / T) + s) / (1 + s) * torch.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = torch.clip(1 - (ac[1:] / ac[:-1]), 0.0001, 0.9999)
+    alphas = 1.0 - betas
+    alpha_bar = torch.cumprod(alphas, dim=0)
+    alpha_bar_prev = F.pad(alpha_bar[:-1], (1, 0), value=1.0)
+    sqrt_ab = torch.sqrt(alpha_bar)
+    sqrt_1mab = torch.sqrt(1.0 - alpha_bar)
+    return {
+        "betas": betas,
+        "alphas": alphas,
+        "alpha_bar": alpha_bar,
+        "sqrt_alpha_bar": sqrt_ab,
+        "sqrt_one_minus_alpha_bar": sqrt_1mab,
+        "sqrt_recip_alpha_bar": torch.sqrt(1.0 / alpha_bar),
+        "sqrt_recip_alpha_bar_minus_one": torch.sqrt(1.0 / alpha_bar - 1),
+        "posterior_variance": betas * (1.0 - alpha_bar_prev) / (1.0 - alpha_bar),
+        "lambda_t": torch.log(sqrt_ab / sqrt_1mab),
+    }
+
+
+def ddim_step(tab: State, x_t: Tensor, t: Tensor, t_prev: Tensor, eps: Tensor,
+              eta: float = 0.0, noise: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+    """DDIM update (schedule.py:179-202).  Returns (x_prev, x0_pred)."""
+    ab = tab["alpha_bar"].to(x_t.dtype)
+    ab_t = ab[t][:, None, None]
+    ab_p = torch.where(t_prev[:, None, None] >= 0, ab[t_prev.clamp(min=0)][:, None, None],
+                       torch.ones_like(ab_t))
+    x0 = (x_t - torch.sqrt(1 - ab_t) * eps) / torch.sqrt(ab_t)
+    x0 = torch.clamp(x0, -3, 3)
+    sigma = eta * torch.sqrt((1 - ab_p) / (1 - ab_t) * (1 - ab_t / ab_p))
+    dir_xt = torch.sqrt(1 - ab_p - sigma ** 2) * eps
+    if eta > 0:
+        if noise is None:
+            noise = torch.randn_like(x_t)
+    else:
+        noise = 0
+    x_prev = torch.sqrt(ab_p) * x0 + dir_xt + sigma * noise
+    return x_prev, x0
+
+
+def ddpm_step(tab: State, x_t: Tensor, t: Tensor, eps: Tensor,
+              noise: Optional[Tensor] = None) -> Tensor:
+    """Ancestral DDPM update (schedule.py:221-238).  ``noise`` may be injected
+    (the reference draws ``torch.randn_like(x_t)`` at :232)."""
+    dt = x_t.dtype
+    alpha = tab["alphas"].to(dt)[t][:, None, None]
+    alpha_bar = tab["alpha_bar"].to(dt)[t][:, None, None]
+    beta = tab["betas"].to(dt)[t][:, None, None]
+    coef1 = 1.0 / torch.sqrt(alpha)
+    coef2 = beta / torch.sqrt(1.0 - alpha_bar)
+    mean = coef1 * (x_t - coef2 * eps)
+    var = tab["posterior_variance"].to(dt)[t][:, None, None]
+    if noise is None:
+        noise = torch.randn_like(x_t)
+    nonzero = (t > 0).to(dt)[:, None, None]
+    return mean + nonzero * torch.sqrt(var) * noise
+
+
+# ----------------------------------------------------------------------------
+# layers/embeddings.py
+# ----------------------------------------------------------------------------
+def time_freqs(dim: int = HIDDEN) -> Tensor:
+    """fp32 frequency vector of SinusoidalTimeEmb (embeddings.py:37-41)."""
+    half = dim // 2
+    return torch.exp(torch.arange(half, dtype=torch.float32) * (-math.log(10000.0) / (half - 1)))
+
+
+def time_embedding(t: Tensor, dim: int = HIDDEN, dtype=torch.float32) -> Tensor:
+    """SinusoidalTimeEmb.forward (embeddings.py:37-43): cat[sin, cos]."""
+    args = t.to(dtype).unsqueeze(1) * time_freqs(dim).to(dtype).unsqueeze(0)
+    return torch.cat([torch.sin(args), torch.cos(args)], dim=1)
+
+
+def positional_table(max_len: int, dim: int = HIDDEN) -> Tensor:
+    """SinusoidalPositionalEmb.__init__ (embeddings.py:122-128), fp32.
+    Used both to check the persistent ``pe`` buffers and to extend them past
+    1000 / 512 rows for BASELINE config 5 (a stated deviation)."""
+    pe = torch.zeros(max_len, dim)
+    position = torch.arange(0, max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, dim, 2) * (-math.log(10000.0) / dim))
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+def _pe_rows(sd: State, key: str, n: int, dtype) -> Tensor:
+    pe = sd[key]
+    if n > pe.shape[0]:  # F7 deviation: same closed form, more rows
+        pe = positional_table(n, pe.shape[1]).to(pe.device)
+    return pe[:n].to(dtype)
+
+
+# ----------------------------------------------------------------------------
+# layers/mla.py, layers/transformer.py, layers/attention.py
+# ----------------------------------------------------------------------------
+def rms_norm(x: Tensor, weight: Tensor, eps: float = 1e-6) -> Tensor:
+    """RMSNorm.forward (mla.py:53-58); normalises in >= fp32."""
+    xf = x.float() if x.dtype in (torch.float16, torch.bfloat16) else x
+    out = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)).type_as(x)
+    return out * weight
+
+
+def ada_rms_norm(x: Tensor, cond: Tensor, sd: State, prefix: str) -> Tensor:
+    """AdaLayerNorm.forward (transformer.py:64-68)."""
+    mod = F.linear(cond, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
+    scale, shift = mod.chunk(2, dim=-1)
+    x = rms_norm(x, sd[prefix + "norm.weight"])
+    return x * (1 + scale.unsqueeze(1)) + shift.unsqueeze(1)
+
+
+def band_mask(T: int, window: int, device) -> Tensor:
+    """create_local_attention_mask (attention.py:27-30): |i-j| <= window."""
+    r = torch.arange(T, device=device)
+    return ((r[None, :] - r[:, None]).abs() <= window)[None, None]
+
+
+def self_attention(x: Tensor, sd: State, prefix: str, heads: int = HEADS,
+                   window: Optional[int] = WINDOW) -> Tensor:
+    """EfficientAttention.forward (attention.py:87-123)."""
+    B, T, C = x.shape
+    d = C // heads
+    qkv = F.linear(x, sd[prefix + "qkv.weight"]).reshape(B, T, 3, heads, d).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    mask = band_mask(T, window, x.device) if window is not None else None
+    out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask)
+    out = out.transpose(1, 2).reshape(B, T, C)
+    return F.linear(out, sd[prefix + "proj.weight"], sd[prefix + "proj.bias"])
+
+
+def cross_kv(context: Tensor, sd: State, prefix: str, heads: int = HEADS) -> Tuple[Tensor, Tensor]:
+    """The step-invariant half of MultiHeadLatentAttention.forward (mla.py:144-153)."""
+    B, S, C = context.shape
+    d = C // heads
+    c_kv = rms_norm(F.linear(context, sd[prefix + "kv_down_proj.weight"]), sd[prefix + "kv_norm.weight"])
+    kv = F.linear(c_kv, sd[prefix + "kv_up_proj.weight"]).reshape(B, S, 2, heads, d).permute(2, 0, 3, 1, 4)
+    return kv[0], kv[1]
+
+
+def cross_attention(x: Tensor, context: Tensor, sd: State, prefix: str, heads: int = HEADS) -> Tensor:
+    """MultiHeadLatentAttention.forward with context given, cond=None
+    (mla.py:133-194; RoPE and mask branches are dead on this path, F3)."""
+    B, T, C = x.shape
+    d = C // heads
+    q = F.linear(x, sd[prefix + "q_proj.weight"]).reshape(B, T, heads, d).transpose(1, 2)
+    k, v = cross_kv(context, sd, prefix, heads)
+    out = F.scaled_dot_product_attention(q, k, v)
+    out = out.transpose(1, 2).reshape(B, T, C)
+    return F.linear(out, sd[prefix + "out_proj.weight"])
+
+
+def feed_forward(x: Tensor, sd: State, prefix: str) -> Tensor:
+    """FeedForward / SwiGLU (transformer.py:13-49): first half * silu(second half)."""
+    u = F.linear(x, sd[prefix + "net.0.weight"], sd[prefix + "net.0.bias"])
+    a, gate = u.chunk(2, dim=-1)
+    return F.linear(a * F.silu(gate), sd[prefix + "net.3.weight"], sd[prefix + "net.3.bias"])
+
+
+def transformer_block(x: Tensor, context: Tensor, cond: Tensor, sd: State, prefix: str,
+                      heads: int = HEADS, window: Optional[int] = WINDOW) -> Tensor:
+    """DiffusionTransformerBlock.forward with use_adaln=True (transformer.py:141-160)."""
+    x = x + self_attention(ada_rms_norm(x, cond, sd, prefix + "norm1."), sd, prefix + "attn.", heads, window)
+    x = x + cross_attention(rms_norm(x, sd[prefix + "norm2.weight"]), context, sd, prefix + "cross_attn.", heads)
+    x = x + feed_forward(ada_rms_norm(x, cond, sd, prefix + "norm3."), sd, prefix + "ffn.")
+    return x
+
+
+# ----------------------------------------------------------------------------
+# models/decoder.py
+# ----------------------------------------------------------------------------
+def time_condition(sd: State, t: Tensor, step_idx: Optional[Tensor]) -> Tensor:
+    """t_cond of EdgeDiffusionDecoder.forward (decoder.py:77-80)."""
+    w = sd["time_emb.1.weight"]
+    e = time_embedding(t, w.shape[1], w.dtype)
+    c = F.linear(F.gelu(F.linear(e, w, sd["time_emb.1.bias"])), sd["time_emb.3.weight"], sd["time_emb.3.bias"])
+    if step_idx is not None:
+        c = c + sd["step_emb.weight"][step_idx]
+    return c
+
+
+def decoder_forward(sd: State, x_t: Tensor, t: Tensor, sem_idx: Optional[Tensor] = None,
+                    step_idx: Optional[Tensor] = None, sem_features: Optional[Tensor] = None,
+                    heads: int = HEADS, window: Optional[int] = WINDOW,
+                    return_hidden: bool = False):
+    """EdgeDiffusionDecoder.forward (decoder.py:66-109)."""
+    cond = time_condition(sd, t, step_idx)
+    if sem_features is not None:
+        context = F.linear(sem_features, sd["sem_proj.weight"], sd["sem_proj.bias"])
+    elif sem_idx is not None:
+        context = sd["token_emb.weight"][sem_idx]
+    else:
+        raise ValueError("Either sem_idx or sem_features must be provided")
+    dt = context.dtype
+    context = context + _pe_rows(sd, "context_pos_emb.pe", context.shape[1], dt)
+    h = F.linear(x_t, sd["in_proj.weight"], sd["in_proj.bias"])
+    h = h + _pe_rows(sd, "pos_emb.pe", h.shape[1], dt)
+    hidden = [h]
+    n_layers = 1 + max(int(k.split(".")[1]) for k in sd if k.startswith("layers."))
+    for i in range(n_layers):
+        h = transformer_block(h, context, cond, sd, f"layers.{i}.", heads, window)
+        hidden.append(h)
+    h = F.layer_norm(h, (h.shape[-1],), sd["final_norm.weight"], sd["final_norm.bias"], 1e-5)
+    eps = F.linear(h, sd["out_proj.weight"], sd["out_proj.bias"])
+    return (eps, hidden) if return_hidden else eps
+
+
+# ----------------------------------------------------------------------------
+# models/vq.py, models/encoder.py
+# ----------------------------------------------------------------------------
+def vq_distances(codebook: Tensor, flat: Tensor) -> Tensor:
+    """vq.py:75-79; note Python precedence: ``2 * flat @ W.t()`` == ``(2*flat) @ W.t()``."""
+    return (flat.pow(2).sum(1, keepdim=True) - 2 * flat @ codebook.t()
+            + codebook.pow(2).sum(1, keepdim=True).t())
+
+
+def vq_encode(codebook: Tensor, z: Tensor) -> Tensor:
+    """VectorQuantizer.encode (vq.py:148-159): first-minimum argmin, int64."""
+    B, T, D = z.shape
+    return vq_distances(codebook, z.reshape(-1, D)).argmin(dim=1).view(B, T)
+
+
+def vq_forward(codebook: Tensor, z: Tensor):
+    """VectorQuantizer.forward in eval mode (vq.py:53-107) -> 5-tuple."""
+    B, T, D = z.shape
+    idx = vq_distances(codebook, z.reshape(-1, D)).argmin(dim=1)
+    z_q = codebook[idx].view(B, T, D)
+    vq_loss = torch.tensor(0.0, device=z.device)
+    z_q = z + (z_q - z)  # straight-through estimator rounding (vq.py:98)
+    counts = torch.bincount(idx, minlength=codebook.shape[0]).float()
+    probs = counts / counts.sum().clamp_min(1.0)
+    perplexity = torch.exp(-(probs * torch.log(probs.clamp_min(1e-12))).sum())
+    used = (counts > 0).sum()
+    return z_q, idx.view(B, T), vq_loss, perplexity, used
+
+
+def encoder_proj(sd: State, h: Tensor) -> Tensor:
+    """SemanticEncoder.proj (encoder.py:41-46): Linear, GELU, LayerNorm, Linear."""
+    z = F.gelu(F.linear(h, sd["0.weight"], sd["0.bias"]))
+    z = F.layer_norm(z, (z.shape[-1],), sd["2.weight"], sd["2.bias"], 1e-5)
+    return F.linear(z, sd["3.weight"], sd["3.bias"])
+
+
+# ----------------------------------------------------------------------------
+# layers/conv.py (operator-level only)
+# ----------------------------------------------------------------------------
+def dsconv_forward(sd: State, x: Tensor, stride: int = 1) -> Tensor:
+    """DepthwiseSeparableConv.forward (conv.py:61-64), x: [B, C_in, T]."""
+    wd = sd["depthwise.weight"]
+    k = wd.shape[-1]
+    y = F.conv1d(x, wd, None, stride=stride, padding=k // 2, groups=wd.shape[0])
+    y = F.conv1d(y, sd["pointwise.weight"], sd["pointwise.bias"])
+    groups = min(8, y.shape[1])
+    y = F.group_norm(y, groups, sd["norm.weight"], sd["norm.bias"], 1e-5)
+    return F.gelu(y)
+
+
+# ----------------------------------------------------------------------------
+# inference.py
+# ----------------------------------------------------------------------------
+def ddim_timesteps(num_steps: int, diff_steps: int = DIFF_STEPS):
+    """inference.py:35-36,41: (t, t_prev) pairs of generate_mel."""
+    stride = diff_steps // num_steps
+    ts = list(range(diff_steps - 1, 0, -stride))[:num_steps]
+    return [(t, max(t - stride, 0)) for t in ts]
+
+
+def generate_mel(sd: State, tab: State, sem_idx: Tensor, num_steps: int = 4,
+                 x_T: Optional[Tensor] = None, temperature: float = 1.0,
+                 trace: Optional[list] = None) -> Tensor:
+    """EdgeInference.generate_mel (inference.py:23-53).  ``x_T`` injects the
+    initial noise (the reference draws randn(B, 2S, n_mels) * temperature at :33).
+    ``trace`` (optional list) receives (x_t, eps, x_prev, x0) per step for
+    teacher-forced parity."""
+    B, S = sem_idx.shape
+    if x_T is None:
+        x_T = torch.randn(B, 2 * S, N_MELS) * temperature
+    x = x_T
+    x0 = None
+    with torch.no_grad():
+        for i, (t, t_prev) in enumerate(ddim_timesteps(num_steps, tab["alpha_bar"].shape[0])):
+            tt = torch.full((B,), t, dtype=torch.long)
+            si = torch.full((B,), i, dtype=torch.long)
+            tp = torch.full((B,), t_prev, dtype=torch.long)
+            eps = decoder_forward(sd, x, tt, sem_idx, si)
+            x_in = x
+            x, x0 = ddim_step(tab, x, tt, tp, eps, 0.0)
+            if trace is not None:
+                trace.append((x_in, eps, x, x0))
+    return x0
+
+
+def ddpm_loop(sd: State, tab: State, sem_idx: Tensor, x_T: Tensor, noises, t_start: Optional[int] = None,
+              t_end: int = 0) -> Tensor:
+    """Harness-driven ancestral loop for BASELINE config 4:
+    ``eps = decoder(x, t, sem_idx, step_idx=None); x = ddpm_step(x, t, eps)`` for
+    t = t_start .. t_end.  ``noises[i]`` is the pre-drawn N(0,1) tensor of step i."""
+    B = sem_idx.shape[0]
+    T = tab["alpha_bar"].shape[0]
+    t_start = T - 1 if t_start is None else t_start
+    x = x_T
+    with torch.no_grad():
+        for i, t in enumerate(range(t_start, t_end - 1, -1)):
+            tt = torch.full((B,), t, dtype=torch.long)
+            eps = decoder_forward(sd, x, tt, sem_idx, None)
+            x = ddpm_step(tab, x, tt, eps, noises[i])
+    return x
+
+
+def to_dtype(sd: State, dtype) -> State:
+    return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

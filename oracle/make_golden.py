@@ -1,0 +1,134 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference (build
+container only; needs /root/reference).  Run:  python -m oracle.make_golden
+
+Inputs and weights are regenerated from seeds (oracle/synth.py) at test time;
+the fixtures hold the reference's OUTPUTS plus checksums of the regenerated
+inputs, so they stay small.  TEST INFRASTRUCTURE ONLY.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import ref_harness as R
+from . import synth
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+ROWS = [0, 1, 63, 64, 65, 127, 128, 129, 198, 199]   # band-edge rows kept from hidden states
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(1)          # fixed summation order for the recorded outputs
+    os.makedirs(OUT, exist_ok=True)
+    ref = R.make_reference(0)
+    E, dec, sched = ref["E"], ref["decoder"], ref["schedule"]
+    sd = synth.synth_decoder_state(0)
+    meta = dict(weights=synth.state_checksum(sd), torch=torch.__version__)
+
+    # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
+    B, S = 2, 100
+    idx = synth.synth_sem_idx(11, B, S)
+    x = synth.synth_noise(11, B, 2 * S)
+    cases = {}
+    for name, t, si in (("mixed", [999, 500], [0, 3]), ("nostep", [3, 749], None), ("late", [249, 0], [15, 1])):
+        tt = torch.tensor(t)
+        ss = None if si is None else torch.tensor(si)
+        hidden = []
+        hooks = [l.register_forward_hook(lambda m, i, o: hidden.append(o[:, ROWS].clone())) for l in dec.layers]
+        with torch.no_grad():
+            eps = dec(x, tt, idx, ss)
+            cond = dec.time_emb(tt)
+            if ss is not None:
+                cond = cond + dec.step_emb(ss)
+        for h in hooks:
+            h.remove()
+        cases[name] = dict(t=tt, step_idx=ss, eps=eps, hidden_rows=torch.stack(hidden), cond=cond)
+    torch.save(dict(meta=meta, B=B, S=S, seed=11, rows=ROWS, cases=cases,
+                    idx_sum=int(idx.sum()), x_sum=float(x.double().sum())),
+               os.path.join(OUT, "decoder_step.pt"))
+
+    # --- decoder.forward with sem_features (v-path conditioning, decoder.py:83-85)
+    feats = synth.synth_features(12, 2, 40, 128)
+    xs = synth.synth_noise(12, 2, 80)
+    with torch.no_grad():
+        eps_f = dec(xs, torch.tensor([700, 20]), None, None, sem_features=feats)
+    torch.save(dict(meta=meta, seed=12, eps=eps_f), os.path.join(OUT, "decoder_semfeat.pt"))
+
+    # --- EdgeInference.generate_mel, 4-step and 1-step, with the per-step trace
+    B, S = 1, 72
+    idx = synth.synth_sem_idx(13, B, S)
+    xT = synth.synth_noise(13, B, 2 * S)
+    gm = {}
+    for steps in (4, 1, 16):
+        trace = []
+        real_ddim = sched.get_ddim_step
+
+        def spy(x_t, t, t_prev, eps, eta=0.0):
+            xp, x0 = real_ddim(x_t, t, t_prev, eps, eta)
+            trace.append(dict(x_t=x_t.clone(), t=int(t[0]), t_prev=int(t_prev[0]), eps=eps.clone(),
+                              x_prev=xp.clone(), x0=x0.clone()))
+            return xp, x0
+
+        sched.get_ddim_step = spy
+        try:
+            out = R.reference_generate_mel(ref, idx, steps, xT)
+        finally:
+            sched.get_ddim_step = real_ddim
+        if steps == 16:   # keep only the ends of the long trace
+            trace = [trace[0], trace[-1]]
+        gm[steps] = dict(x0=out, trace=trace)
+    torch.save(dict(meta=meta, B=B, S=S, seed=13, runs=gm), os.path.join(OUT, "generate_mel.pt"))
+
+    # --- DiffusionSchedule tables and the two update rules
+    tab = {k: getattr(sched, k).clone() for k in
+           ("betas", "alphas", "alpha_bar", "sqrt_alpha_bar", "sqrt_one_minus_alpha_bar", "sqrt_recip_alpha_bar",
+            "sqrt_recip_alpha_bar_minus_one", "posterior_variance", "lambda_t")}
+    xs = synth.synth_noise(14, 4, 10)
+    es = synth.synth_noise(14, 4, 10, tag="eps")
+    ns = synth.synth_noise(14, 4, 10, tag="noise")
+    t = torch.tensor([999, 749, 1, 0])
+    tp = torch.tensor([749, 499, 0, 0])
+    xp, x0 = sched.get_ddim_step(xs, t, tp, es, 0.0)
+    real = torch.randn_like
+    torch.randn_like = lambda a: ns.clone()
+    try:
+        xd = sched.ddpm_step(xs, t, es)
+    finally:
+        torch.randn_like = real
+    torch.save(dict(meta=meta, tables=tab, seed=14, t=t, t_prev=tp, ddim_x_prev=xp, ddim_x0=x0, ddpm_x_prev=xd,
+                    q_sample=sched.q_sample(xs, t, ns)[0], v_target=sched.get_v_target(xs, ns, t),
+                    x0_from_eps=sched.predict_x0_from_eps(xs, t, es), x0_from_v=sched.predict_x0_from_v(xs, t, es),
+                    eps_from_v=sched.predict_eps_from_v(xs, t, es), steps4=sched.get_schedule_for_steps(4)),
+               os.path.join(OUT, "schedule.pt"))
+
+    # --- SemanticEncoder.proj + VectorQuantizer (forward 5-tuple, encode, decode)
+    h = synth.synth_features(15, 4, 50)
+    with torch.no_grad():
+        z = ref["proj"](h)
+        z_q, vidx, vq_loss, perp, used = ref["vq"](z)
+        enc = ref["vq"].encode(z)
+        decd = ref["vq"].decode(vidx[:1, :5])
+    torch.save(dict(meta=dict(meta, vq=synth.state_checksum(synth.synth_vq_state(0)),
+                              proj=synth.state_checksum(synth.synth_proj_state(0))),
+                    seed=15, z=z, z_q=z_q, idx=vidx, vq_loss=vq_loss, perplexity=perp, used=used,
+                    encode=enc, decode=decd), os.path.join(OUT, "vq.pt"))
+
+    # --- DepthwiseSeparableConv (operator level, F2)
+    conv = {}
+    for name, (cin, cout, k, stride, B, T) in dict(default=(160, 160, 3, 1, 2, 50), odd=(80, 96, 5, 2, 3, 37),
+                                                   tiny=(4, 4, 3, 1, 1, 9)).items():
+        m = E.layers.DepthwiseSeparableConv(cin, cout, k, stride).eval()
+        m.load_state_dict(synth.synth_dsconv_state(16, cin, cout, k), strict=True)
+        xin = synth.synth_noise(16, B, cin, T, tag="conv_" + name)
+        with torch.no_grad():
+            conv[name] = dict(shape=(cin, cout, k, stride, B, T), y=m(xin))
+    torch.save(dict(meta=meta, seed=16, cases=conv), os.path.join(OUT, "dsconv.pt"))
+
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
