@@ -50,6 +50,11 @@ SIGNATURES = {
     "edtts_version": (C.c_int, []),
     "edtts_last_error": (C.c_char_p, []),
     "edtts_device_supported": (C.c_int, []),
+    "edtts_kernel_classes": (C.c_int, []),
+    "edtts_kernel_class_name": (C.c_char_p, [C.c_int]),
+    "edtts_launch_counts": (C.c_int, [_p, C.c_int]),
+    "edtts_prof_enable": (C.c_int, [C.c_int]),
+    "edtts_prof_collect": (C.c_int, [_p, _p, C.c_int]),
     "edtts_vq_argmin": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "edtts_vq_workspace_bytes": (_i64, [_i32]),
     "edtts_vq_gather_ste": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
@@ -125,6 +130,29 @@ def i64(t: torch.Tensor) -> torch.Tensor:
     if t.dtype != torch.int64:
         t = t.long()
     return t.contiguous()
+
+
+def launch_counts() -> dict:
+    """Kernel launches made through libedtts so far, by kernel class (includes launches recorded
+    into CUDA graphs at capture time, not their replays)."""
+    lib = load()
+    n = lib.edtts_kernel_classes()
+    arr = (C.c_uint64 * n)()
+    check(lib.edtts_launch_counts(arr, n), "launch_counts")
+    return {lib.edtts_kernel_class_name(i).decode(): int(arr[i]) for i in range(n)}
+
+
+def prof_enable(on: bool) -> None:
+    load().edtts_prof_enable(1 if on else 0)
+
+
+def prof_collect() -> dict:
+    """{class: (total_ms, launches)} of the eager launches since the last collect (synchronises)."""
+    lib = load()
+    n = lib.edtts_kernel_classes()
+    ms, cnt = (C.c_double * n)(), (C.c_uint64 * n)()
+    check(lib.edtts_prof_collect(ms, cnt, n), "prof_collect")
+    return {lib.edtts_kernel_class_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
 
 class Workspace:

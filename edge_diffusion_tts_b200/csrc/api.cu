@@ -2,6 +2,7 @@
 // single-kernel test hooks of the C ABI.
 #include <stdarg.h>
 #include <string.h>
+#include <vector>
 
 #define EDTTS_DECL_ONLY
 #include "common.cuh"
@@ -30,9 +31,79 @@ int check_launch(const char* what) {
   return EDTTS_OK;
 }
 
+// ---- launch counter + per-class event timing ---------------------------------
+struct ProfSlot {
+  cudaEvent_t a, b;
+  int cls;
+};
+static unsigned long long g_launches[KC_COUNT] = {0};
+static bool g_prof_on = false;
+static std::vector<ProfSlot>* g_slots = nullptr;
+
+LaunchScope::LaunchScope(int cls, cudaStream_t stream) : cls_(cls), stream_(stream), slot_(nullptr) {
+  ++g_launches[cls];
+  if (!g_prof_on) return;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return;
+  if (!g_slots) g_slots = new std::vector<ProfSlot>();
+  ProfSlot ps;
+  ps.cls = cls;
+  if (cudaEventCreate(&ps.a) != cudaSuccess || cudaEventCreate(&ps.b) != cudaSuccess) return;
+  cudaEventRecord(ps.a, stream);
+  g_slots->push_back(ps);
+  slot_ = reinterpret_cast<void*>(g_slots->size());   // index + 1
+}
+
+LaunchScope::~LaunchScope() {
+  if (slot_) cudaEventRecord((*g_slots)[reinterpret_cast<size_t>(slot_) - 1].b, stream_);
+}
+
 }  // namespace edtts
 
 using namespace edtts;
+
+extern "C" int edtts_kernel_classes(void) { return KC_COUNT; }
+
+extern "C" const char* edtts_kernel_class_name(int cls) {
+  static const char* names[KC_COUNT] = {"gemm_simt_fp32", "attn_window_simt_fp32", "attn_cross_simt_fp32", "cond",
+                                        "embed_ctx", "vq", "schedule", "dsconv", "tc_gemm_bf16",
+                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc"};
+  return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
+}
+
+extern "C" int edtts_launch_counts(uint64_t* counts_out, int n) {
+  EDTTS_REQUIRE(counts_out && n >= KC_COUNT, EDTTS_EINVAL, "launch_counts: need room for %d classes", KC_COUNT);
+  for (int i = 0; i < KC_COUNT; ++i) counts_out[i] = g_launches[i];
+  return EDTTS_OK;
+}
+
+extern "C" int edtts_prof_enable(int on) {
+  g_prof_on = on != 0;
+  return EDTTS_OK;
+}
+
+// Synchronises the device (host-side measurement helper, never called on the sampling path),
+// accumulates per-class elapsed ms and launch counts of the recorded launches, then clears them.
+extern "C" int edtts_prof_collect(double* ms_out, uint64_t* n_out, int n) {
+  EDTTS_REQUIRE(ms_out && n_out && n >= KC_COUNT, EDTTS_EINVAL, "prof_collect: need room for %d classes", KC_COUNT);
+  for (int i = 0; i < KC_COUNT; ++i) {
+    ms_out[i] = 0.0;
+    n_out[i] = 0;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return check_launch("prof_collect sync");
+  if (!g_slots) return EDTTS_OK;
+  for (auto& ps : *g_slots) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ps.a, ps.b) == cudaSuccess) {
+      ms_out[ps.cls] += ms;
+      n_out[ps.cls] += 1;
+    }
+    cudaEventDestroy(ps.a);
+    cudaEventDestroy(ps.b);
+  }
+  g_slots->clear();
+  return EDTTS_OK;
+}
 
 extern "C" int edtts_version(void) { return 100; }
 extern "C" const char* edtts_last_error(void) { return g_err; }

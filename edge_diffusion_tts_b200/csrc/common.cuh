@@ -34,6 +34,23 @@ int check_launch(const char* what);          // cudaPeekAtLastError -> EDTTS_ECU
     }                                   \
   } while (0)
 
+// Kernel classes for the launch counter and the optional per-class event timing
+// (edtts_prof_*): bench.py uses them to time the dominant kernel live.
+enum KernelClass : int {
+  KC_GEMM_SIMT = 0, KC_ATTN_WINDOW_SIMT, KC_ATTN_CROSS_SIMT, KC_COND, KC_EMBED, KC_VQ, KC_SCHEDULE, KC_DSCONV,
+  KC_TC_GEMM, KC_TC_ATTN_WINDOW, KC_TC_ATTN_CROSS, KC_TC_MISC, KC_COUNT
+};
+
+// RAII around one kernel launch: counts it and, when profiling is on and the stream is
+// not capturing, brackets it with CUDA events on the launching stream.
+struct LaunchScope {
+  LaunchScope(int cls, cudaStream_t stream);
+  ~LaunchScope();
+  int cls_;
+  cudaStream_t stream_;
+  void* slot_;
+};
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -14,6 +14,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
   EDTTS_REQUIRE(g.pro == PRO_NONE || g.K <= 192, EDTTS_EINVAL, "gemm: norm prologue needs K <= 192 (K=%d)", g.K);
   const unsigned gx = (unsigned)((g.rows + G_BM - 1) / G_BM);
   const bool dual = g.epi == EPI_SWIGLU;
+  LaunchScope ls(KC_GEMM_SIMT, stream);
   if (g.N % 80 == 0) {
     dim3 grid(gx, g.N / 80);
     if (dual) gemm_simt_kernel<5, true><<<grid, G_THREADS, 0, stream>>>(g);
@@ -30,6 +31,7 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t stream) {
 
 int launch_attn_simt(const AttnArgs& a, int B, cudaStream_t stream) {
   dim3 grid((a.Tq + AT_Q - 1) / AT_Q, NH, B);
+  LaunchScope ls(a.window >= 0 ? KC_ATTN_WINDOW_SIMT : KC_ATTN_CROSS_SIMT, stream);
   attn_simt_kernel<<<grid, AT_Q, 0, stream>>>(a);
   return check_launch("attn_simt");
 }
@@ -105,6 +107,7 @@ using namespace edtts;
 extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t* t, const int64_t* step_idx,
                                   float* cond_out, float* mod_out, int32_t B, void* stream) {
   EDTTS_REQUIRE(w && t && B > 0 && (cond_out || mod_out), EDTTS_EINVAL, "cond_prepare: null argument");
+  LaunchScope ls(KC_COND, as_stream(stream));
   cond_kernel<<<B, 256, 0, as_stream(stream)>>>(*w, t, step_idx, cond_out, mod_out);
   return check_launch("cond_kernel");
 }
@@ -130,6 +133,7 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
   float* craw = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256));
   if (sem_idx) {
     const int64_t n4 = rows * (H / 4);
+    LaunchScope ls(KC_EMBED, st);
     embed_ctx_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(w->token_emb, w->ctx_pe, sem_idx, ctx, rows, S,
                                                                    w->codebook_size);
     int rc = check_launch("embed_ctx");

@@ -141,16 +141,25 @@ extern "C" int edtts_dsconv_forward(const float* x, const float* dw_w, const flo
       cudaFuncSetAttribute(dsconv_mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return check_launch("dsconv smem attribute");
   dim3 grid((t_out + DC_TT - 1) / DC_TT, B);
-  dsconv_mix_kernel<<<grid, DC_THREADS, smem, st>>>(x, dw_w, pw_w, pw_b, y_out, c_in, c_out, T, t_out, kernel_size,
-                                                    stride);
-  int rc = check_launch("dsconv_mix");
+  int rc;
+  {
+    LaunchScope ls(KC_DSCONV, st);
+    dsconv_mix_kernel<<<grid, DC_THREADS, smem, st>>>(x, dw_w, pw_w, pw_b, y_out, c_in, c_out, T, t_out, kernel_size,
+                                                      stride);
+    rc = check_launch("dsconv_mix");
+  }
   if (rc) return rc;
   const int cpg = c_out / groups;
   float* stats = reinterpret_cast<float*>(workspace);
-  dsconv_stats_kernel<<<B * groups, 256, 0, st>>>(y_out, stats, (int64_t)cpg * t_out, 1e-5f);
-  if ((rc = check_launch("dsconv_stats"))) return rc;
+  {
+    LaunchScope ls(KC_DSCONV, st);
+    dsconv_stats_kernel<<<B * groups, 256, 0, st>>>(y_out, stats, (int64_t)cpg * t_out, 1e-5f);
+    rc = check_launch("dsconv_stats");
+  }
+  if (rc) return rc;
   const int64_t total = (int64_t)B * c_out * t_out;
   const int64_t blocks = (total + 255) / 256;
+  LaunchScope ls(KC_DSCONV, st);
   dsconv_norm_gelu_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, st>>>(y_out, stats, gn_w, gn_b,
                                                                                           total, c_out, t_out, cpg);
   return check_launch("dsconv_norm_gelu");

@@ -90,6 +90,7 @@ extern "C" int edtts_ddim_step(const float* x_t, const float* eps, const float* 
   const int64_t total = (int64_t)B * n;
   const bool vec = n % 4 == 0 && aligned16(x_t) && aligned16(eps) && (!noise || aligned16(noise)) &&
                    (!x_prev_out || aligned16(x_prev_out)) && (!x0_out || aligned16(x0_out));
+  LaunchScope ls(KC_SCHEDULE, as_stream(stream));
   if (vec)
     ddim_kernel<4><<<stream_grid(total / 4), 256, 0, as_stream(stream)>>>(x_t, eps, eta == 0.f ? nullptr : noise,
                                                                           alpha_bar, t, t_prev, eta, x_prev_out, x0_out,
@@ -108,6 +109,7 @@ extern "C" int edtts_ddpm_step(const float* x_t, const float* eps, const float* 
                 EDTTS_EINVAL, "ddpm_step: null argument");
   const int64_t total = (int64_t)B * n;
   const bool vec = n % 4 == 0 && aligned16(x_t) && aligned16(eps) && aligned16(noise) && aligned16(x_prev_out);
+  LaunchScope ls(KC_SCHEDULE, as_stream(stream));
   if (vec)
     ddpm_kernel<4><<<stream_grid(total / 4), 256, 0, as_stream(stream)>>>(x_t, eps, noise, alphas, alpha_bar, betas,
                                                                           posterior_var, t, x_prev_out, total, n);

@@ -219,9 +219,14 @@ extern "C" int edtts_vq_argmin(const float* z, const float* codebook, int64_t* i
   if (rows == 0) return EDTTS_OK;
   cudaStream_t st = as_stream(stream);
   float* ee = reinterpret_cast<float*>(workspace);
-  vq_code_norms_kernel<<<(codebook_size * 32 + 255) / 256, 256, 0, st>>>(codebook, ee, codebook_size, dim);
-  int rc = check_launch("vq_code_norms");
+  int rc;
+  {
+    LaunchScope ls(KC_VQ, st);
+    vq_code_norms_kernel<<<(codebook_size * 32 + 255) / 256, 256, 0, st>>>(codebook, ee, codebook_size, dim);
+    rc = check_launch("vq_code_norms");
+  }
   if (rc) return rc;
+  LaunchScope ls(KC_VQ, st);
   vq_argmin_kernel<<<(unsigned)((rows + VQ_BM - 1) / VQ_BM), VQ_THREADS, 0, st>>>(z, codebook, ee, idx_out, rows, dim,
                                                                                  codebook_size);
   return check_launch("vq_argmin");
@@ -232,6 +237,7 @@ extern "C" int edtts_vq_gather_ste(const float* z, const float* codebook, const 
   EDTTS_REQUIRE(z && codebook && idx && zq_out, EDTTS_EINVAL, "vq_gather_ste: null argument");
   if (rows == 0) return EDTTS_OK;
   const int64_t n = rows * dim;
+  LaunchScope ls(KC_VQ, as_stream(stream));
   vq_gather_ste_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(z, codebook, idx, zq_out, rows, dim,
                                                                                   codebook_size);
   return check_launch("vq_gather_ste");
@@ -245,6 +251,7 @@ extern "C" int edtts_vq_bincount(const int64_t* idx, int32_t* counts_out, int64_
   if (cudaMemsetAsync(counts_out, 0, (size_t)codebook_size * 4, st) != cudaSuccess) return check_launch("memset");
   if (rows == 0) return EDTTS_OK;
   const int blocks = (int)((rows + 256 * 8 - 1) / (256 * 8));
+  LaunchScope ls(KC_VQ, st);
   vq_bincount_kernel<<<blocks < 1 ? 1 : (blocks > 1184 ? 1184 : blocks), 256, (size_t)codebook_size * 4, st>>>(
       idx, counts_out, rows, codebook_size);
   return check_launch("vq_bincount");

@@ -117,6 +117,16 @@ const char* edtts_last_error(void);
 /* 1 if the device `stream` belongs to can run the kernels (sm_100), else 0. */
 int edtts_device_supported(void);
 
+/* --- measurement helpers (bench.py; never on the sampling path) ------------- */
+/* Kernels are grouped in classes; every launch made through this library is counted. */
+int edtts_kernel_classes(void);
+const char* edtts_kernel_class_name(int cls);
+int edtts_launch_counts(uint64_t* counts_out, int n);
+/* When enabled, every launch outside stream capture is bracketed by CUDA events on its
+ * stream; edtts_prof_collect synchronises, returns per-class elapsed ms / launches, clears. */
+int edtts_prof_enable(int on);
+int edtts_prof_collect(double* ms_out, uint64_t* n_out, int n);
+
 /* --- VectorQuantizer (models/vq.py) --------------------------------------- */
 /* vq.py:75-82 / :153-159: idx[r] = argmin_k ||z_r - E_k||^2, first minimum.
  * fp32 FFMA distances; near-ties are re-ranked in fp64 so the result equals the
