@@ -138,7 +138,8 @@ extern "C" int edtts_encoder_proj(const float* h, const float* w0, const float* 
 extern "C" int edtts_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K,
                                  int32_t N, int32_t precision, void* stream) {
   EDTTS_REQUIRE(x && w && y && rows > 0, EDTTS_EINVAL, "test_linear: null argument");
-  if (precision == EDTTS_PREC_BF16) return tc_test_linear(x, w, bias, y, rows, K, N, as_stream(stream));
+  if (precision >= EDTTS_PREC_BF16)   // 1: fp32-A prologue path, 2: chunk-major A, 3: chunk-major out (see tc_path.cu)
+    return tc_test_linear(x, w, bias, y, rows, K, N, precision, as_stream(stream));
   GemmArgs g;
   g.A = x; g.rows = rows; g.K = K; g.lda = K; g.W = w; g.N = N; g.bias = bias; g.out = y; g.ldo = N;
   return launch_gemm_simt(g, as_stream(stream));
@@ -148,7 +149,8 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
                                     int32_t kv_stride, float* o, int32_t B, int32_t Tq, int32_t Tk, int32_t window,
                                     int32_t precision, void* stream) {
   EDTTS_REQUIRE(q && k && v && o && B > 0 && Tq > 0 && Tk > 0, EDTTS_EINVAL, "test_attention: null argument");
-  EDTTS_REQUIRE(precision == EDTTS_PREC_FP32, EDTTS_ENOTSUP, "test_attention: only fp32 is exposed");
+  if (precision == EDTTS_PREC_BF16)
+    return tc_test_attention(q, q_stride, k, v, kv_stride, o, B, Tq, Tk, window, as_stream(stream));
   AttnArgs a{q, q_stride, k, v, kv_stride, o, H, Tq, Tk, window, 1.0f / sqrtf((float)HD)};
   return launch_attn_simt(a, B, as_stream(stream));
 }

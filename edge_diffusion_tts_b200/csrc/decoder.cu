@@ -114,7 +114,7 @@ extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t*
 
 extern "C" int64_t edtts_context_workspace_bytes(int32_t B, int32_t S) {
   const int64_t rows = (int64_t)B * S;
-  return align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256);
+  return align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) + align_up(rows * 2 * H * 4, 256);
 }
 
 extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64_t* sem_idx, const float* sem_features,
@@ -126,11 +126,14 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
   EDTTS_REQUIRE(S <= w->ctx_rows, EDTTS_EINVAL, "context_prepare: S=%d exceeds the %d-row context PE table", S,
                 w->ctx_rows);
   EDTTS_REQUIRE(workspace_bytes >= edtts_context_workspace_bytes(B, S), EDTTS_ENOSPC, "context_prepare: workspace");
-  (void)precision;   // step-invariant and <4% of the FLOPs: always the fp32 kernels
+  // step-invariant and <4% of the FLOPs: always computed by the fp32 kernels; for the bf16 path the
+  // result is then stored as the bf16 chunk-major operand image the tcgen05 cross-attention fetches
   cudaStream_t st = as_stream(stream);
   const int64_t rows = (int64_t)B * S;
   float* ctx = reinterpret_cast<float*>(workspace);
   float* craw = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256));
+  float* kvtmp = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256) +
+                                          align_up(rows * RANK * 4, 256));
   if (sem_idx) {
     const int64_t n4 = rows * (H / 4);
     LaunchScope ls(KC_EMBED, st);
@@ -154,10 +157,14 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     if (rc) return rc;
     GemmArgs u;   // kv_norm + kv_up_proj (mla.py:147-153)
     u.A = craw; u.rows = rows; u.K = RANK; u.lda = RANK; u.W = L.kv_up_w; u.N = 2 * H;
-    u.out = kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
+    u.out = precision == EDTTS_PREC_BF16 ? kvtmp : kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
     u.pro = PRO_RMS; u.norm_w = L.kv_norm_w; u.norm_eps = 1e-6f;
     rc = launch_gemm_simt(u, st);
     if (rc) return rc;
+    if (precision == EDTTS_PREC_BF16) {
+      rc = tc::pack_activation(kvtmp, 2 * H, reinterpret_cast<uint16_t*>(kv_out) + (int64_t)l * rows * 2 * H, rows, 2 * H, st);
+      if (rc) return rc;
+    }
   }
   return EDTTS_OK;
 }

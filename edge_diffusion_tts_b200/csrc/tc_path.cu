@@ -1,19 +1,392 @@
-// placeholder until the tcgen05 path lands
+// bf16 tensor-core path (EDTTS_PREC_BF16): weight packing, kernel launchers and the
+// decoder step built from the tcgen05 kernels in tc_gemm.cuh / tc_attention.cuh.
 #include "tc_path.cuh"
+#include "tc_gemm.cuh"
+#include "tc_attention.cuh"
+
 namespace edtts {
-int64_t tc_decoder_workspace_bytes(int32_t, int32_t, int32_t) { return 0; }
-int tc_decoder_step(const edtts_decoder_weights*, const float*, const float*, const float*, const edtts_step_args*,
-                    void*, int32_t, int32_t, int32_t, cudaStream_t) {
-  set_error("bf16 tensor-core path not built");
+namespace tc {
+
+// ---- packed weight image --------------------------------------------------------------
+// Every matrix is stored per column block y as the UMMA operand image [K/8][N_CTA][8] bf16,
+// so a CTA fetches its slab with one bulk copy.  ffn.net.0 is row-permuted so that block y
+// holds the 80 "x" rows and the 80 matching "gate" rows of SwiGLU output columns 80y..80y+79.
+struct LayerOff {
+  int64_t qkv, attn_proj, q_proj, cross_out, ffn0, ffn0_bias, ffn3;
+};
+struct PackedOff {
+  int64_t in_proj, out_proj;
+  LayerOff layer[NL];
+  int64_t total;
+};
+
+static PackedOff packed_offsets() {
+  PackedOff p;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) {
+    const int64_t at = o;
+    o += align_up(bytes, 128);
+    return at;
+  };
+  p.in_proj = take((int64_t)H * M * 2);
+  p.out_proj = take((int64_t)M * H * 2);
+  for (int l = 0; l < NL; ++l) {
+    p.layer[l].qkv = take((int64_t)3 * H * H * 2);
+    p.layer[l].attn_proj = take((int64_t)H * H * 2);
+    p.layer[l].q_proj = take((int64_t)H * H * 2);
+    p.layer[l].cross_out = take((int64_t)H * H * 2);
+    p.layer[l].ffn0 = take((int64_t)2 * FFN * H * 2);
+    p.layer[l].ffn0_bias = take((int64_t)2 * FFN * 4);
+    p.layer[l].ffn3 = take((int64_t)H * FFN * 2);
+  }
+  p.total = o;
+  return p;
+}
+
+__device__ __forceinline__ int swiglu_row(int p, int n_cta, int ffn) {
+  const int y = p / n_cta, n = p % n_cta, nu = n_cta / 2;
+  return n < nu ? y * nu + n : ffn + y * nu + (n - nu);
+}
+
+// src fp32 [N_total][K] (nn.Linear weight) -> dst bf16 [N_total/N_CTA][K/8][N_CTA][8]
+__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int n_total, int K,
+                                   int n_cta, int swiglu_ffn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_total * K) return;
+  const int j = i & 7;
+  const int n = (i >> 3) % n_cta;
+  const int c = (i >> 3) / n_cta % (K / 8);
+  const int y = (i >> 3) / n_cta / (K / 8);
+  const int p = y * n_cta + n;
+  const int row = swiglu_ffn ? swiglu_row(p, n_cta, swiglu_ffn) : p;
+  dst[i] = __float2bfloat16_rn(src[(int64_t)row * K + c * 8 + j]);
+}
+__global__ void pack_bias_swiglu_kernel(const float* __restrict__ src, float* __restrict__ dst, int n_total, int n_cta,
+                                        int ffn) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_total) dst[p] = src[swiglu_row(p, n_cta, ffn)];
+}
+// test helpers: fp32 row-major [R][K] <-> bf16 chunk-major [K/8][R][8]
+__global__ void pack_act_kernel(const float* __restrict__ src, int lda, __nv_bfloat16* __restrict__ dst, int64_t R,
+                                int K) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * K) return;
+  const int j = (int)(i & 7);
+  const int64_t r = (i >> 3) % R;
+  const int c = (int)((i >> 3) / R);
+  dst[i] = __float2bfloat16_rn(src[r * lda + c * 8 + j]);
+}
+__global__ void unpack_act_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t R, int N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * N) return;
+  const int j = (int)(i & 7);
+  const int64_t r = (i >> 3) % R;
+  const int c = (int)((i >> 3) / R);
+  dst[r * N + c * 8 + j] = __bfloat162float(src[i]);
+}
+
+static int pack_weight(const float* src, void* dst, int n_total, int K, int n_cta, int swiglu_ffn, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  const int n = n_total * K;
+  pack_weight_kernel<<<(n + 255) / 256, 256, 0, st>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n_total, K, n_cta,
+                                                      swiglu_ffn);
+  return check_launch("pack_weight");
+}
+
+// ---- GEMM launcher -----------------------------------------------------------------------
+template <int K, int N_CTA>
+static int launch_tc_gemm_t(const TcGemmArgs& g, int ny, cudaStream_t st) {
+  using L = TcGemmSmem<K, N_CTA>;
+  static bool configured = false;
+  static int ctas_per_sm = 1;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc_gemm_kernel<K, N_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
+        cudaSuccess)
+      return check_launch("tc_gemm smem attribute");
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_gemm_kernel<K, N_CTA>, TC_THREADS, L::TOTAL);
+    ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);   // TMEM: 2 x 256 columns
+    configured = true;
+  }
+  const int64_t ntiles = (g.R + TILE_M - 1) / TILE_M;
+  int sms = 148;
+  int64_t nx = ((int64_t)sms * ctas_per_sm + ny - 1) / ny;
+  if (nx > ntiles) nx = ntiles;
+  if (nx < 1) nx = 1;
+  LaunchScope ls(KC_TC_GEMM, st);
+  tc_gemm_kernel<K, N_CTA><<<dim3((unsigned)nx, ny), TC_THREADS, L::TOTAL, st>>>(g);
+  return check_launch("tc_gemm");
+}
+
+int launch_tc_gemm(const TcGemmArgs& g, int K, int n_cta, int ny, cudaStream_t st) {
+  if (K == 80 && n_cta == 160) return launch_tc_gemm_t<80, 160>(g, ny, st);
+  if (K == 160 && n_cta == 160) return launch_tc_gemm_t<160, 160>(g, ny, st);
+  if (K == 320 && n_cta == 160) return launch_tc_gemm_t<320, 160>(g, ny, st);
+  if (K == 160 && n_cta == 80) return launch_tc_gemm_t<160, 80>(g, ny, st);
+  set_error("tc_gemm: no kernel for K=%d N_CTA=%d", K, n_cta);
   return EDTTS_ENOTSUP;
 }
-int tc_test_linear(const float*, const float*, const float*, float*, int64_t, int32_t, int32_t, cudaStream_t) {
-  set_error("bf16 tensor-core path not built");
-  return EDTTS_ENOTSUP;
+
+int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  const int64_t n = R * K;
+  pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, lda, reinterpret_cast<__nv_bfloat16*>(dst_chunk), R, K);
+  return check_launch("pack_activation");
 }
+
+template <bool WINDOW>
+static int launch_tc_attn(const TcAttnArgs& a, int B, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc_attn_kernel<WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) !=
+        cudaSuccess)
+      return check_launch("tc_attn smem attribute");
+    configured = true;
+  }
+  LaunchScope ls(WINDOW ? KC_TC_ATTN_WINDOW : KC_TC_ATTN_CROSS, st);
+  tc_attn_kernel<WINDOW><<<dim3((a.Tq + AT_M - 1) / AT_M, NH, B), 128, AttnSmem::TOTAL, st>>>(a);
+  return check_launch(WINDOW ? "tc_attn_window" : "tc_attn_cross");
+}
+
+static const float kScaleLog2e = 1.4426950408889634f / sqrtf((float)HD);
+
+int launch_tc_attn_window(const __nv_bfloat16* qkv, __nv_bfloat16* o, int B, int T, cudaStream_t st) {
+  TcAttnArgs a;
+  a.q = qkv; a.q_rows = (int64_t)B * T; a.kv = qkv; a.kv_rows = (int64_t)B * T;
+  a.q_chunk0 = 0; a.k_chunk0 = 20; a.v_chunk0 = 40; a.o = o; a.Tq = T; a.Tk = T; a.scale_log2e = kScaleLog2e;
+  return launch_tc_attn<true>(a, B, st);
+}
+
+int launch_tc_attn_cross(const __nv_bfloat16* q, const void* kv_chunk, __nv_bfloat16* o, int B, int T, int S,
+                         cudaStream_t st) {
+  TcAttnArgs a;
+  a.q = q; a.q_rows = (int64_t)B * T; a.kv = reinterpret_cast<const __nv_bfloat16*>(kv_chunk); a.kv_rows = (int64_t)B * S;
+  a.q_chunk0 = 0; a.k_chunk0 = 0; a.v_chunk0 = 20; a.o = o; a.Tq = T; a.Tk = S; a.scale_log2e = kScaleLog2e;
+  return launch_tc_attn<false>(a, B, st);
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// ---- workspace ------------------------------------------------------------------------------
+struct TcWs {
+  int64_t h, qkv, q, o, u, total;
+};
+static TcWs tc_ws_layout(int64_t R) {
+  TcWs w;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) {
+    const int64_t at = o;
+    o += align_up(bytes, 256);
+    return at;
+  };
+  w.h = take(R * H * 4);
+  take(ATT_PAD_BYTES);                 // finite (zeroed) slack below qkv for the band halo of row 0
+  w.qkv = take(R * 3 * H * 2);
+  take(ATT_PAD_BYTES);                 // and above the last row
+  w.q = take(R * H * 2);
+  w.o = take(R * H * 2);
+  w.u = take(R * FFN * 2);
+  w.total = o;
+  return w;
+}
+
+int64_t tc_decoder_workspace_bytes(int32_t B, int32_t T, int32_t S) {
+  (void)S;
+  return tc_ws_layout((int64_t)B * T).total;
+}
+
+int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                    const edtts_step_args* args, void* workspace, int32_t B, int32_t T, int32_t S, cudaStream_t st) {
+  EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "decoder_step(bf16): weights.packed_bf16 is null; call "
+                                              "edtts_pack_weights_bf16 first");
+  const PackedOff po = packed_offsets();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
+  auto img = [&](int64_t off) { return reinterpret_cast<const __nv_bfloat16*>(pk + off); };
+  const int64_t R = (int64_t)B * T;
+  const TcWs wl = tc_ws_layout(R);
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* h = reinterpret_cast<float*>(ws + wl.h);
+  __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + wl.qkv);
+  __nv_bfloat16* qx = reinterpret_cast<__nv_bfloat16*>(ws + wl.q);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(ws + wl.o);
+  __nv_bfloat16* u = reinterpret_cast<__nv_bfloat16*>(ws + wl.u);
+  int rc;
+  // the halo slack must hold finite numbers (masked keys still enter P.V as 0 * v)
+  if (cudaMemsetAsync(ws + wl.qkv - ATT_PAD_BYTES, 0, ATT_PAD_BYTES, st) != cudaSuccess ||
+      cudaMemsetAsync(ws + wl.qkv + align_up(R * 3 * H * 2, 256), 0, ATT_PAD_BYTES, st) != cudaSuccess)
+    return check_launch("tc workspace memset");
+  {  // h = in_proj(x_t) + pe[:T]
+    TcGemmArgs g;
+    g.amode = A_F32; g.A_f32 = x_t; g.lda = M; g.R = R; g.T = T; g.W_img = img(po.in_proj); g.bias = w->in_proj_b;
+    g.epi = TE_PE; g.out_f32 = h; g.ldo = H; g.pe = w->pos_pe;
+    if ((rc = launch_tc_gemm(g, M, H, 1, st))) return rc;
+  }
+  for (int l = 0; l < NL; ++l) {
+    const edtts_layer_weights& L = w->layers[l];
+    const LayerOff& lo = po.layer[l];
+    {  // q,k,v = attn.qkv(norm1(h, cond)) -> bf16 chunk-major [60][R][8]
+      TcGemmArgs g;
+      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.qkv);
+      g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H; g.mod_stride = 2 * NL * 2 * H;
+      g.epi = TE_CHUNK; g.out_chunk = qkv;
+      if ((rc = launch_tc_gemm(g, H, H, 3, st))) return rc;
+    }
+    if ((rc = launch_tc_attn_window(qkv, o, B, T, st))) return rc;
+    {  // h += attn.proj(o) + bias
+      TcGemmArgs g;
+      g.amode = A_CHUNK; g.A_chunk = o; g.R = R; g.T = T; g.W_img = img(lo.attn_proj); g.bias = L.attn_proj_b;
+      g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
+      if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
+    }
+    {  // q = q_proj(norm2(h)) -> bf16 chunk-major [20][R][8]
+      TcGemmArgs g;
+      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.q_proj);
+      g.pro = PRO_RMS; g.norm_w = L.norm2_w; g.epi = TE_CHUNK; g.out_chunk = qx;
+      if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
+    }
+    // bf16 path: kv is the chunk-major bf16 image written by edtts_context_prepare(precision=BF16)
+    if ((rc = launch_tc_attn_cross(qx, reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H, o, B, T,
+                                   S, st)))
+      return rc;
+    {  // h += out_proj(o)
+      TcGemmArgs g;
+      g.amode = A_CHUNK; g.A_chunk = o; g.R = R; g.T = T; g.W_img = img(lo.cross_out);
+      g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
+      if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
+    }
+    {  // u = swiglu(ffn.net.0(norm3(h, cond))) -> bf16 chunk-major [40][R][8]
+      TcGemmArgs g;
+      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.ffn0);
+      g.bias = reinterpret_cast<const float*>(pk + lo.ffn0_bias);
+      g.pro = PRO_ADARMS; g.norm_w = L.norm3_norm_w; g.mod = mod + (int64_t)(2 * l + 1) * 2 * H;
+      g.mod_stride = 2 * NL * 2 * H; g.epi = TE_SWIGLU; g.out_chunk = u;
+      if ((rc = launch_tc_gemm(g, H, H, 4, st))) return rc;
+    }
+    {  // h += ffn.net.3(u) + bias
+      TcGemmArgs g;
+      g.amode = A_CHUNK; g.A_chunk = u; g.R = R; g.T = T; g.W_img = img(lo.ffn3); g.bias = L.ffn3_b;
+      g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
+      if ((rc = launch_tc_gemm(g, FFN, H, 1, st))) return rc;
+    }
+  }
+  {  // eps = out_proj(final_norm(h)) with the DDIM/DDPM update fused
+    TcGemmArgs g;
+    g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(po.out_proj); g.bias = w->out_proj_b;
+    g.pro = PRO_LN; g.norm_w = w->final_norm_w; g.norm_b = w->final_norm_b; g.norm_eps = 1e-5f;
+    g.epi = TE_STEP; g.ldo = M; g.x_t = x_t; g.step = *args;
+    if ((rc = launch_tc_gemm(g, H, M, 1, st))) return rc;
+  }
+  return EDTTS_OK;
+}
+
+// ---- single-kernel test hook ---------------------------------------------------------------
+// mode 1: fp32 A (prologue path), fp32 out; mode 2: bf16 chunk-major A (bulk-copy path), fp32 out;
+// mode 3: fp32 A, bf16 chunk-major out (TE_CHUNK) unpacked back to fp32.  Allocates temporaries
+// (test hook only -- never used on the sampling path).
+int tc_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K, int32_t N,
+                   int mode, cudaStream_t st) {
+  EDTTS_REQUIRE((K == 80 || K == 160 || K == 320) && N % 160 == 0 || (K == 160 && N == 80), EDTTS_ENOTSUP,
+                "tc_test_linear: K=%d N=%d has no tcgen05 kernel", K, N);
+  const int n_cta = (N == 80) ? 80 : 160, ny = N / n_cta;
+  __nv_bfloat16 *wimg = nullptr, *achunk = nullptr, *ochunk = nullptr;
+  if (cudaMalloc(&wimg, (size_t)N * K * 2) != cudaSuccess) return check_launch("cudaMalloc");
+  int rc = pack_weight(w, wimg, N, K, n_cta, 0, st);
+  TcGemmArgs g;
+  g.R = rows; g.T = (int)rows; g.W_img = wimg; g.bias = bias; g.out_f32 = y; g.ldo = N; g.epi = TE_F32;
+  g.amode = A_F32; g.A_f32 = x; g.lda = K;
+  if (!rc && mode == 2) {
+    if (cudaMalloc(&achunk, (size_t)rows * K * 2) != cudaSuccess) rc = check_launch("cudaMalloc");
+    if (!rc) {
+      const int64_t n = rows * K;
+      pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, K, achunk, rows, K);
+      rc = check_launch("pack_act");
+      g.amode = A_CHUNK; g.A_chunk = achunk;
+    }
+  }
+  if (!rc && mode == 3) {
+    if (cudaMalloc(&ochunk, (size_t)rows * N * 2) != cudaSuccess) rc = check_launch("cudaMalloc");
+    g.epi = TE_CHUNK; g.out_chunk = ochunk;
+  }
+  if (!rc) rc = launch_tc_gemm(g, K, n_cta, ny, st);
+  if (!rc && mode == 3) {
+    const int64_t n = rows * N;
+    unpack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ochunk, y, rows, N);
+    rc = check_launch("unpack_act");
+  }
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) {
+    set_error("tc_test_linear: %s", cudaGetErrorString(e));
+    rc = EDTTS_ECUDA;
+  }
+  cudaFree(wimg);
+  cudaFree(achunk);
+  cudaFree(ochunk);
+  return rc;
+}
+
+// fp32 row-major q [B*Tq][q_stride], k / v [B*Tk][kv_stride] -> o [B*Tq][160], through the tcgen05 kernels.
+int tc_test_attention(const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* o, int B,
+                      int Tq, int Tk, int window, cudaStream_t st) {
+  const int64_t Rq = (int64_t)B * Tq, Rk = (int64_t)B * Tk;
+  EDTTS_REQUIRE(window < 0 || (window == WIN && Tq == Tk), EDTTS_ENOTSUP, "tc_test_attention: window must be %d", WIN);
+  uint8_t* buf = nullptr;
+  const size_t q_bytes = (size_t)Rq * H * 2, kv_bytes = (size_t)Rk * 2 * H * 2, o_bytes = (size_t)Rq * H * 2;
+  const size_t total = ATT_PAD_BYTES + q_bytes + kv_bytes + ATT_PAD_BYTES + o_bytes;
+  if (cudaMalloc(&buf, total) != cudaSuccess) return check_launch("cudaMalloc");
+  cudaMemsetAsync(buf, 0, total, st);
+  __nv_bfloat16* qc = reinterpret_cast<__nv_bfloat16*>(buf + ATT_PAD_BYTES);
+  __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(buf + ATT_PAD_BYTES + q_bytes);
+  __nv_bfloat16* vc = kc + Rk * H;
+  __nv_bfloat16* oc = reinterpret_cast<__nv_bfloat16*>(buf + ATT_PAD_BYTES + q_bytes + kv_bytes + ATT_PAD_BYTES);
+  int rc = pack_activation(q, q_stride, qc, Rq, H, st);
+  if (!rc) rc = pack_activation(k, kv_stride, kc, Rk, H, st);
+  if (!rc) rc = pack_activation(v, kv_stride, vc, Rk, H, st);
+  if (!rc) rc = window >= 0 ? launch_tc_attn_window(qc, oc, B, Tq, st) : launch_tc_attn_cross(qc, kc, oc, B, Tq, Tk, st);
+  if (!rc) {
+    const int64_t n = Rq * H;
+    unpack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(oc, o, Rq, H);
+    rc = check_launch("unpack_act");
+  }
+  const cudaError_t e = cudaStreamSynchronize(st);
+  if (!rc && e != cudaSuccess) {
+    set_error("tc_test_attention: %s", cudaGetErrorString(e));
+    rc = EDTTS_ECUDA;
+  }
+  cudaFree(buf);
+  return rc;
+}
+
 }  // namespace edtts
-extern "C" int64_t edtts_packed_bf16_bytes(void) { return 0; }
-extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights*, void*, void*) {
-  edtts::set_error("bf16 tensor-core path not built");
-  return EDTTS_ENOTSUP;
+
+using namespace edtts;
+
+extern "C" int64_t edtts_packed_bf16_bytes(void) { return tc::packed_offsets().total; }
+
+extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* packed_out, void* stream) {
+  EDTTS_REQUIRE(w && packed_out, EDTTS_EINVAL, "pack_weights_bf16: null argument");
+  const tc::PackedOff po = tc::packed_offsets();
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed_out);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  if ((rc = tc::pack_weight(w->in_proj_w, pk + po.in_proj, H, M, H, 0, st))) return rc;
+  if ((rc = tc::pack_weight(w->out_proj_w, pk + po.out_proj, M, H, M, 0, st))) return rc;
+  for (int l = 0; l < NL; ++l) {
+    const edtts_layer_weights& L = w->layers[l];
+    const tc::LayerOff& lo = po.layer[l];
+    if ((rc = tc::pack_weight(L.attn_qkv_w, pk + lo.qkv, 3 * H, H, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.attn_proj_w, pk + lo.attn_proj, H, H, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.q_proj_w, pk + lo.q_proj, H, H, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.cross_out_w, pk + lo.cross_out, H, H, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.ffn0_w, pk + lo.ffn0, 2 * FFN, H, H, FFN, st))) return rc;
+    {
+      LaunchScope ls(KC_TC_MISC, st);
+      tc::pack_bias_swiglu_kernel<<<(2 * FFN + 255) / 256, 256, 0, st>>>(
+          L.ffn0_b, reinterpret_cast<float*>(pk + lo.ffn0_bias), 2 * FFN, H, FFN);
+      if ((rc = check_launch("pack_bias"))) return rc;
+    }
+    if ((rc = tc::pack_weight(L.ffn3_w, pk + lo.ffn3, H, FFN, H, 0, st))) return rc;
+  }
+  return EDTTS_OK;
 }

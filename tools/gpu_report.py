@@ -40,7 +40,10 @@ def stats(tag, a, b):
 
 
 def linear(prec):
-    for rows, K, N in ((300, 160, 480), (129, 80, 160), (1000, 320, 160), (77, 768, 128), (5, 160, 80), (4096, 160, 640)):
+    shapes = ((300, 160, 480), (129, 80, 160), (1000, 320, 160), (77, 768, 128), (5, 160, 80), (4096, 160, 640))
+    if prec >= 1:
+        shapes = ((128, 160, 160), (300, 160, 480), (129, 80, 160), (1000, 320, 160), (5, 160, 80), (40000, 160, 640))
+    for rows, K, N in shapes:
         g = torch.Generator().manual_seed(rows)
         x, w, b = torch.randn(rows, K, generator=g), torch.randn(N, K, generator=g) * K ** -0.5, torch.randn(N, generator=g)
         y = torch.zeros(rows, N, device=DEV)
@@ -54,15 +57,15 @@ def linear(prec):
         stats(f"linear p{prec} {rows}x{K}x{N}", y, torch.nn.functional.linear(x.double(), w.double(), b.double()))
 
 
-def attention():
-    for B, Tq, Tk, window in ((2, 200, 200, 64), (1, 333, 333, 64), (2, 150, 75, -1), (1, 800, 400, -1)):
+def attention(prec=0):
+    for B, Tq, Tk, window in ((2, 200, 200, 64), (1, 333, 333, 64), (2, 150, 75, -1), (1, 800, 400, -1), (3, 800, 800, 64)):
         g = torch.Generator().manual_seed(Tq + Tk)
         q = torch.randn(B, Tq, 160, generator=g)
         kv = torch.randn(B, Tk, 320, generator=g)
         o = torch.zeros(B, Tq, 160, device=DEV)
         qd, kvd = q.to(DEV), kv.to(DEV)
         rc = lib.edtts_test_attention(qd.data_ptr(), 160, kvd.data_ptr(), kvd.data_ptr() + 640, 320, o.data_ptr(), B, Tq,
-                                      Tk, window, 0, _lib.stream_ptr(DEV))
+                                      Tk, window, prec, _lib.stream_ptr(DEV))
         if rc:
             print("   rc", rc, lib.edtts_last_error())
             continue
@@ -71,7 +74,8 @@ def attention():
         vh = kv[..., 160:].reshape(B, Tk, 4, 40).transpose(1, 2).double()
         mask = O.band_mask(Tq, window, "cpu") if window >= 0 else None
         ref = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask).transpose(1, 2).reshape(B, Tq, 160)
-        stats(f"attention B{B} Tq{Tq} Tk{Tk} w{window}", o, ref)
+        torch.cuda.synchronize()
+        stats(f"attention p{prec} B{B} Tq{Tq} Tk{Tk} w{window}", o, ref)
 
 
 def make_model(prec="fp32"):
@@ -147,12 +151,17 @@ def vq():
               f"oracle32 vs 64 {(r32 != r64).sum().item()}")
 
 
-section("linear fp32", lambda: linear(0))
-section("attention fp32", attention)
-section("decoder fp32", decoder)
-section("generate fp32", generate)
-section("vq", vq)
+if "--skip-fp32" not in sys.argv:
+    section("linear fp32", lambda: linear(0))
+    section("attention fp32", attention)
+    section("decoder fp32", decoder)
+    section("generate fp32", generate)
+    section("vq", vq)
+if "--bf16-kernels" in sys.argv:
+    section("linear bf16 (fp32 A)", lambda: linear(1))
+    section("linear bf16 (chunk A)", lambda: linear(2))
+    section("linear bf16 (chunk out)", lambda: linear(3))
+    section("attention bf16", lambda: attention(1))
 if "--bf16" in sys.argv:
-    section("linear bf16", lambda: linear(1))
     section("decoder bf16", lambda: decoder("bf16"))
     section("generate bf16", lambda: generate("bf16"))
