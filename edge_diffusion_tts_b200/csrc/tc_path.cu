@@ -97,31 +97,32 @@ static int pack_weight(const float* src, void* dst, int n_total, int K, int n_ct
 template <int K, int N_CTA>
 static int launch_tc_gemm_t(const TcGemmArgs& g, int ny, cudaStream_t st) {
   using L = TcGemmSmem<K, N_CTA>;
+  EDTTS_REQUIRE(!(g.amode == A_F32 && g.epi == TE_RESID), EDTTS_EINVAL, "tc_gemm: fp32 input with residual epilogue");
   static bool configured = false;
-  static int ctas_per_sm = 1;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_gemm_kernel<K, N_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL) !=
-        cudaSuccess)
+    const int max_smem = L::OFF_IO + (L::IN_BYTES > L::OUT_BYTES ? L::IN_BYTES : L::OUT_BYTES) + 64;
+    if (cudaFuncSetAttribute(tc_gemm_kernel<K, N_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             max_smem > 232448 ? 232448 : max_smem) != cudaSuccess)
       return check_launch("tc_gemm smem attribute");
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc_gemm_kernel<K, N_CTA>, TC_THREADS, L::TOTAL);
-    ctas_per_sm = occ < 1 ? 1 : (occ > 2 ? 2 : occ);   // TMEM: 2 x 256 columns
     configured = true;
   }
+  const int smem = L::total(g.amode, g.epi);
+  EDTTS_REQUIRE(smem <= 232448, EDTTS_ENOTSUP, "tc_gemm<%d,%d>: %d B of shared memory", K, N_CTA, smem);
   const int64_t ntiles = (g.R + TILE_M - 1) / TILE_M;
-  int sms = 148;
-  int64_t nx = ((int64_t)sms * ctas_per_sm + ny - 1) / ny;
+  int64_t nx = 148 / ny;                       // persistent: one CTA per SM
   if (nx > ntiles) nx = ntiles;
   if (nx < 1) nx = 1;
   LaunchScope ls(KC_TC_GEMM, st);
-  tc_gemm_kernel<K, N_CTA><<<dim3((unsigned)nx, ny), TC_THREADS, L::TOTAL, st>>>(g);
+  tc_gemm_kernel<K, N_CTA><<<dim3((unsigned)nx, ny), TC_THREADS, smem, st>>>(g, smem - L::OFF_IO - 64);
   return check_launch("tc_gemm");
 }
 
 int launch_tc_gemm(const TcGemmArgs& g, int K, int n_cta, int ny, cudaStream_t st) {
   if (K == 80 && n_cta == 160) return launch_tc_gemm_t<80, 160>(g, ny, st);
+  if (K == 160 && n_cta == 240) return launch_tc_gemm_t<160, 240>(g, ny, st);
   if (K == 160 && n_cta == 160) return launch_tc_gemm_t<160, 160>(g, ny, st);
-  if (K == 320 && n_cta == 160) return launch_tc_gemm_t<320, 160>(g, ny, st);
+  if (K == 160 && n_cta == 320) return launch_tc_gemm_t<160, 320>(g, ny, st);
+  if (K == 320 && n_cta == 80) return launch_tc_gemm_t<320, 80>(g, ny, st);
   if (K == 160 && n_cta == 80) return launch_tc_gemm_t<160, 80>(g, ny, st);
   set_error("tc_gemm: no kernel for K=%d N_CTA=%d", K, n_cta);
   return EDTTS_ENOTSUP;
@@ -141,6 +142,7 @@ static int launch_tc_attn(const TcAttnArgs& a, int B, cudaStream_t st) {
     if (cudaFuncSetAttribute(tc_attn_kernel<WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) !=
         cudaSuccess)
       return check_launch("tc_attn smem attribute");
+    cudaFuncSetAttribute(tc_attn_kernel<WINDOW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     configured = true;
   }
   LaunchScope ls(WINDOW ? KC_TC_ATTN_WINDOW : KC_TC_ATTN_CROSS, st);
@@ -219,7 +221,7 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     return check_launch("tc workspace memset");
   {  // h = in_proj(x_t) + pe[:T]
     TcGemmArgs g;
-    g.amode = A_F32; g.A_f32 = x_t; g.lda = M; g.R = R; g.T = T; g.W_img = img(po.in_proj); g.bias = w->in_proj_b;
+    g.amode = A_F32; g.A_f32 = x_t; g.R = R; g.T = T; g.W_img = img(po.in_proj); g.bias = w->in_proj_b;
     g.epi = TE_PE; g.out_f32 = h; g.ldo = H; g.pe = w->pos_pe;
     if ((rc = launch_tc_gemm(g, M, H, 1, st))) return rc;
   }
@@ -228,10 +230,10 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     const LayerOff& lo = po.layer[l];
     {  // q,k,v = attn.qkv(norm1(h, cond)) -> bf16 chunk-major [60][R][8]
       TcGemmArgs g;
-      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.qkv);
+      g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.qkv);
       g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H; g.mod_stride = 2 * NL * 2 * H;
       g.epi = TE_CHUNK; g.out_chunk = qkv;
-      if ((rc = launch_tc_gemm(g, H, H, 3, st))) return rc;
+      if ((rc = launch_tc_gemm(g, H, 240, 2, st))) return rc;
     }
     if ((rc = launch_tc_attn_window(qkv, o, B, T, st))) return rc;
     {  // h += attn.proj(o) + bias
@@ -242,7 +244,7 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     }
     {  // q = q_proj(norm2(h)) -> bf16 chunk-major [20][R][8]
       TcGemmArgs g;
-      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.q_proj);
+      g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.q_proj);
       g.pro = PRO_RMS; g.norm_w = L.norm2_w; g.epi = TE_CHUNK; g.out_chunk = qx;
       if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
     }
@@ -258,22 +260,22 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     }
     {  // u = swiglu(ffn.net.0(norm3(h, cond))) -> bf16 chunk-major [40][R][8]
       TcGemmArgs g;
-      g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(lo.ffn0);
+      g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.ffn0);
       g.bias = reinterpret_cast<const float*>(pk + lo.ffn0_bias);
       g.pro = PRO_ADARMS; g.norm_w = L.norm3_norm_w; g.mod = mod + (int64_t)(2 * l + 1) * 2 * H;
       g.mod_stride = 2 * NL * 2 * H; g.epi = TE_SWIGLU; g.out_chunk = u;
-      if ((rc = launch_tc_gemm(g, H, H, 4, st))) return rc;
+      if ((rc = launch_tc_gemm(g, H, 2 * H, 2, st))) return rc;
     }
     {  // h += ffn.net.3(u) + bias
       TcGemmArgs g;
       g.amode = A_CHUNK; g.A_chunk = u; g.R = R; g.T = T; g.W_img = img(lo.ffn3); g.bias = L.ffn3_b;
       g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
-      if ((rc = launch_tc_gemm(g, FFN, H, 1, st))) return rc;
+      if ((rc = launch_tc_gemm(g, FFN, M, 2, st))) return rc;
     }
   }
   {  // eps = out_proj(final_norm(h)) with the DDIM/DDPM update fused
     TcGemmArgs g;
-    g.amode = A_F32; g.A_f32 = h; g.lda = H; g.R = R; g.T = T; g.W_img = img(po.out_proj); g.bias = w->out_proj_b;
+    g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(po.out_proj); g.bias = w->out_proj_b;
     g.pro = PRO_LN; g.norm_w = w->final_norm_w; g.norm_b = w->final_norm_b; g.norm_eps = 1e-5f;
     g.epi = TE_STEP; g.ldo = M; g.x_t = x_t; g.step = *args;
     if ((rc = launch_tc_gemm(g, H, M, 1, st))) return rc;
@@ -287,15 +289,18 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
 // (test hook only -- never used on the sampling path).
 int tc_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K, int32_t N,
                    int mode, cudaStream_t st) {
-  EDTTS_REQUIRE((K == 80 || K == 160 || K == 320) && N % 160 == 0 || (K == 160 && N == 80), EDTTS_ENOTSUP,
-                "tc_test_linear: K=%d N=%d has no tcgen05 kernel", K, N);
-  const int n_cta = (N == 80) ? 80 : 160, ny = N / n_cta;
+  int n_cta = 0;
+  if (K == 80 && N == 160) n_cta = 160;
+  if (K == 160) n_cta = (N == 80) ? 80 : (N == 160) ? 160 : (N == 480) ? 240 : (N == 640) ? 320 : 0;
+  if (K == 320 && N == 160) n_cta = 80;
+  EDTTS_REQUIRE(n_cta > 0, EDTTS_ENOTSUP, "tc_test_linear: K=%d N=%d has no tcgen05 kernel", K, N);
+  const int ny = N / n_cta;
   __nv_bfloat16 *wimg = nullptr, *achunk = nullptr, *ochunk = nullptr;
   if (cudaMalloc(&wimg, (size_t)N * K * 2) != cudaSuccess) return check_launch("cudaMalloc");
   int rc = pack_weight(w, wimg, N, K, n_cta, 0, st);
   TcGemmArgs g;
   g.R = rows; g.T = (int)rows; g.W_img = wimg; g.bias = bias; g.out_f32 = y; g.ldo = N; g.epi = TE_F32;
-  g.amode = A_F32; g.A_f32 = x; g.lda = K;
+  g.amode = A_F32; g.A_f32 = x;
   if (!rc && mode == 2) {
     if (cudaMalloc(&achunk, (size_t)rows * K * 2) != cudaSuccess) rc = check_launch("cudaMalloc");
     if (!rc) {
@@ -375,18 +380,18 @@ extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* pac
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     const tc::LayerOff& lo = po.layer[l];
-    if ((rc = tc::pack_weight(L.attn_qkv_w, pk + lo.qkv, 3 * H, H, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.attn_qkv_w, pk + lo.qkv, 3 * H, H, 240, 0, st))) return rc;
     if ((rc = tc::pack_weight(L.attn_proj_w, pk + lo.attn_proj, H, H, H, 0, st))) return rc;
     if ((rc = tc::pack_weight(L.q_proj_w, pk + lo.q_proj, H, H, H, 0, st))) return rc;
     if ((rc = tc::pack_weight(L.cross_out_w, pk + lo.cross_out, H, H, H, 0, st))) return rc;
-    if ((rc = tc::pack_weight(L.ffn0_w, pk + lo.ffn0, 2 * FFN, H, H, FFN, st))) return rc;
+    if ((rc = tc::pack_weight(L.ffn0_w, pk + lo.ffn0, 2 * FFN, H, 2 * H, FFN, st))) return rc;
     {
       LaunchScope ls(KC_TC_MISC, st);
       tc::pack_bias_swiglu_kernel<<<(2 * FFN + 255) / 256, 256, 0, st>>>(
-          L.ffn0_b, reinterpret_cast<float*>(pk + lo.ffn0_bias), 2 * FFN, H, FFN);
+          L.ffn0_b, reinterpret_cast<float*>(pk + lo.ffn0_bias), 2 * FFN, 2 * H, FFN);
       if ((rc = check_launch("pack_bias"))) return rc;
     }
-    if ((rc = tc::pack_weight(L.ffn3_w, pk + lo.ffn3, H, FFN, H, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.ffn3_w, pk + lo.ffn3, H, FFN, M, 0, st))) return rc;
   }
   return EDTTS_OK;
 }
