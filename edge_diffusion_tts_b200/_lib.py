@@ -74,6 +74,8 @@ SIGNATURES = {
     "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "edtts_test_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "edtts_test_attention": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "edtts_test_hidden": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32,
+                                    _i32, _p]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -67,7 +67,7 @@ extern "C" int edtts_kernel_classes(void) { return KC_COUNT; }
 extern "C" const char* edtts_kernel_class_name(int cls) {
   static const char* names[KC_COUNT] = {"gemm_simt_fp32", "attn_window_simt_fp32", "attn_cross_simt_fp32", "cond",
                                         "embed_ctx", "vq", "schedule", "dsconv", "tc_gemm_bf16",
-                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc"};
+                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc", "tc_layer_bf16"};
   return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
 }
 
@@ -153,4 +153,14 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
     return tc_test_attention(q, q_stride, k, v, kv_stride, o, B, Tq, Tk, window, as_stream(stream));
   AttnArgs a{q, q_stride, k, v, kv_stride, o, H, Tq, Tk, window, 1.0f / sqrtf((float)HD)};
   return launch_attn_simt(a, B, as_stream(stream));
+}
+
+extern "C" int edtts_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                                 float* h_out, void* workspace, int64_t workspace_bytes, int32_t B, int32_t T, int32_t S,
+                                 int32_t n_layers, int32_t stop_phase, int32_t fused, void* stream) {
+  EDTTS_REQUIRE(w && x_t && mod && kv && h_out && workspace && B > 0 && T > 0 && S > 0, EDTTS_EINVAL,
+                "test_hidden: null argument");
+  EDTTS_REQUIRE(workspace_bytes >= edtts_decoder_workspace_bytes(B, T, S, EDTTS_PREC_BF16), EDTTS_ENOSPC,
+                "test_hidden: workspace too small");
+  return tc_test_hidden(w, x_t, mod, kv, h_out, workspace, B, T, S, n_layers, stop_phase, fused, as_stream(stream));
 }

@@ -3,6 +3,7 @@
 #include "tc_path.cuh"
 #include "tc_gemm.cuh"
 #include "tc_attention.cuh"
+#include <stdlib.h>
 
 namespace edtts {
 namespace tc {
@@ -199,8 +200,17 @@ int64_t tc_decoder_workspace_bytes(int32_t B, int32_t T, int32_t S) {
   return tc_ws_layout((int64_t)B * T).total;
 }
 
-int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
-                    const edtts_step_args* args, void* workspace, int32_t B, int32_t T, int32_t S, cudaStream_t st) {
+static bool env_flag(const char* name, bool dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  return v[0] != '0';
+}
+
+// in_proj, then `n_layers` transformer blocks; fused = the whole block after the QKV GEMM is one launch
+// (tc_layer.cuh), otherwise 7 launches.  stop_phase != 0 stops the LAST block early (test hook, fused only).
+static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                         void* workspace, int32_t B, int32_t T, int32_t S, int n_layers, int stop_phase, bool fused,
+                         cudaStream_t st) {
   EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "decoder_step(bf16): weights.packed_bf16 is null; call "
                                               "edtts_pack_weights_bf16 first");
   const PackedOff po = packed_offsets();
@@ -225,15 +235,22 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     g.epi = TE_PE; g.out_f32 = h; g.ldo = H; g.pe = w->pos_pe;
     if ((rc = launch_tc_gemm(g, M, H, 1, st))) return rc;
   }
-  for (int l = 0; l < NL; ++l) {
+  for (int l = 0; l < n_layers; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     const LayerOff& lo = po.layer[l];
+    const __nv_bfloat16* kvl = reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H;
     {  // q,k,v = attn.qkv(norm1(h, cond)) -> bf16 chunk-major [60][R][8]
       TcGemmArgs g;
       g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.qkv);
       g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H; g.mod_stride = 2 * NL * 2 * H;
       g.epi = TE_CHUNK; g.out_chunk = qkv;
       if ((rc = launch_tc_gemm(g, H, 240, 2, st))) return rc;
+    }
+    if (fused) {
+      if ((rc = launch_tc_layer(pk + po.total, l, h, qkv, kvl, mod + (int64_t)(2 * l + 1) * 2 * H, 2 * NL * 2 * H, B, T, S,
+                                l == n_layers - 1 ? stop_phase : 0, st)))
+        return rc;
+      continue;
     }
     if ((rc = launch_tc_attn_window(qkv, o, B, T, st))) return rc;
     {  // h += attn.proj(o) + bias
@@ -242,6 +259,7 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
       if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
     }
+    if (l == n_layers - 1 && stop_phase == 1) break;
     {  // q = q_proj(norm2(h)) -> bf16 chunk-major [20][R][8]
       TcGemmArgs g;
       g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.q_proj);
@@ -249,15 +267,14 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
     }
     // bf16 path: kv is the chunk-major bf16 image written by edtts_context_prepare(precision=BF16)
-    if ((rc = launch_tc_attn_cross(qx, reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H, o, B, T,
-                                   S, st)))
-      return rc;
+    if ((rc = launch_tc_attn_cross(qx, kvl, o, B, T, S, st))) return rc;
     {  // h += out_proj(o)
       TcGemmArgs g;
       g.amode = A_CHUNK; g.A_chunk = o; g.R = R; g.T = T; g.W_img = img(lo.cross_out);
       g.epi = TE_RESID; g.out_f32 = h; g.ldo = H;
       if ((rc = launch_tc_gemm(g, H, H, 1, st))) return rc;
     }
+    if (l == n_layers - 1 && stop_phase == 2) break;
     {  // u = swiglu(ffn.net.0(norm3(h, cond))) -> bf16 chunk-major [40][R][8]
       TcGemmArgs g;
       g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.ffn0);
@@ -273,13 +290,39 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       if ((rc = launch_tc_gemm(g, FFN, M, 2, st))) return rc;
     }
   }
+  return EDTTS_OK;
+}
+
+int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                    const edtts_step_args* args, void* workspace, int32_t B, int32_t T, int32_t S, cudaStream_t st) {
+  static const bool fused = env_flag("EDTTS_FUSED_LAYER", true);
+  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, NL, 0, fused, st);
+  if (rc) return rc;
+  const PackedOff po = packed_offsets();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
+  const int64_t R = (int64_t)B * T;
+  float* h = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + tc_ws_layout(R).h);
   {  // eps = out_proj(final_norm(h)) with the DDIM/DDPM update fused
     TcGemmArgs g;
-    g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(po.out_proj); g.bias = w->out_proj_b;
+    g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = reinterpret_cast<const __nv_bfloat16*>(pk + po.out_proj);
+    g.bias = w->out_proj_b;
     g.pro = PRO_LN; g.norm_w = w->final_norm_w; g.norm_b = w->final_norm_b; g.norm_eps = 1e-5f;
     g.epi = TE_STEP; g.ldo = M; g.x_t = x_t; g.step = *args;
     if ((rc = launch_tc_gemm(g, H, M, 1, st))) return rc;
   }
+  return EDTTS_OK;
+}
+
+int tc_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, float* h_out,
+                   void* workspace, int32_t B, int32_t T, int32_t S, int n_layers, int stop_phase, int fused,
+                   cudaStream_t st) {
+  EDTTS_REQUIRE(n_layers >= 0 && n_layers <= NL && stop_phase >= 0 && stop_phase <= 2, EDTTS_EINVAL,
+                "test_hidden: n_layers=%d stop_phase=%d", n_layers, stop_phase);
+  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, n_layers, stop_phase, fused != 0, st);
+  if (rc) return rc;
+  const int64_t R = (int64_t)B * T;
+  const float* h = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(workspace) + tc_ws_layout(R).h);
+  if (cudaMemcpyAsync(h_out, h, R * H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return check_launch("test_hidden copy");
   return EDTTS_OK;
 }
 
@@ -367,7 +410,7 @@ int tc_test_attention(const float* q, int q_stride, const float* k, const float*
 
 using namespace edtts;
 
-extern "C" int64_t edtts_packed_bf16_bytes(void) { return tc::packed_offsets().total; }
+extern "C" int64_t edtts_packed_bf16_bytes(void) { return tc::packed_offsets().total + tc::tc_layer_packed_bytes(); }
 
 extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* packed_out, void* stream) {
   EDTTS_REQUIRE(w && packed_out, EDTTS_EINVAL, "pack_weights_bf16: null argument");
@@ -393,5 +436,6 @@ extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* pac
     }
     if ((rc = tc::pack_weight(L.ffn3_w, pk + lo.ffn3, H, FFN, M, 0, st))) return rc;
   }
-  return EDTTS_OK;
+  // images of the fused transformer-block kernel follow the per-GEMM images
+  return tc::tc_layer_pack(w, pk + po.total, st);
 }

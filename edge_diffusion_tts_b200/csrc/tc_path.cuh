@@ -11,7 +11,16 @@ int tc_test_linear(const float* x, const float* w, const float* bias, float* y, 
                    int mode, cudaStream_t stream);
 int tc_test_attention(const float* q, int q_stride, const float* k, const float* v, int kv_stride, float* o, int B,
                       int Tq, int Tk, int window, cudaStream_t stream);
+// hidden state after `n_layers` blocks (the last one optionally stopped after phase `stop_phase`), test hook
+int tc_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, float* h_out,
+                   void* workspace, int32_t B, int32_t T, int32_t S, int n_layers, int stop_phase, int fused,
+                   cudaStream_t stream);
 namespace tc {
+int64_t tc_layer_packed_bytes();
+int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st);
+// one fused DiffusionTransformerBlock (tc_layer.cuh); layer_img_base = image written by tc_layer_pack
+int launch_tc_layer(const void* layer_img_base, int layer, float* h, const void* qkv, const void* kvx, const float* mod3,
+                    int mod_stride, int B, int T, int S, int stop_phase, cudaStream_t st);
 // fp32 row-major [R][lda] (first K columns) -> bf16 chunk-major [K/8][R][8]
 int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, cudaStream_t st);
 }

@@ -221,6 +221,14 @@ int edtts_test_attention(const float* q, int32_t q_stride, const float* k, const
                          float* o, int32_t B, int32_t Tq, int32_t Tk, int32_t window, int32_t precision,
                          void* stream);
 
+/* Residual stream h [B*T,160] of the bf16 path after in_proj and `n_layers` transformer blocks, the last block
+ * optionally stopped early: stop_phase 1 = after x + attn(norm1(x)) (transformer.py:146), 2 = after the
+ * cross-attention residual (:151), 0 = whole block (:158).  fused = 1 runs each block as the single fused
+ * kernel, 0 as separate GEMM / attention launches.  mod, kv, workspace as for edtts_decoder_step (bf16). */
+int edtts_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
+                      float* h_out, void* workspace, int64_t workspace_bytes, int32_t B, int32_t T, int32_t S,
+                      int32_t n_layers, int32_t stop_phase, int32_t fused, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,48 @@ def vq():
               f"oracle32 vs 64 {(r32 != r64).sum().item()}")
 
 
+def hidden(shapes=((2, 100), (1, 37), (3, 400))):
+    """Residual stream after partial / whole transformer blocks: fused kernel and separate launches vs the oracle."""
+    import torch.nn.functional as F
+    cfg, sd, dec, sched, inf = make_model("bf16")
+    for B, S in shapes:
+        T = 2 * S
+        idx = synth.synth_sem_idx(S, B, S)
+        x = synth.synth_noise(S, B, T)
+        t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(S))
+        si = torch.randint(0, 16, (B,), generator=torch.Generator().manual_seed(S + 1))
+        cond = O.time_condition(sd, t, si)
+        ctx = sd["token_emb.weight"][idx] + O._pe_rows(sd, "context_pos_emb.pe", S, torch.float32)
+        h0 = F.linear(x, sd["in_proj.weight"], sd["in_proj.bias"]) + O._pe_rows(sd, "pos_emb.pe", T, torch.float32)
+        refs = {}
+        h = h0
+        for l in range(4):
+            pre = f"layers.{l}."
+            h1 = h + O.self_attention(O.ada_rms_norm(h, cond, sd, pre + "norm1."), sd, pre + "attn.")
+            h2 = h1 + O.cross_attention(O.rms_norm(h1, sd[pre + "norm2.weight"]), ctx, sd, pre + "cross_attn.")
+            h3 = h2 + O.feed_forward(O.ada_rms_norm(h2, cond, sd, pre + "norm3."), sd, pre + "ffn.")
+            refs[(l + 1, 1)], refs[(l + 1, 2)], refs[(l + 1, 0)] = h1, h2, h3
+            h = h3
+        xd = x.to(DEV)
+        mod = dec.prepare_cond(t.to(DEV), si.to(DEV), T, S)
+        kv = dec.prepare_context(idx.to(DEV), None, T)
+        w = dec._weights(T, S)
+        nbytes = lib.edtts_decoder_workspace_bytes(B, T, S, _lib.PREC_BF16)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+        out = torch.zeros(B, T, 160, device=DEV)
+        cases = [(1, 1), (1, 2), (1, 0), (4, 0)]
+        for fused in (0, 1):
+            for nl, stop in cases:
+                out.zero_()
+                rc = lib.edtts_test_hidden(w, xd.data_ptr(), mod.data_ptr(), kv.data_ptr(), out.data_ptr(), ws.data_ptr(),
+                                           nbytes, B, T, S, nl, stop, fused, _lib.stream_ptr(DEV))
+                if rc:
+                    print("   rc", rc, lib.edtts_last_error())
+                    continue
+                torch.cuda.synchronize()
+                stats(f"hidden B{B} S{S} layers={nl} stop={stop} fused={fused}", out, refs[(nl, stop)])
+
+
 if "--skip-fp32" not in sys.argv:
     section("linear fp32", lambda: linear(0))
     section("attention fp32", attention)
@@ -165,3 +207,5 @@ if "--bf16-kernels" in sys.argv:
 if "--bf16" in sys.argv:
     section("decoder bf16", lambda: decoder("bf16"))
     section("generate bf16", lambda: generate("bf16"))
+if "--hidden" in sys.argv:
+    section("hidden bf16 (fused vs separate)", hidden)
