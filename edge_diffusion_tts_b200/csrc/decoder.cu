@@ -162,7 +162,8 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     rc = launch_gemm_simt(u, st);
     if (rc) return rc;
     if (precision == EDTTS_PREC_BF16) {
-      rc = tc::pack_activation(kvtmp, 2 * H, reinterpret_cast<uint16_t*>(kv_out) + (int64_t)l * rows * 2 * H, rows, 2 * H, st);
+      rc = tc::pack_activation(kvtmp, 2 * H, reinterpret_cast<uint16_t*>(kv_out) + (int64_t)l * rows * 2 * H, rows, 2 * H,
+                                 /*v (columns 160..319) as f16:*/ H, st);
       if (rc) return rc;
     }
   }

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(128) tc_attn_kernel(const TcAttnArgs a) {
           lsum += p;
           s[j] = p;
         }
-        p0 = pack_bf16x8(s);
-        p1 = pack_bf16x8(s + 8);
+        p0 = pack_f16x8(s);                  // P and V are f16 operands
+        p1 = pack_f16x8(s + 8);
       }
       *reinterpret_cast<uint4*>(sP + (c0 >> 3) * (AT_M * 16) + tid * 16) = p0;
       *reinterpret_cast<uint4*>(sP + ((c0 >> 3) + 1) * (AT_M * 16) + tid * 16) = p1;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) tc_attn_kernel(const TcAttnArgs a) {
     if (tid == 0) {
       mbar_wait(bar_v, ph_v);
       tc_fence_after();
-      constexpr uint32_t IDESC_O = make_idesc(AT_M, 48, /*b_mn_major=*/true);
+      constexpr uint32_t IDESC_O = make_idesc_f16(AT_M, 48, /*b_mn_major=*/true);
       const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
 #pragma unroll
       for (int ks = 0; ks < AT_KB / 16; ++ks)

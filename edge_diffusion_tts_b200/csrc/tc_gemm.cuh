@@ -38,6 +38,7 @@ struct TcGemmArgs {
   int epi = TE_F32;
   float* out_f32 = nullptr;  int ldo = 0;            // TE_RESID / TE_PE / TE_F32 (row-major fp32)
   __nv_bfloat16* out_chunk = nullptr;                // TE_CHUNK / TE_SWIGLU: [cols/8][R][8] bf16
+  int f16_from_chunk = 1 << 30;                      // TE_CHUNK: chunks >= this are written as f16 (attention V operand)
   const float* pe = nullptr;                         // TE_PE: [T][ldo]
   const float* x_t = nullptr;  edtts_step_args step{};   // TE_STEP
 };
@@ -241,8 +242,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_gemm_kernel(const TcGemmArgs
         }
         if (row < g.R) {
           __nv_bfloat16* o = g.out_chunk + ((int64_t)((n0 + c0) >> 3) * g.R + row) * 8;
-          *reinterpret_cast<uint4*>(o) = pack_bf16x8(v);
-          *reinterpret_cast<uint4*>(o + g.R * 8) = pack_bf16x8(v + 8);
+          const bool f16 = ((n0 + c0) >> 3) >= g.f16_from_chunk;
+          *reinterpret_cast<uint4*>(o) = f16 ? pack_f16x8(v) : pack_bf16x8(v);
+          *reinterpret_cast<uint4*>(o + g.R * 8) = f16 ? pack_f16x8(v + 8) : pack_bf16x8(v + 8);
         }
       }
     } else if (g.epi == TE_SWIGLU) {

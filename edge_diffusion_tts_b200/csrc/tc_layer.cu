@@ -1,6 +1,7 @@
 // Fused transformer-block kernel of the bf16 tensor-core path: weight image packing and launcher.
 #include "tc_path.cuh"
 #include "tc_layer.cuh"
+#include <stdlib.h>
 
 namespace edtts {
 namespace tc {
@@ -84,9 +85,26 @@ int launch_tc_layer(const void* layer_img_base, int layer, float* h, const void*
   a.tiles_per_utt = (T + 127) / 128;
   a.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
   a.stop_phase = stop_phase;
+  a.phase_clocks = nullptr;
+  static long long* clk_buf = nullptr;
+  static const bool want_clocks = getenv("EDTTS_LAYER_CLOCKS") != nullptr;
+  if (want_clocks) {
+    if (!clk_buf) cudaMalloc(&clk_buf, 148 * 24 * sizeof(long long));
+    a.phase_clocks = clk_buf;
+  }
   const int ntiles = B * a.tiles_per_utt;
   LaunchScope ls(KC_TC_LAYER, st);
   tc_layer_kernel<<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
+  if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
+    long long hc[24];
+    cudaMemcpy(hc, clk_buf, sizeof(hc), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc_layer clocks] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3+store %lld\n",
+            hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7]);
+    for (int k = 1; k < 3; ++k)
+      fprintf(stderr, "[tc_layer %s] other %lld waitS+load %lld max %lld exp+store %lld arriveP %lld - %lld head %lld waitO %lld\n",
+              k == 1 ? "window" : "cross ", hc[8 * k], hc[8 * k + 1], hc[8 * k + 2], hc[8 * k + 3], hc[8 * k + 4], hc[8 * k + 5],
+              hc[8 * k + 6], hc[8 * k + 7]);
+  }
   return check_launch("tc_layer");
 }
 

@@ -8,36 +8,50 @@
 //   h (128 x 160 fp32) lives in TENSOR MEMORY for the whole layer: every output projection is a
 //   tcgen05.mma that ACCUMULATES into the h columns, so the three residual adds cost nothing.
 //
-//   window attention (attention.py:94-111)   4 heads, two at a time (one per warpgroup):
-//        S = Q_h K_h^T (128 x 128 keys) -> softmax (thread <-> frame, out of TMEM) -> P (bf16, smem)
-//        -> O_h += P V_h ; two key blocks cover the band t0-64 .. t0+191, online softmax
+//   window attention (attention.py:94-111)   4 heads, two in flight (one per compute warpgroup)
 //   h += O Wproj^T                            tcgen05.mma into h
 //   n2 = RMSNorm(h + b_proj) w2               row pass, TMEM -> regs -> bf16 A operand (smem)
 //   q  = n2 Wq^T                              tcgen05.mma into scratch columns, -> bf16 Q operand
-//   cross attention (mla.py:176-180)          same kernel body, keys = the S context tokens
+//   cross attention (mla.py:176-180)          same machinery, keys = the S context tokens
 //   h += O Wout^T
 //   n3 = AdaRMSNorm(h)                        row pass
 //   u  = swiglu(n3 W0^T + b0)                 two halves of 160 u-columns, each 128 x 320 in TMEM
 //   h += u W3^T (+ b3)                        tcgen05.mma into h, then h -> HBM
 //
-// 256 threads = 2 warpgroups.  In the attention phases each warpgroup owns two heads and its
-// own K/V/P buffers, TMEM columns and mbarriers, so the tensor core works on one head while the
-// CUDA cores run the other head's softmax.  In the row passes warpgroup g handles columns
-// 80g .. 80g+79 of every row (thread <-> row, TMEM lane = row).  Weights are streamed from L2
-// in 160 x 160 bf16 chunks (51,200 B, pre-packed UMMA operand images) through two slots by the
-// TMA engine, prefetched one GEMM ahead.
+// 384 threads, warp-specialised:
+//   warps 0-3 / 4-7   compute warpgroups (thread <-> frame, TMEM lane = frame).  In the attention
+//                     phases warpgroup g owns heads g and g+2; in the row passes it handles columns
+//                     80g .. 80g+79 of every row.  Thread 0 also issues the GEMM-chain MMAs and
+//                     weight-chunk copies (they are strictly ordered with the row passes anyway).
+//   warp 8 / 10       TMA producer of warpgroup 0 / 1: K (3 stages) and V (2 stages) blocks of 64 keys
+//   warp 9 / 11       MMA issuer of warpgroup 0 / 1:  S = Q K^T into a double-buffered TMEM block,
+//                     O += P V accumulating in TMEM
+// Attention is a single streaming pass per head in which no thread waits for a tensor-core round
+// trip: S blocks (64 keys) arrive in a double-buffered TMEM block, p = exp2(s*c - m) goes to shared
+// memory as bf16 (double buffered) and P V ACCUMULATES in TMEM.  m is a lazily updated running row
+// maximum: only when a block raises it by more than 2^8 does the warp rescale its O rows in TMEM
+// (tcgen05.ld / st) -- after the first block or two of a head that never happens -- so O is read
+// once per head and the result is exact (O and the row sum carry the same factor).
+// All hand-offs are mbarriers (full/free pairs per buffer); the only CTA-wide barriers are the
+// named barriers between GEMM-chain stages.  Weights are streamed from L2 in 160 x 160 bf16 chunks
+// (51,200 B, pre-packed UMMA operand images) through two slots, prefetched one GEMM ahead.
 #pragma once
 #include "umma.cuh"
 
 namespace edtts {
 namespace tc {
 
-constexpr int LY_THREADS = 256;
+constexpr int LY_THREADS = 384;
+constexpr int LY_CTHREADS = 256;              // compute threads
 constexpr int LY_SLAB = 128 * 16;             // one 8-wide K slab of a 128-row operand
 constexpr int LY_WSLAB = 160 * 16;            // one 8-wide K slab of a 160-row weight chunk
 constexpr int LY_WCHUNK = 20 * LY_WSLAB;      // 51,200 B: W[160 out][160 in] bf16
 constexpr int LY_NCHUNK = 9;                  // proj, q_proj, out_proj, ffn0 x4, ffn3 x2
 enum LyChunk : int { WC_PROJ = 0, WC_Q, WC_OUT, WC_F0_X0, WC_F0_G0, WC_F0_X1, WC_F0_G1, WC_F3_K0, WC_F3_K1 };
+constexpr int LY_KB = 64;                     // keys per attention block
+constexpr int LY_KSLAB = LY_KB * 16;          // one 8-wide slab of a 64-key K / V block
+constexpr int LY_KBUF = 6 * LY_KSLAB;         // K (or V) block, head_dim padded 40 -> 48
+constexpr int LY_PBUF = (LY_KB / 8) * LY_SLAB;   // P block: 128 frames x 64 keys bf16
 
 // per-layer constant vector (floats), packed by tc_layer.cu
 constexpr int LC_PROJ_B = 0, LC_N2W = 160, LC_N3W = 320, LC_F0B = 480, LC_F3B = 1120, LC_COUNT = 1280;
@@ -50,20 +64,27 @@ constexpr int LO_W0 = LO_A + 21 * LY_SLAB;                // weight slot 0
 constexpr int LO_X = LO_W0 + LY_WCHUNK;                   // overlay region
 constexpr int LO_W1 = LO_X;                               //   GEMM chain: weight slot 1
 constexpr int LO_U = LO_X + LY_WCHUNK;                    //   GEMM chain: u half (128 x 160 bf16)
-constexpr int LO_P = LO_X;                                //   attention: P of warpgroup g at + g * 32 KB
-constexpr int LO_KV = LO_X + 2 * 16 * LY_SLAB;            //   attention: K | V of warpgroup g at + g * 24 KB
-constexpr int LO_X_END = LO_KV + 2 * 12 * LY_SLAB;
+constexpr int LO_P = LO_X;                                //   attention: P[wg][buf]
+constexpr int LY_KST = 3, LY_VST = 2;                     //   K / V stages per warpgroup
+constexpr int LO_KV = LO_P + 4 * LY_PBUF;                 //   attention: wg: K0 | K1 | K2 | V0 | V1
+constexpr int LO_X_END = LO_KV + 2 * (LY_KST + LY_VST) * LY_KBUF;
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
 constexpr int LO_BAR = LO_RED + 2 * 128 * 4;
-constexpr int LY_SMEM = LO_BAR + 16 * 8 + 16;
+constexpr int LY_NBAR = 8 + 2 * 20;
+constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
 static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay region");
 static_assert(LY_SMEM <= 232448, "shared memory budget");
+
+// mbarrier indices
+enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_WG0 = 8 };
+enum LyWgBar : int { WB_KFULL = 0, WB_KFREE = 3, WB_VFULL = 6, WB_VFREE = 8, WB_SFULL = 10, WB_SFREE = 12, WB_PFULL = 14,
+                     WB_PFREE = 16, WB_OFULL = 18, WB_OFREE = 19, WB_COUNT = 20 };
 
 // tensor memory map (columns)
 constexpr uint32_t TM_H = 0;                              // residual stream, 160 columns
 constexpr uint32_t TM_G = 160;                            // GEMM chain scratch, 320 columns
-constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention: S (128) | O (48) per warpgroup
+constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention, per warpgroup: S0 (64) | S1 (64) | O (48)
 
 struct LayerArgs {
   float* h;                          // [R][160] fp32 residual stream, in place
@@ -78,6 +99,7 @@ struct LayerArgs {
   int tiles_per_utt;
   float scale_log2e;                 // head_dim^-0.5 * log2(e)
   int stop_phase;                    // debug: 1 = stop after attention + proj, 2 = after cross, 0 = whole block
+  long long* phase_clocks;           // debug: [gridDim.x][24] cycles per phase / attention section (thread 0), or null
 };
 
 __device__ __forceinline__ float fast_silu(float g) {
@@ -97,218 +119,361 @@ struct LyTile {
   int b, t0, nq;
   int64_t row0;
 };
+__device__ __forceinline__ LyTile ly_tile(const LayerArgs& a, int tile) {
+  LyTile tl;
+  tl.b = tile / a.tiles_per_utt;
+  tl.t0 = (tile % a.tiles_per_utt) * 128;
+  tl.nq = min(128, a.T - tl.t0);
+  tl.row0 = (int64_t)tl.b * a.T + tl.t0;
+  return tl;
+}
 
-// One attention phase of one warpgroup (heads wg and wg + 2).  Q is in sA (slabs 5*head ..), the
-// normalised output replaces it there.  K/V of the first (head, block) item must already be in flight.
+// Key blocks of one attention phase.  Window: block kb (0..3) holds frames t0-64+64kb .. +63, blocks with no
+// frame inside the utterance are skipped; cross: block i holds context tokens 64i .. 64i+63.
+struct LyPlan {
+  int kb0, nb;
+};
 template <bool WINDOW>
-__device__ __forceinline__ void ly_attention(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint32_t tmem_base,
-                                             uint64_t* bars, uint32_t& ph_k, uint32_t& ph_v, uint32_t& ph_s,
-                                             uint32_t& ph_o) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
-  const bool wl = (tid & 127) == 0;                       // warpgroup leader: issues copies and MMAs
-  uint8_t* sA = smem + LO_A;
-  uint8_t* sP = smem + LO_P + wg * (16 * LY_SLAB);
-  uint8_t* sK = smem + LO_KV + wg * (12 * LY_SLAB);
-  uint8_t* sV = sK + 6 * LY_SLAB;
-  uint64_t* bar_k = bars + 4 + wg;
-  uint64_t* bar_v = bars + 6 + wg;
-  uint64_t* bar_s = bars + 8 + wg;
-  uint64_t* bar_o = bars + 10 + wg;
-  const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-  const uint32_t tS = trow + TM_S0 + wg * TM_WG;
-  const uint32_t tO = tS + 128;
-  const uint32_t dS = tmem_base + TM_S0 + wg * TM_WG;     // MMA destinations (lane 0)
-  const uint32_t dO = dS + 128;
+__device__ __forceinline__ LyPlan ly_plan(const LayerArgs& a, const LyTile& tl) {
+  LyPlan p;
+  if (WINDOW) {
+    p.kb0 = tl.t0 == 0 ? 1 : 0;
+    const int kb1 = min(3, (a.T - 1 - (tl.t0 - WIN)) >> 6);
+    p.nb = kb1 - p.kb0 + 1;
+  } else {
+    p.kb0 = 0;
+    p.nb = (a.S + LY_KB - 1) / LY_KB;
+  }
+  return p;
+}
+// keys the MMAs of block i cover (a multiple of 16)
+template <bool WINDOW>
+__device__ __forceinline__ int ly_nkeys(const LayerArgs& a, int i) {
+  if (WINDOW) return LY_KB;
+  return (min(LY_KB, a.S - i * LY_KB) + 15) & ~15;
+}
 
-  const int nblocks = WINDOW ? ((tl.t0 + WIN < a.T) ? 2 : 1) : (a.S + 127) / 128;
-  const int n_items = 2 * nblocks;
-
-  auto issue_k = [&](int it) {                            // leader only
-    const int head = wg + 2 * (it / nblocks), kb = it % nblocks;
+// ---- TMA producer of one warpgroup, one attention phase (one thread) ------------------------------------------
+template <bool WINDOW>
+__device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint64_t* wb, int wg,
+                                             uint32_t& nk, uint32_t& nv) {
+  const LyPlan pl = ly_plan<WINDOW>(a, tl);
+  uint8_t* kv = smem + LO_KV + wg * ((LY_KST + LY_VST) * LY_KBUF);
+  auto load = [&](int head, int i, bool is_v, uint32_t& cnt) {
+    const uint32_t nst = is_v ? LY_VST : LY_KST;
+    const uint32_t buf = cnt % nst, use = cnt / nst;
+    uint64_t* full = wb + (is_v ? WB_VFULL : WB_KFULL) + buf;
+    mbar_wait(wb + (is_v ? WB_VFREE : WB_KFREE) + buf, (use & 1) ^ 1);
+    uint8_t* dst = kv + ((is_v ? LY_KST : 0) + buf) * LY_KBUF;
     if (WINDOW) {
-      const int64_t g0 = tl.row0 - WIN + 128 * kb;
-      mbar_expect_tx(bar_k, 5 * LY_SLAB);
+      const int64_t g0 = tl.row0 - WIN + LY_KB * (pl.kb0 + i);
+      const int c0 = (is_v ? 40 : 20) + head * 5;
+      mbar_expect_tx(full, 5 * LY_KSLAB);
 #pragma unroll
-      for (int g = 0; g < 5; ++g)
-        bulk_g2s(sK + g * LY_SLAB, a.qkv + ((int64_t)(20 + head * 5 + g) * a.R + g0) * 8, LY_SLAB, bar_k);
+      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.qkv + ((int64_t)(c0 + g) * a.R + g0) * 8, LY_KSLAB, full);
     } else {
-      const int nv = min(128, a.S - kb * 128);
-      const int64_t g0 = (int64_t)tl.b * a.S + kb * 128;
-      mbar_expect_tx(bar_k, 5 * nv * 16);
+      const int nvalid = min(LY_KB, a.S - i * LY_KB);
+      const int64_t g0 = (int64_t)tl.b * a.S + i * LY_KB;
+      const int c0 = (is_v ? 20 : 0) + head * 5;
+      if (is_v && (nvalid & 15)) {                        // keys nvalid .. round16(nvalid)-1 enter P V with p = 0: finite v needed
+        for (int r = nvalid; r < ((nvalid + 15) & ~15); ++r)
 #pragma unroll
-      for (int g = 0; g < 5; ++g)
-        bulk_g2s(sK + g * LY_SLAB, a.kvx + ((int64_t)(head * 5 + g) * a.RS + g0) * 8, nv * 16, bar_k);
-    }
-  };
-  auto issue_v = [&](int it) {
-    const int head = wg + 2 * (it / nblocks), kb = it % nblocks;
-    if (WINDOW) {
-      const int64_t g0 = tl.row0 - WIN + 128 * kb;
-      mbar_expect_tx(bar_v, 5 * LY_SLAB);
-#pragma unroll
-      for (int g = 0; g < 5; ++g)
-        bulk_g2s(sV + g * LY_SLAB, a.qkv + ((int64_t)(40 + head * 5 + g) * a.R + g0) * 8, LY_SLAB, bar_v);
-    } else {
-      const int nv = min(128, a.S - kb * 128);
-      const int64_t g0 = (int64_t)tl.b * a.S + kb * 128;
-      mbar_expect_tx(bar_v, 5 * nv * 16);
-#pragma unroll
-      for (int g = 0; g < 5; ++g)
-        bulk_g2s(sV + g * LY_SLAB, a.kvx + ((int64_t)(20 + head * 5 + g) * a.RS + g0) * 8, nv * 16, bar_v);
-    }
-  };
-
-  float o_acc[HD];
-  float m_run = -INFINITY, l_run = 0.f;
-
-  for (int it = 0; it < n_items; ++it) {
-    const int head = wg + 2 * (it / nblocks), kb = it % nblocks;
-    if (kb == 0) {
-      m_run = -INFINITY;
-      l_run = 0.f;
-#pragma unroll
-      for (int d = 0; d < HD; ++d) o_acc[d] = 0.f;
-    }
-    // valid key columns [lo, hi] of this thread's row; 32-column chunks [cfirst, clast] of this warp
-    int lo, hi, cfirst, clast, nkeys;
-    if (WINDOW) {
-      const int j0 = tl.t0 - WIN + 128 * kb;              // frame index of key column 0
-      nkeys = 128;
-      if (kb == 0) {
-        lo = max(row, -j0);
-        hi = min(127, a.T - 1 - j0);
-        cfirst = max(lq, (j0 < 0 ? -j0 : 0) >> 5);
-        clast = 3;
-      } else {
-        lo = 0;
-        hi = min(row, a.T - 1 - j0);
-        cfirst = 0;
-        clast = min(lq, (a.T - 1 - j0) >> 5);
+          for (int g = 0; g < 5; ++g) *reinterpret_cast<uint4*>(dst + g * LY_KSLAB + r * 16) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
       }
-    } else {
-      const int nv = min(128, a.S - kb * 128);
-      nkeys = (nv + 15) & ~15;
-      lo = 0;
-      hi = nv - 1;
-      cfirst = 0;
-      clast = (nv - 1) >> 5;
-    }
-    const int nchunks = (nkeys + 31) >> 5;
-
-    // ---- S = Q_h K^T ---------------------------------------------------------------------
-    if (wl) {
-      mbar_wait(bar_k, ph_k);
-      tc_fence_after();
-      const uint32_t idesc = make_idesc(128, (uint32_t)nkeys);
-      const uint32_t qa = smem_u32(sA) + head * 5 * LY_SLAB, ka = smem_u32(sK);
+      mbar_expect_tx(full, 5 * nvalid * 16);
 #pragma unroll
-      for (int ks = 0; ks < 3; ++ks)
-        umma_bf16(dS, make_desc(qa + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(ka + ks * 2 * LY_SLAB, LY_SLAB, 128), idesc,
-                  ks > 0);
-      umma_commit(bar_s);
+      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.kvx + ((int64_t)(c0 + g) * a.RS + g0) * 8, nvalid * 16, full);
     }
-    ph_k ^= 1;
-    mbar_wait(bar_s, ph_s);
-    ph_s ^= 1;
+    ++cnt;
+  };
+  for (int hh = 0; hh < 2; ++hh) {
+    const int head = wg + 2 * hh;
+    for (int i = 0; i < LY_KST && i < pl.nb; ++i) load(head, i, false, nk);
+    for (int i = 0; i < LY_VST && i < pl.nb; ++i) load(head, i, true, nv);
+    for (int i = 0; i < pl.nb; ++i) {                     // K(i+3) needs S(i) retired, V(i+2) needs P V(i) retired
+      if (i + LY_KST < pl.nb) load(head, i + LY_KST, false, nk);
+      if (i + LY_VST < pl.nb) load(head, i + LY_VST, true, nv);
+    }
+  }
+}
+
+// ---- MMA issuer of one warpgroup, one attention phase (one thread) ------------------------------------------------
+template <bool WINDOW>
+__device__ __forceinline__ void ly_mma_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint32_t tmem_base,
+                                             uint64_t* wb, int wg, uint32_t& ns, uint32_t& nv, uint32_t& nh) {
+  const LyPlan pl = ly_plan<WINDOW>(a, tl);
+  const uint32_t sA = smem_u32(smem + LO_A);
+  const uint32_t sP = smem_u32(smem + LO_P + wg * (2 * LY_PBUF));
+  const uint32_t sKV = smem_u32(smem + LO_KV + wg * ((LY_KST + LY_VST) * LY_KBUF));
+  const uint32_t dS = tmem_base + TM_S0 + wg * TM_WG;
+  const uint32_t dO = dS + 2 * LY_KB;
+  auto s_op = [&](int head, int i) {
+    const uint32_t sbuf = ns & 1, kbuf = ns % LY_KST;
+    mbar_wait(wb + WB_KFULL + kbuf, (ns / LY_KST) & 1);
+    mbar_wait(wb + WB_SFREE + sbuf, ((ns >> 1) & 1) ^ 1);
     tc_fence_after();
-    if (wl && it + 1 < n_items) issue_k(it + 1);          // K buffer is free again
-
-    // ---- softmax ------------------------------------------------------------------------------
-    float bmax = -INFINITY;
-    for (int ch = cfirst; ch <= clast; ++ch) {
-      float s[32];
-      tmem_ld32(tS + ch * 32, s);
-      const bool full = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
-      if (full) {
+    const uint32_t idesc = make_idesc(128, (uint32_t)ly_nkeys<WINDOW>(a, i));
+    const uint32_t qa = sA + head * 5 * LY_SLAB, ka = sKV + kbuf * LY_KBUF;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) bmax = fmaxf(bmax, s[j]);
+    for (int ks = 0; ks < 3; ++ks)
+      umma_bf16(dS + sbuf * LY_KB, make_desc(qa + ks * 2 * LY_SLAB, LY_SLAB, 128),
+                make_desc(ka + ks * 2 * LY_KSLAB, LY_KSLAB, 128), idesc, ks > 0);
+    umma_commit(wb + WB_SFULL + sbuf);
+    umma_commit(wb + WB_KFREE + kbuf);
+    ++ns;
+  };
+  auto pv_op = [&](int i, bool last) {
+    const uint32_t buf = nv & 1, par = (nv >> 1) & 1;
+    mbar_wait(wb + WB_PFULL + buf, par);
+    mbar_wait(wb + WB_VFULL + buf, par);
+    if (i == 0) mbar_wait(wb + WB_OFREE, (nh & 1) ^ 1);
+    tc_fence_after();
+    constexpr uint32_t IDESC_O = make_idesc_f16(128, 48, /*b_mn_major=*/true);   // P, V are f16
+    const uint32_t pa = sP + buf * LY_PBUF, va = sKV + (LY_KST + buf) * LY_KBUF;
+    const int nks = ly_nkeys<WINDOW>(a, i) >> 4;
+    for (int ks = 0; ks < nks; ++ks)
+      umma_bf16(dO, make_desc(pa + ks * 2 * LY_SLAB, LY_SLAB, 128),
+                make_desc(va + ks * 2 * 128, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_KSLAB), IDESC_O, i > 0 || ks > 0);
+    umma_commit(wb + WB_PFREE + buf);
+    umma_commit(wb + WB_VFREE + buf);
+    if (last) umma_commit(wb + WB_OFULL);
+    ++nv;
+  };
+  for (int hh = 0; hh < 2; ++hh) {
+    const int head = wg + 2 * hh;
+    s_op(head, 0);
+    if (pl.nb > 1) s_op(head, 1);
+    for (int i = 0; i < pl.nb; ++i) {
+      pv_op(i, i == pl.nb - 1);
+      if (i + 2 < pl.nb) s_op(head, i + 2);
+    }
+    ++nh;
+  }
+}
+
+// one arrival per warp on a count-4 mbarrier, after every lane's preceding work
+__device__ __forceinline__ void ly_warp_arrive(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+// ---- compute warpgroup, one attention phase: heads wg and wg + 2 ------------------------------------------------------
+// Q is in sA (slabs 5*head ..); the normalised output replaces it there.
+//
+// Per 64-key block and thread (= frame): 64 scores come out of TMEM into registers (the TMEM block is released
+// at once, so the next S = Q K^T runs under this block's arithmetic), the running maximum is checked, and
+//     p = ex2.approx.f16x2(cvt.f16x2(s * c - m))
+// goes straight to the P operand (f16, 8 keys = one 16-byte store).  Two scores per MUFU operation and no
+// running sum: V carries a constant 1 in its padding dimension 40 (ly_init_pads), so the tensor core delivers
+// the row sum of exactly the rounded p as column 40 of O.
+__device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
+  const __half2 h = __floats2half2_rn(x_lo, x_hi);
+  uint32_t in = *reinterpret_cast<const uint32_t*>(&h), out;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(in));
+  return out;
+}
+// TMEM -> registers, 64 columns, NOT waited for
+__device__ __forceinline__ void ly_s_issue(uint32_t taddr, uint32_t (&r)[64]) {
+#pragma unroll
+  for (int c = 0; c < 2; ++c)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[32 * c + 0]), "=r"(r[32 * c + 1]), "=r"(r[32 * c + 2]), "=r"(r[32 * c + 3]), "=r"(r[32 * c + 4]),
+          "=r"(r[32 * c + 5]), "=r"(r[32 * c + 6]), "=r"(r[32 * c + 7]), "=r"(r[32 * c + 8]), "=r"(r[32 * c + 9]),
+          "=r"(r[32 * c + 10]), "=r"(r[32 * c + 11]), "=r"(r[32 * c + 12]), "=r"(r[32 * c + 13]), "=r"(r[32 * c + 14]),
+          "=r"(r[32 * c + 15]), "=r"(r[32 * c + 16]), "=r"(r[32 * c + 17]), "=r"(r[32 * c + 18]), "=r"(r[32 * c + 19]),
+          "=r"(r[32 * c + 20]), "=r"(r[32 * c + 21]), "=r"(r[32 * c + 22]), "=r"(r[32 * c + 23]), "=r"(r[32 * c + 24]),
+          "=r"(r[32 * c + 25]), "=r"(r[32 * c + 26]), "=r"(r[32 * c + 27]), "=r"(r[32 * c + 28]), "=r"(r[32 * c + 29]),
+          "=r"(r[32 * c + 30]), "=r"(r[32 * c + 31])
+        : "r"(taddr + 32 * c)
+        : "memory");
+}
+// wait for the loads above; the registers are tied to the wait so that no use can be scheduled before it
+__device__ __forceinline__ void ly_s_wait(uint32_t (&r)[64]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+  asm volatile(""
+               : "+r"(r[32]), "+r"(r[33]), "+r"(r[34]), "+r"(r[35]), "+r"(r[36]), "+r"(r[37]), "+r"(r[38]), "+r"(r[39]),
+                 "+r"(r[40]), "+r"(r[41]), "+r"(r[42]), "+r"(r[43]), "+r"(r[44]), "+r"(r[45]), "+r"(r[46]), "+r"(r[47]),
+                 "+r"(r[48]), "+r"(r[49]), "+r"(r[50]), "+r"(r[51]), "+r"(r[52]), "+r"(r[53]), "+r"(r[54]), "+r"(r[55]),
+                 "+r"(r[56]), "+r"(r[57]), "+r"(r[58]), "+r"(r[59]), "+r"(r[60]), "+r"(r[61]), "+r"(r[62]), "+r"(r[63])
+               :
+               : "memory");
+}
+
+// K padding slabs (dims 40..47) = 0, V padding slabs = (1, 0, .., 0): the GEMM-chain buffers overlay them, so the
+// compute threads rewrite them before every attention phase (640 16-byte stores per CTA)
+__device__ __forceinline__ void ly_init_pads(uint8_t* smem, int tid) {
+  for (int i = tid; i < 2 * (LY_KST + LY_VST) * LY_KB; i += LY_CTHREADS) {
+    const int r = i % LY_KB, b = (i / LY_KB) % (LY_KST + LY_VST), w = i / (LY_KB * (LY_KST + LY_VST));
+    uint8_t* slab = smem + LO_KV + (w * (LY_KST + LY_VST) + b) * LY_KBUF + 5 * LY_KSLAB;
+    *reinterpret_cast<uint4*>(slab + r * 16) = make_uint4(b >= LY_KST ? 0x00003C00u : 0u, 0u, 0u, 0u);
+  }
+}
+
+template <bool WINDOW>
+__device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint32_t tmem_base,
+                                                 uint64_t* wb, uint32_t& cs, uint32_t& cp, uint32_t& co, long long* fc) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  long long fc_last = clock64();
+#define LY_FC(i)                              \
+  if (fc) {                                   \
+    const long long now_ = clock64();         \
+    fc[i] += now_ - fc_last;                  \
+    fc_last = now_;                           \
+  }
+  const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
+  const LyPlan pl = ly_plan<WINDOW>(a, tl);
+  uint8_t* sA = smem + LO_A;
+  uint8_t* sP = smem + LO_P + wg * (2 * LY_PBUF);
+  const uint32_t tS = tmem_base + ((uint32_t)(lq * 32) << 16) + TM_S0 + wg * TM_WG;
+  const uint32_t tO = tS + 2 * LY_KB;
+  const float c = a.scale_log2e;
+
+  float m_run = -INFINITY;                                // running row maximum in exp2 units (s * c), lazily updated
+
+  // one block of 64 keys
+  auto step = [&](uint32_t (&cur)[64], int i) {
+    const uint32_t pbuf = cp & 1;
+    LY_FC(0)
+    mbar_wait(wb + WB_SFULL + (cs & 1), (cs >> 1) & 1);
+    tc_fence_after();
+    ly_s_issue(tS + (cs & 1) * LY_KB, cur);               // both 32-column loads in flight, one wait
+    ly_s_wait(cur);
+    tc_fence_before();
+    ly_warp_arrive(wb + WB_SFREE + (cs & 1), lane);       // the TMEM block is free again at once
+    ++cs;
+    LY_FC(1)
+    // valid key columns [lo, hi] of this thread's row inside block i (empty if hi < lo)
+    int lo, hi;
+    if (WINDOW) {
+      const int off0 = LY_KB * (pl.kb0 + i);              // band offset (frame - (t0 - 64)) of column 0
+      lo = max(max(row, WIN - tl.t0) - off0, 0);
+      hi = min(min(row + 2 * WIN, a.T - 1 - tl.t0 + WIN) - off0, LY_KB - 1);
+    } else {
+      lo = 0;
+      hi = min(LY_KB, a.S - i * LY_KB) - 1;
+    }
+    const bool any = hi >= lo;
+    const int base = -lo;
+    const unsigned span = (unsigned)(hi - lo);
+    const int nch = (ly_nkeys<WINDOW>(a, i) + 31) >> 5;
+    bool need[2], full[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      need[ch] = ch < nch && __any_sync(0xffffffffu, any && lo <= ch * 32 + 31 && hi >= ch * 32);   // warp-uniform
+      full[ch] = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
+    }
+    // ---- block maximum, lazy update of the running maximum ------------------------------------------------
+    float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      if (!need[ch]) continue;
+      if (full[ch]) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          b0 = fmaxf(b0, __uint_as_float(cur[32 * ch + j]));
+          b1 = fmaxf(b1, __uint_as_float(cur[32 * ch + j + 1]));
+          b2 = fmaxf(b2, __uint_as_float(cur[32 * ch + j + 2]));
+          b3 = fmaxf(b3, __uint_as_float(cur[32 * ch + j + 3]));
+        }
       } else {
-        const int base = ch * 32 - lo;
-        const unsigned span = (unsigned)(hi - lo);
-        const bool any = hi >= lo;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (any && (unsigned)(base + j) <= span) bmax = fmaxf(bmax, s[j]);
+          if (any && (unsigned)(base + 32 * ch + j) <= span) b0 = fmaxf(b0, __uint_as_float(cur[32 * ch + j]));
       }
     }
-    const float m_new = fmaxf(m_run, bmax * a.scale_log2e);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = ex2_approx(m_run - m_use);        // m_run = -inf -> 0
-    float lsum = 0.f;
-    for (int ch = 0; ch < nchunks; ++ch) {
-      uint4 pk[4];
-      if (ch < cfirst || ch > clast) {                    // warp-uniform: columns no row of this warp needs
+    const float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * c;
+    const bool grow = bmax > m_run + 6.0f;                // also true for the first finite block maximum
+    if (__any_sync(0xffffffffu, grow)) {
+      const float m_upd = grow ? bmax : m_run;
+      if (i > 0) {                                        // rescale this warp's O rows (and the row sum in column 40):
+        const float f = (m_upd == m_run) ? 1.0f : ex2_approx(m_run - m_upd);     // m_run = -inf -> 0
+        mbar_wait(wb + WB_PFREE + (pbuf ^ 1), ((cp - 1) >> 1) & 1);              // P V (i-1) must have retired
+        tc_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pk[g] = make_uint4(0, 0, 0, 0);
-      } else {
-        float s[32];
-        tmem_ld32(tS + ch * 32, s);
-        const bool full = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
-        if (full) {
+        for (int q = 0; q < 3; ++q) {
+          float ob[16];
+          tmem_ld16(tO + 16 * q, ob);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            s[j] = ex2_approx(fmaf(s[j], a.scale_log2e, -m_use));
-            lsum += s[j];
-          }
-        } else {
-          const int base = ch * 32 - lo;
-          const unsigned span = (unsigned)(hi - lo);
-          const bool any = hi >= lo;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float p = ex2_approx(fmaf(s[j], a.scale_log2e, -m_use));
-            s[j] = (any && (unsigned)(base + j) <= span) ? p : 0.f;
-            lsum += s[j];
-          }
+          for (int d = 0; d < 16; ++d) ob[d] *= f;
+          tmem_st16(tO + 16 * q, ob);
         }
+        tmem_st_wait();
+      }
+      m_run = m_upd;
+    }
+    const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+    LY_FC(2)
+    // ---- p -> P (f16, shared memory).  The P buffer is free: S(i) was issued after P V (i-2), and the tensor
+    //      core retires its work in issue order, so S(i) complete implies P V (i-2) complete. ----------------------
+    uint8_t* prow = sP + pbuf * LY_PBUF + row * 16;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) pk[g] = pack_bf16x8(s + 8 * g);
+    for (int ch = 0; ch < 2; ++ch) {
+      if (ch >= nch) continue;
+      uint32_t pk[16];
+      if (!need[ch]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = 0u;
+      } else if (full[ch]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          pk[j] = ly_exp2_f16x2(fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use),
+                                fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
+          float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
+          if (!(any && (unsigned)(base + 32 * ch + 2 * j) <= span)) x0 = -INFINITY;
+          if (!(any && (unsigned)(base + 32 * ch + 2 * j + 1) <= span)) x1 = -INFINITY;
+          pk[j] = ly_exp2_f16x2(x0, x1);
+        }
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) *reinterpret_cast<uint4*>(sP + (ch * 4 + g) * LY_SLAB + row * 16) = pk[g];
+      for (int g = 0; g < 4; ++g)
+        *reinterpret_cast<uint4*>(prow + (ch * 4 + g) * LY_SLAB) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
     }
-    l_run = l_run * alpha + lsum;
-    m_run = m_new;
+    LY_FC(3)
     fence_proxy_async();
     tc_fence_before();
-    named_bar_sync(1 + wg, 128);                          // P complete, S columns drained
+    ly_warp_arrive(wb + WB_PFULL + pbuf, lane);
+    ++cp;
+    LY_FC(4)
+  };
 
-    // ---- O_blk = P V -------------------------------------------------------------------------
-    if (wl) {
-      mbar_wait(bar_v, ph_v);
-      tc_fence_after();
-      constexpr uint32_t IDESC_O = make_idesc(128, 48, /*b_mn_major=*/true);
-      const uint32_t pa = smem_u32(sP), va = smem_u32(sV);
-      const int nks = nkeys >> 4;
-      for (int ks = 0; ks < nks; ++ks)
-        umma_bf16(dO, make_desc(pa + ks * 2 * LY_SLAB, LY_SLAB, 128),
-                  make_desc(va + ks * 2 * 128, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_SLAB), IDESC_O, ks > 0);
-      umma_commit(bar_o);
-    }
-    ph_v ^= 1;
-    mbar_wait(bar_o, ph_o);
-    ph_o ^= 1;
+  for (int hh = 0; hh < 2; ++hh) {
+    const int head = wg + 2 * hh;
+    uint32_t sc[64];
+    m_run = -INFINITY;
+    for (int i = 0; i < pl.nb; ++i) step(sc, i);
+
+    // ---- head done: O / l replaces Q_h in sA ---------------------------------------------------------------------
+    LY_FC(6)
+    mbar_wait(wb + WB_OFULL, co & 1);
     tc_fence_after();
-    if (wl && it + 1 < n_items) issue_v(it + 1);          // V buffer is free again
-    {
-      float ob[HD];
-      tmem_ld32(tO, ob);
-      tmem_ld8(tO + 32, ob + 32);
-#pragma unroll
-      for (int d = 0; d < HD; ++d) o_acc[d] = fmaf(o_acc[d], alpha, ob[d]);
-    }
-    if (kb == nblocks - 1) {                              // head done: normalised output replaces Q_h in sA
-      const float inv = __fdividef(1.0f, l_run);
-#pragma unroll
-      for (int g = 0; g < 5; ++g) {
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = o_acc[g * 8 + j] * inv;
-        *reinterpret_cast<uint4*>(sA + (head * 5 + g) * LY_SLAB + row * 16) = pack_bf16x8(v);
-      }
-    }
+    LY_FC(7)
+    float ob[48];
+    tmem_ld32(tO, ob);
+    tmem_ld16(tO + 32, ob + 32);
     tc_fence_before();
+    ly_warp_arrive(wb + WB_OFREE, lane);
+    ++co;
+    const float inv = __fdividef(1.0f, ob[HD]);           // column 40 = sum of p (V's constant-one dimension)
+#pragma unroll
+    for (int g = 0; g < 5; ++g) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ob[g * 8 + j] * inv;
+      *reinterpret_cast<uint4*>(sA + (head * 5 + g) * LY_SLAB + row * 16) = pack_bf16x8(v);
+    }
   }
   fence_proxy_async();
 }
@@ -322,23 +487,29 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   float* sC = reinterpret_cast<float*>(smem + LO_CONST);
   float* sRed = reinterpret_cast<float*>(smem + LO_RED);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LO_BAR);
-  uint64_t* bar_w0 = bars + 0;
-  uint64_t* bar_w1 = bars + 1;
-  uint64_t* bar_q = bars + 2;
-  uint64_t* bar_g = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* bar_w0 = bars + LB_W0;
+  uint64_t* bar_w1 = bars + LB_W1;
+  uint64_t* bar_q = bars + LB_Q;
+  uint64_t* bar_g = bars + LB_G;
+  uint64_t* bar_kvgo = bars + LB_KVGO;
+  uint64_t* bar_attgo = bars + LB_ATTGO;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LY_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
-  const int cb = 80 * wg;                                 // this thread's column half in the row passes
-  const bool wl = (tid & 127) == 0;
 
   // finite shared memory everywhere (stale rows enter MMAs as 0 * x), zero pad slabs
   for (int i = tid * 16; i < LO_BAR; i += LY_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   for (int i = tid; i < LC_COUNT; i += LY_THREADS) sC[i] = a.consts[i];
   if (tid == 0) {
-    for (int i = 0; i < 12; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < LB_WG0; ++i) mbar_init(bars + i, 1);
+    for (int w = 0; w < 2; ++w) {
+      uint64_t* wbi = bars + LB_WG0 + w * WB_COUNT;
+      for (int i = 0; i < WB_COUNT; ++i) {
+        const bool per_warp = (i >= WB_SFREE && i < WB_SFREE + 2) || (i >= WB_PFULL && i < WB_PFULL + 2) || i == WB_OFREE;
+        mbar_init(wbi + i, per_warp ? 4 : 1);
+      }
+    }
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(tmem_slot);
@@ -347,10 +518,45 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-
   const int ntiles = a.B * a.tiles_per_utt;
-  uint32_t ph_w0 = 0, ph_w1 = 0, ph_q = 0, ph_g = 0, ph_k = 0, ph_v = 0, ph_s = 0, ph_o = 0;
+
+  // =========================== control warps: TMA producers and MMA issuers ===========================
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // registers go to the compute warpgroups
+    if (lane == 0) {
+      const int cwg = (warp - 8) >> 1;
+      const bool is_mma = (warp - 8) & 1;
+      uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
+      uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;       // TMA: c0 = K loads, c1 = V loads; MMA: S ops, PV ops, heads
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const LyTile tl = ly_tile(a, tile);
+        for (int ph = 0; ph < 2; ++ph) {
+          if (ph == 1 && a.stop_phase == 1) break;
+          if (!is_mma) {
+            mbar_wait(bar_kvgo, n_phase & 1);
+            if (ph == 0) ly_tma_phase<true>(a, tl, smem, cwb, cwg, c0, c1);
+            else ly_tma_phase<false>(a, tl, smem, cwb, cwg, c0, c1);
+          } else {
+            mbar_wait(bar_attgo, n_phase & 1);
+            tc_fence_after();
+            if (ph == 0) ly_mma_phase<true>(a, tl, smem, tmem_base, cwb, cwg, c0, c1, c2);
+            else ly_mma_phase<false>(a, tl, smem, tmem_base, cwb, cwg, c0, c1, c2);
+          }
+          ++n_phase;
+        }
+      }
+    }
+    return;
+  }
+
+  // =========================== compute warpgroups ===========================================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
+  const int cb = 80 * wg;                                 // this thread's column half in the row passes
+  uint64_t* wb = bars + LB_WG0 + wg * WB_COUNT;
+  const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
+  uint32_t ph_w0 = 0, ph_w1 = 0, ph_q = 0, ph_g = 0, cs = 0, cp = 0, co = 0;
+  auto csync = [&]() { named_bar_sync(3, LY_CTHREADS); };
   auto load_w = [&](int chunk, uint8_t* slot, uint64_t* bar) {   // tid 0 only
     mbar_expect_tx(bar, LY_WCHUNK);
     bulk_g2s(slot, a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, bar);
@@ -381,44 +587,40 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
   };
 
-  if (tid == 0 && blockIdx.x < ntiles) load_w(WC_PROJ, sW0, bar_w0);
+  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long fcw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fcx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pc_last = clock64();
+#define LY_PHASE(i)                                   \
+  if (a.phase_clocks && tid == 0) {                   \
+    const long long now_ = clock64();                 \
+    pc[i] += now_ - pc_last;                          \
+    pc_last = now_;                                   \
+  }
+  if (tid == 0 && blockIdx.x < ntiles) {
+    load_w(WC_PROJ, sW0, bar_w0);
+    mbar_arrive(bar_kvgo);                                // K/V buffers are free: first window phase may load
+  }
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    LyTile tl;
-    tl.b = tile / a.tiles_per_utt;
-    tl.t0 = (tile % a.tiles_per_utt) * 128;
-    tl.nq = min(128, a.T - tl.t0);
-    tl.row0 = (int64_t)tl.b * a.T + tl.t0;
+    const LyTile tl = ly_tile(a, tile);
 
-    // ---- tile prologue: Q -> sA, first K/V blocks, h -> TMEM, AdaLN vectors ----------------
+    // ---- tile prologue: Q -> sA, h -> TMEM, AdaLN vectors ------------------------------------------------------
     if (tid == 0) {
       mbar_expect_tx(bar_q, 20 * tl.nq * 16);
 #pragma unroll 1
       for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * a.R + tl.row0) * 8, tl.nq * 16, bar_q);
     }
-    if (wl) {
-      // first window item of this warpgroup: head wg, key block 0
-      const int64_t g0 = tl.row0 - WIN;
-      uint8_t* sK = smem + LO_KV + wg * (12 * LY_SLAB);
-      uint8_t* sV = sK + 6 * LY_SLAB;
-      mbar_expect_tx(bars + 4 + wg, 5 * LY_SLAB);
-      mbar_expect_tx(bars + 6 + wg, 5 * LY_SLAB);
-#pragma unroll
-      for (int g = 0; g < 5; ++g) {
-        bulk_g2s(sK + g * LY_SLAB, a.qkv + ((int64_t)(20 + wg * 5 + g) * a.R + g0) * 8, LY_SLAB, bars + 4 + wg);
-        bulk_g2s(sV + g * LY_SLAB, a.qkv + ((int64_t)(40 + wg * 5 + g) * a.R + g0) * 8, LY_SLAB, bars + 6 + wg);
-      }
-    }
     {
-      const float* src = a.h + (tl.row0 + row) * H + cb;
-#pragma unroll 1
+      const float4* src = reinterpret_cast<const float4*>(a.h + (tl.row0 + row) * H + cb);
+      float4 x[20];
+#pragma unroll
+      for (int q = 0; q < 20; ++q) x[q] = row < tl.nq ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
       for (int i = 0; i < 5; ++i) {
         float v[16];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row < tl.nq) x = *reinterpret_cast<const float4*>(src + 16 * i + 4 * q);
-          v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+          v[4 * q] = x[4 * i + q].x; v[4 * q + 1] = x[4 * i + q].y; v[4 * q + 2] = x[4 * i + q].z; v[4 * q + 3] = x[4 * i + q].w;
         }
         tmem_st16(trow + TM_H + cb + 16 * i, v);
       }
@@ -429,30 +631,23 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
       sC[LS_SH3 + tid] = m[H + tid];
     }
+    ly_init_pads(smem, tid);
+    fence_proxy_async();
     mbar_wait(bar_q, ph_q);
     ph_q ^= 1;
     tc_fence_before();
-    __syncthreads();
+    csync();
+    if (tid == 0) mbar_arrive(bar_attgo);                 // Q in place, attention TMEM columns and P buffers free
+    LY_PHASE(0)
 
-    // ---- banded self-attention ---------------------------------------------------------------
-    ly_attention<true>(a, tl, smem, tmem_base, bars, ph_k, ph_v, ph_s, ph_o);
-    __syncthreads();
-    if (wl) {                                             // context K/V of the first cross item (overlay tail is free)
-      const int nv = min(128, a.S);
-      const int64_t g0 = (int64_t)tl.b * a.S;
-      uint8_t* sK = smem + LO_KV + wg * (12 * LY_SLAB);
-      uint8_t* sV = sK + 6 * LY_SLAB;
-      mbar_expect_tx(bars + 4 + wg, 5 * nv * 16);
-      mbar_expect_tx(bars + 6 + wg, 5 * nv * 16);
-#pragma unroll
-      for (int g = 0; g < 5; ++g) {
-        bulk_g2s(sK + g * LY_SLAB, a.kvx + ((int64_t)(wg * 5 + g) * a.RS + g0) * 8, nv * 16, bars + 4 + wg);
-        bulk_g2s(sV + g * LY_SLAB, a.kvx + ((int64_t)(20 + wg * 5 + g) * a.RS + g0) * 8, nv * 16, bars + 6 + wg);
-      }
-    }
+    // ---- banded self-attention -------------------------------------------------------------------------------
+    ly_softmax_phase<true>(a, tl, smem, tmem_base, wb, cs, cp, co, (a.phase_clocks && tid == 0) ? fcw : nullptr);
+    csync();
+    LY_PHASE(1)
 
-    // ---- h += O Wproj^T ------------------------------------------------------------------------
+    // ---- h += O Wproj^T ------------------------------------------------------------------------------------------
     if (tid == 0) {
+      if (a.stop_phase != 1) mbar_arrive(bar_kvgo);       // context K/V may stream in during the GEMM chain
       load_w(WC_Q, sW1, bar_w1);
       mbar_wait(bar_w0, ph_w0);
       tc_fence_after();
@@ -463,7 +658,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     gemm_wait();
     if (tid == 0) load_w(WC_OUT, sW0, bar_w0);
 
-    // ---- n2 = RMSNorm(h + b_proj) * w2 -> sA ; h + b_proj back to TMEM ---------------------------
+    // ---- n2 = RMSNorm(h + b_proj) * w2 -> sA ; h + b_proj back to TMEM ---------------------------------------------
     {
       float v[80];
       float ss = 0.f;
@@ -479,7 +674,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       }
       sRed[wg * 128 + row] = ss;
       tmem_st_wait();
-      __syncthreads();
+      csync();
       const float rstd = rsqrtf((sRed[row] + sRed[128 + row]) * (1.0f / H) + 1e-6f);
 #pragma unroll
       for (int g = 0; g < 10; ++g) {
@@ -491,21 +686,24 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    csync();
     if (a.stop_phase == 1) {
       tc_fence_after();
       store_h(tl, nullptr);
       // drain the prefetches so that the barrier phases stay consistent
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
-      if (wl) { mbar_wait(bars + 4 + wg, ph_k); mbar_wait(bars + 6 + wg, ph_v); }
-      ph_w1 ^= 1; ph_w0 ^= 1; ph_k ^= 1; ph_v ^= 1;
+      ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0 && tile + gridDim.x < ntiles) load_w(WC_PROJ, sW0, bar_w0);
+      csync();
+      if (tid == 0 && tile + gridDim.x < ntiles) {
+        load_w(WC_PROJ, sW0, bar_w0);
+        mbar_arrive(bar_kvgo);
+      }
       continue;
     }
+    LY_PHASE(2)
 
-    // ---- q = n2 Wq^T -> bf16 Q operand in sA -------------------------------------------------------
+    // ---- q = n2 Wq^T -> bf16 Q operand in sA -------------------------------------------------------------------------
     if (tid == 0) {
       mbar_wait(bar_w1, ph_w1);
       tc_fence_after();
@@ -523,13 +721,16 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    csync();
+    if (tid == 0) mbar_arrive(bar_attgo);
+    LY_PHASE(3)
 
-    // ---- cross attention over the context tokens ---------------------------------------------------
-    ly_attention<false>(a, tl, smem, tmem_base, bars, ph_k, ph_v, ph_s, ph_o);
-    __syncthreads();
+    // ---- cross attention over the context tokens ---------------------------------------------------------------------
+    ly_softmax_phase<false>(a, tl, smem, tmem_base, wb, cs, cp, co, (a.phase_clocks && tid == 0) ? fcx : nullptr);
+    csync();
+    LY_PHASE(4)
 
-    // ---- h += O Wout^T -----------------------------------------------------------------------------
+    // ---- h += O Wout^T -----------------------------------------------------------------------------------------------
     if (tid == 0) {
       load_w(WC_F0_X0, sW1, bar_w1);
       mbar_wait(bar_w0, ph_w0);
@@ -541,7 +742,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     gemm_wait();
     if (tid == 0) load_w(WC_F0_G0, sW0, bar_w0);
 
-    // ---- n3 = AdaRMSNorm(h) -> sA --------------------------------------------------------------------
+    // ---- n3 = AdaRMSNorm(h) -> sA --------------------------------------------------------------------------------------
     {
       float v[80];
       float ss = 0.f;
@@ -552,7 +753,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         for (int j = 0; j < 16; ++j) ss = fmaf(v[16 * i + j], v[16 * i + j], ss);
       }
       sRed[wg * 128 + row] = ss;
-      __syncthreads();
+      csync();
       const float rstd = rsqrtf((sRed[row] + sRed[128 + row]) * (1.0f / H) + 1e-6f);
 #pragma unroll
       for (int g = 0; g < 10; ++g) {
@@ -565,19 +766,23 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
+    csync();
     if (a.stop_phase == 2) {
       tc_fence_after();
       store_h(tl, nullptr);
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
       ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
-      __syncthreads();
-      if (tid == 0 && tile + gridDim.x < ntiles) load_w(WC_PROJ, sW0, bar_w0);
+      csync();
+      if (tid == 0 && tile + gridDim.x < ntiles) {
+        load_w(WC_PROJ, sW0, bar_w0);
+        mbar_arrive(bar_kvgo);
+      }
       continue;
     }
+    LY_PHASE(5)
 
-    // ---- feed-forward: two halves of 160 u columns ---------------------------------------------------
+    // ---- feed-forward: two halves of 160 u columns ---------------------------------------------------------------------
 #pragma unroll 1
     for (int half = 0; half < 2; ++half) {
       if (tid == 0) {
@@ -610,10 +815,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       }
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
+      csync();
     }
+    LY_PHASE(6)
 
-    // ---- h += u W3^T ; h + b3 -> HBM --------------------------------------------------------------------
+    // ---- h += u W3^T ; h + b3 -> HBM --------------------------------------------------------------------------------------
     if (tid == 0) {
       mbar_wait(bar_w1, ph_w1);
       mbar_wait(bar_w0, ph_w0);
@@ -625,13 +831,23 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     ph_w1 ^= 1;
     ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0 && tile + gridDim.x < ntiles) load_w(WC_PROJ, sW0, bar_w0);
+    if (tid == 0 && tile + gridDim.x < ntiles) {
+      load_w(WC_PROJ, sW0, bar_w0);
+      mbar_arrive(bar_kvgo);                              // overlay region is free: next tile's window K/V may load
+    }
     store_h(tl, sC + LC_F3B);
     tc_fence_before();
-    __syncthreads();
+    csync();
+    LY_PHASE(7)
   }
+  if (a.phase_clocks && tid == 0)
+    for (int i = 0; i < 8; ++i) {
+      a.phase_clocks[blockIdx.x * 24 + i] = pc[i];
+      a.phase_clocks[blockIdx.x * 24 + 8 + i] = fcw[i];
+      a.phase_clocks[blockIdx.x * 24 + 16 + i] = fcx[i];
+    }
 
-  __syncthreads();
+  csync();
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 

@@ -68,14 +68,17 @@ __global__ void pack_bias_swiglu_kernel(const float* __restrict__ src, float* __
   if (p < n_total) dst[p] = src[swiglu_row(p, n_cta, ffn)];
 }
 // test helpers: fp32 row-major [R][K] <-> bf16 chunk-major [K/8][R][8]
+// columns >= f16_from_col are stored as f16 (attention V operand), the rest as bf16
 __global__ void pack_act_kernel(const float* __restrict__ src, int lda, __nv_bfloat16* __restrict__ dst, int64_t R,
-                                int K) {
+                                int K, int f16_from_col) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= R * K) return;
   const int j = (int)(i & 7);
   const int64_t r = (i >> 3) % R;
   const int c = (int)((i >> 3) / R);
-  dst[i] = __float2bfloat16_rn(src[r * lda + c * 8 + j]);
+  const float v = src[r * lda + c * 8 + j];
+  if (c * 8 >= f16_from_col) reinterpret_cast<__half*>(dst)[i] = __float2half_rn(v);
+  else dst[i] = __float2bfloat16_rn(v);
 }
 __global__ void unpack_act_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t R, int N) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -129,10 +132,11 @@ int launch_tc_gemm(const TcGemmArgs& g, int K, int n_cta, int ny, cudaStream_t s
   return EDTTS_ENOTSUP;
 }
 
-int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, cudaStream_t st) {
+int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, int f16_from_col, cudaStream_t st) {
   LaunchScope ls(KC_TC_MISC, st);
   const int64_t n = R * K;
-  pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, lda, reinterpret_cast<__nv_bfloat16*>(dst_chunk), R, K);
+  pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, lda, reinterpret_cast<__nv_bfloat16*>(dst_chunk), R, K,
+                                                               f16_from_col);
   return check_launch("pack_activation");
 }
 
@@ -243,7 +247,7 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
       TcGemmArgs g;
       g.amode = A_F32; g.A_f32 = h; g.R = R; g.T = T; g.W_img = img(lo.qkv);
       g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H; g.mod_stride = 2 * NL * 2 * H;
-      g.epi = TE_CHUNK; g.out_chunk = qkv;
+      g.epi = TE_CHUNK; g.out_chunk = qkv; g.f16_from_chunk = 40;   // v is the f16 operand of P V
       if ((rc = launch_tc_gemm(g, H, 240, 2, st))) return rc;
     }
     if (fused) {
@@ -348,7 +352,7 @@ int tc_test_linear(const float* x, const float* w, const float* bias, float* y, 
     if (cudaMalloc(&achunk, (size_t)rows * K * 2) != cudaSuccess) rc = check_launch("cudaMalloc");
     if (!rc) {
       const int64_t n = rows * K;
-      pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, K, achunk, rows, K);
+      pack_act_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, K, achunk, rows, K, 1 << 30);
       rc = check_launch("pack_act");
       g.amode = A_CHUNK; g.A_chunk = achunk;
     }
@@ -388,9 +392,9 @@ int tc_test_attention(const float* q, int q_stride, const float* k, const float*
   __nv_bfloat16* kc = reinterpret_cast<__nv_bfloat16*>(buf + ATT_PAD_BYTES + q_bytes);
   __nv_bfloat16* vc = kc + Rk * H;
   __nv_bfloat16* oc = reinterpret_cast<__nv_bfloat16*>(buf + ATT_PAD_BYTES + q_bytes + kv_bytes + ATT_PAD_BYTES);
-  int rc = pack_activation(q, q_stride, qc, Rq, H, st);
-  if (!rc) rc = pack_activation(k, kv_stride, kc, Rk, H, st);
-  if (!rc) rc = pack_activation(v, kv_stride, vc, Rk, H, st);
+  int rc = pack_activation(q, q_stride, qc, Rq, H, 1 << 30, st);
+  if (!rc) rc = pack_activation(k, kv_stride, kc, Rk, H, 1 << 30, st);
+  if (!rc) rc = pack_activation(v, kv_stride, vc, Rk, H, 0, st);
   if (!rc) rc = window >= 0 ? launch_tc_attn_window(qc, oc, B, Tq, st) : launch_tc_attn_cross(qc, kc, oc, B, Tq, Tk, st);
   if (!rc) {
     const int64_t n = Rq * H;

@@ -21,7 +21,7 @@ int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st);
 // one fused DiffusionTransformerBlock (tc_layer.cuh); layer_img_base = image written by tc_layer_pack
 int launch_tc_layer(const void* layer_img_base, int layer, float* h, const void* qkv, const void* kvx, const float* mod3,
                     int mod_stride, int B, int T, int S, int stop_phase, cudaStream_t st);
-// fp32 row-major [R][lda] (first K columns) -> bf16 chunk-major [K/8][R][8]
-int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, cudaStream_t st);
+// fp32 row-major [R][lda] (first K columns) -> 16-bit chunk-major [K/8][R][8]: bf16, columns >= f16_from_col as f16
+int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, int f16_from_col, cudaStream_t st);
 }
 }  // namespace edtts

@@ -13,6 +13,7 @@
 // operand tile in with one bulk copy per slab and no register pass.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace edtts {
@@ -43,11 +44,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must become a trapped launch (error code at the next
-// CUDA call), never a hung GPU.
+// CUDA call), never a hung GPU.  (-DEDTTS_MBAR_DEBUG prints the barrier before trapping.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 24)) {
-      printf("edtts: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+    if (spin > (1u << 22)) {
+#ifdef EDTTS_MBAR_DEBUG
+      printf("edtts: mbarrier wait timed out (block %d thread %d, barrier @%u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
@@ -152,6 +156,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
       "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // ---- misc ---------------------------------------------------------------------------------
@@ -181,6 +192,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo_b
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t M, uint32_t N, bool b_mn_major = false) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// same with f16 operands (format code 0)
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N, bool b_mn_major = false) {
+  return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread for the whole CTA.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           bool accumulate) {
@@ -205,6 +220,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ uint4 pack_bf16x8(const float* v) {
   return make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  const __half2 v = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+__device__ __forceinline__ uint4 pack_f16x8(const float* v) {
+  return make_uint4(pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
 }
 
 }  // namespace tc

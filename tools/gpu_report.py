@@ -151,7 +151,7 @@ def vq():
               f"oracle32 vs 64 {(r32 != r64).sum().item()}")
 
 
-def hidden(shapes=((2, 100), (1, 37), (3, 400))):
+def hidden(shapes=((2, 100), (1, 37), (3, 400), (44, 400))):
     """Residual stream after partial / whole transformer blocks: fused kernel and separate launches vs the oracle."""
     import torch.nn.functional as F
     cfg, sd, dec, sched, inf = make_model("bf16")
