@@ -2,6 +2,7 @@
 #include "tc_path.cuh"
 #include "tc_layer.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace edtts {
 namespace tc {
@@ -11,15 +12,25 @@ constexpr int64_t LY_IMG_W_BYTES = (int64_t)LY_NCHUNK * LY_WCHUNK;
 constexpr int64_t LY_IMG_BYTES = LY_IMG_W_BYTES + LC_COUNT * 4;          // 465,920 (128-byte multiple)
 static_assert(LY_IMG_BYTES % 128 == 0, "layer image alignment");
 
-int64_t tc_layer_packed_bytes() { return NL * LY_IMG_BYTES; }
+// extras behind the NL block images: in_proj [10][160][8], out_proj [20][80][8], then per block attn.qkv as 3 chunks
+constexpr int64_t LY_EXTRA_OFF = NL * LY_IMG_BYTES;
+constexpr int64_t LY_EX_IN = 0, LY_EX_OUT = LY_WCHUNK / 2, LY_EX_QKV = LY_WCHUNK;
+constexpr int64_t LY_EXTRA_BYTES = LY_EX_QKV + (int64_t)NL * 3 * LY_WCHUNK;
+int64_t tc_layer_packed_bytes() { return LY_EXTRA_OFF + LY_EXTRA_BYTES; }
 
-// dst[c][n][j] = src[(row0 + n) * ld + col0 + 8 c + j]   (160 x 160 block of an nn.Linear weight)
-__global__ void pack_chunk_kernel(const float* __restrict__ src, int ld, int row0, int col0,
+// dst[c][n][j] = src[(row0 + n) * ld + col0 + 8 c + j], n < nrows, c < kcols / 8   (block of an nn.Linear weight)
+__global__ void pack_chunk_kernel(const float* __restrict__ src, int ld, int row0, int col0, int nrows, int kcols,
                                   __nv_bfloat16* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 160 * 160) return;
-  const int j = i & 7, n = (i >> 3) % 160, c = (i >> 3) / 160;
+  if (i >= nrows * kcols) return;
+  const int j = i & 7, n = (i >> 3) % nrows, c = (i >> 3) / nrows;
   dst[i] = __float2bfloat16_rn(src[(int64_t)(row0 + n) * ld + col0 + 8 * c + j]);
+}
+static int pack_chunk(const float* src, int ld, int row0, int col0, int nrows, int kcols, void* dst, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  pack_chunk_kernel<<<(nrows * kcols + 255) / 256, 256, 0, st>>>(src, ld, row0, col0, nrows, kcols,
+                                                                reinterpret_cast<__nv_bfloat16*>(dst));
+  return check_launch("pack_chunk");
 }
 
 __global__ void pack_layer_consts_kernel(const edtts_layer_weights L, float* __restrict__ dst) {
@@ -48,10 +59,7 @@ int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st) {
         {L.ffn0_w, H, 0, 0},        {L.ffn0_w, H, FFN, 0},       {L.ffn0_w, H, 160, 0},
         {L.ffn0_w, H, FFN + 160, 0}, {L.ffn3_w, FFN, 0, 0},      {L.ffn3_w, FFN, 0, 160}};
     for (int c = 0; c < LY_NCHUNK; ++c) {
-      LaunchScope ls(KC_TC_MISC, st);
-      pack_chunk_kernel<<<(160 * 160 + 255) / 256, 256, 0, st>>>(src[c].p, src[c].ld, src[c].row0, src[c].col0,
-                                                                 reinterpret_cast<__nv_bfloat16*>(img + (int64_t)c * LY_WCHUNK));
-      int rc = check_launch("pack_chunk");
+      int rc = pack_chunk(src[c].p, src[c].ld, src[c].row0, src[c].col0, 160, 160, img + (int64_t)c * LY_WCHUNK, st);
       if (rc) return rc;
     }
     LaunchScope ls(KC_TC_MISC, st);
@@ -59,31 +67,68 @@ int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st) {
     int rc = check_launch("pack_layer_consts");
     if (rc) return rc;
   }
-  return EDTTS_OK;
+  uint8_t* ex = base + LY_EXTRA_OFF;
+  int rc = pack_chunk(w->in_proj_w, M, 0, 0, H, M, ex + LY_EX_IN, st);
+  if (!rc) rc = pack_chunk(w->out_proj_w, H, 0, 0, M, H, ex + LY_EX_OUT, st);
+  for (int l = 0; l < NL && !rc; ++l)
+    for (int c = 0; c < 3 && !rc; ++c)
+      rc = pack_chunk(w->layers[l].attn_qkv_w, H, 160 * c, 0, 160, 160, ex + LY_EX_QKV + (int64_t)(3 * l + c) * LY_WCHUNK, st);
+  return rc;
 }
 
-int launch_tc_layer(const void* layer_img_base, int layer, float* h, const void* qkv, const void* kvx,
-                    const float* mod3, int mod_stride, int B, int T, int S, int stop_phase, cudaStream_t st) {
+// One launch of the fused kernel.  layer = -1: head (in_proj + pe); otherwise transformer block `layer`.
+// tail: LT_NONE / LT_QKV (norm1 + QKV of block layer+1, written to qkv_out) / LT_FINAL (final_norm + out_proj + step).
+int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, int layer, int tail, float* hc,
+                    const void* qkv_in, void* qkv_out, const void* kvx, const float* mod, const float* x_t,
+                    const edtts_step_args* step, int B, int T, int S, int stop_phase, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
       return check_launch("tc_layer smem attribute");
     configured = true;
   }
-  const uint8_t* img = reinterpret_cast<const uint8_t*>(layer_img_base) + (int64_t)layer * LY_IMG_BYTES;
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(layer_img_base);
+  const uint8_t* ex = base + LY_EXTRA_OFF;
+  const int mod_stride = 2 * NL * 2 * H;                  // mod[b][2 l + {0: norm1, 1: norm3}][scale 160 | shift 160]
   LayerArgs a;
-  a.h = h;
-  a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv);
-  a.kvx = reinterpret_cast<const __nv_bfloat16*>(kvx);
-  a.wimg = reinterpret_cast<const __nv_bfloat16*>(img);
-  a.consts = reinterpret_cast<const float*>(img + LY_IMG_W_BYTES);
-  a.mod3 = mod3;
+  memset(&a, 0, sizeof(a));
+  a.mode = layer < 0 ? LM_HEAD : LM_BLOCK;
+  a.tail = tail;
+  a.hc = hc;
   a.mod_stride = mod_stride;
   a.R = (int64_t)B * T;
   a.RS = (int64_t)B * S;
   a.B = B; a.T = T; a.S = S;
   a.tiles_per_utt = (T + 127) / 128;
   a.scale_log2e = 1.4426950408889634f / sqrtf((float)HD);
+  a.x_t = x_t;
+  if (layer >= 0) {
+    const uint8_t* img = base + (int64_t)layer * LY_IMG_BYTES;
+    a.qkv = reinterpret_cast<const __nv_bfloat16*>(qkv_in);
+    a.kvx = reinterpret_cast<const __nv_bfloat16*>(kvx);
+    a.wimg = reinterpret_cast<const __nv_bfloat16*>(img);
+    a.consts = reinterpret_cast<const float*>(img + LY_IMG_W_BYTES);
+    a.mod3 = mod + (int64_t)(2 * layer + 1) * 2 * H;
+  } else {
+    a.w_in = reinterpret_cast<const __nv_bfloat16*>(ex + LY_EX_IN);
+    a.in_b = w->in_proj_b;
+    a.pe = w->pos_pe;
+  }
+  if (tail == LT_QKV) {
+    const int nl = layer + 1;
+    EDTTS_REQUIRE(nl < NL && qkv_out, EDTTS_EINVAL, "tc_layer: QKV tail after block %d", layer);
+    a.w_qkv = reinterpret_cast<const __nv_bfloat16*>(ex + LY_EX_QKV + (int64_t)3 * nl * LY_WCHUNK);
+    a.n1w = w->layers[nl].norm1_norm_w;
+    a.mod1 = mod + (int64_t)(2 * nl) * 2 * H;
+    a.qkv_out = reinterpret_cast<__nv_bfloat16*>(qkv_out);
+  } else if (tail == LT_FINAL) {
+    EDTTS_REQUIRE(step && x_t, EDTTS_EINVAL, "tc_layer: final tail needs the step arguments");
+    a.w_out = reinterpret_cast<const __nv_bfloat16*>(ex + LY_EX_OUT);
+    a.fn_w = w->final_norm_w;
+    a.fn_b = w->final_norm_b;
+    a.out_b = w->out_proj_b;
+    a.step = *step;
+  }
   a.stop_phase = stop_phase;
   a.phase_clocks = nullptr;
   static long long* clk_buf = nullptr;
@@ -96,16 +141,30 @@ int launch_tc_layer(const void* layer_img_base, int layer, float* h, const void*
   LaunchScope ls(KC_TC_LAYER, st);
   tc_layer_kernel<<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
   if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
-    long long hc[24];
-    cudaMemcpy(hc, clk_buf, sizeof(hc), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc_layer clocks] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3+store %lld\n",
-            hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7]);
+    long long hc_[24];
+    cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc_layer clocks L%d] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3+tail %lld\n",
+            layer, hc_[0], hc_[1], hc_[2], hc_[3], hc_[4], hc_[5], hc_[6], hc_[7]);
     for (int k = 1; k < 3; ++k)
       fprintf(stderr, "[tc_layer %s] other %lld waitS+load %lld max %lld exp+store %lld arriveP %lld - %lld head %lld waitO %lld\n",
-              k == 1 ? "window" : "cross ", hc[8 * k], hc[8 * k + 1], hc[8 * k + 2], hc[8 * k + 3], hc[8 * k + 4], hc[8 * k + 5],
-              hc[8 * k + 6], hc[8 * k + 7]);
+              k == 1 ? "window" : "cross ", hc_[8 * k], hc_[8 * k + 1], hc_[8 * k + 2], hc_[8 * k + 3], hc_[8 * k + 4],
+              hc_[8 * k + 5], hc_[8 * k + 6], hc_[8 * k + 7]);
   }
   return check_launch("tc_layer");
+}
+
+// chunk-major fp32 [40][R][4] -> row-major [R][160] (test hook)
+__global__ void unpack_hc_kernel(const float* __restrict__ hc, float* __restrict__ h, int64_t R) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one float4
+  if (i >= R * 40) return;
+  const int64_t r = i % R;
+  const int c = (int)(i / R);
+  *reinterpret_cast<float4*>(h + r * H + 4 * c) = *reinterpret_cast<const float4*>(hc + i * 4);
+}
+int unpack_hc(const float* hc, float* h, int64_t R, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  unpack_hc_kernel<<<(unsigned)((R * 40 + 255) / 256), 256, 0, st>>>(hc, h, R);
+  return check_launch("unpack_hc");
 }
 
 }  // namespace tc

@@ -37,6 +37,7 @@
 // (51,200 B, pre-packed UMMA operand images) through two slots, prefetched one GEMM ahead.
 #pragma once
 #include "umma.cuh"
+#include "tc_path.cuh"
 
 namespace edtts {
 namespace tc {
@@ -56,7 +57,9 @@ constexpr int LY_PBUF = (LY_KB / 8) * LY_SLAB;   // P block: 128 frames x 64 key
 // per-layer constant vector (floats), packed by tc_layer.cu
 constexpr int LC_PROJ_B = 0, LC_N2W = 160, LC_N3W = 320, LC_F0B = 480, LC_F3B = 1120, LC_COUNT = 1280;
 // shared-memory copy: the above + the tile's AdaLN vectors g3 = w3 * (1 + scale), sh3 = shift
-constexpr int LS_G3 = 1280, LS_SH3 = 1440, LS_COUNT = 1600;
+constexpr int LS_G3 = 1280, LS_SH3 = 1440;
+// tail: bias added to the finished h (b3 or in_proj.bias), next norm's (gain, shift) or final_norm (w, b), out_proj.bias
+constexpr int LS_TB = 1600, LS_TG = 1760, LS_TS = 1920, LS_OB = 2080, LS_COUNT = 2160;
 
 // shared memory map (bytes)
 constexpr int LO_A = 0;                                   // 21 slabs: A operand / Q / attention output
@@ -70,7 +73,7 @@ constexpr int LO_KV = LO_P + 4 * LY_PBUF;                 //   attention: wg: K0
 constexpr int LO_X_END = LO_KV + 2 * (LY_KST + LY_VST) * LY_KBUF;
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
-constexpr int LO_BAR = LO_RED + 2 * 128 * 4;
+constexpr int LO_BAR = LO_RED + 4 * 128 * 4;
 constexpr int LY_NBAR = 8 + 2 * 20;
 constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
 static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay region");
@@ -86,10 +89,14 @@ constexpr uint32_t TM_H = 0;                              // residual stream, 16
 constexpr uint32_t TM_G = 160;                            // GEMM chain scratch, 320 columns
 constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention, per warpgroup: S0 (64) | S1 (64) | O (48)
 
+
 struct LayerArgs {
-  float* h;                          // [R][160] fp32 residual stream, in place
-  const __nv_bfloat16* qkv;          // [60][R][8] chunk-major q | k | v of this layer (finite slack around it)
-  const __nv_bfloat16* kvx;          // [40][RS][8] chunk-major context k | v of this layer
+  int mode;                          // LM_BLOCK: one transformer block; LM_HEAD: h = in_proj(x_t) + pe instead (decoder.py:96-97)
+  int tail;                          // what follows on the finished h rows: LT_QKV = the NEXT block's norm1 + QKV projection,
+                                     // LT_FINAL = final_norm + out_proj + update rule (decoder.py:108-109, schedule.py)
+  float* hc;                         // residual stream between launches, chunk-major fp32 [40][R][4], in place
+  const __nv_bfloat16* qkv;          // [60][R][8] chunk-major q | k | v (f16) of this block (finite slack around it)
+  const __nv_bfloat16* kvx;          // [40][RS][8] chunk-major context k | v (f16) of this block
   const __nv_bfloat16* wimg;         // LY_NCHUNK weight chunks
   const float* consts;               // LC_COUNT floats
   const float* mod3;                 // norm3 (scale | shift) of utterance 0; + b * mod_stride
@@ -98,6 +105,22 @@ struct LayerArgs {
   int B, T, S;
   int tiles_per_utt;
   float scale_log2e;                 // head_dim^-0.5 * log2(e)
+  // LM_HEAD
+  const float* x_t;                  // [R][80] fp32 (also the x_t of the fused update rule, LT_FINAL)
+  const __nv_bfloat16* w_in;         // in_proj.weight as [10][160][8]
+  const float* in_b;                 // [160]
+  const float* pe;                   // pos_emb.pe [>= T][160]
+  // LT_QKV
+  const __nv_bfloat16* w_qkv;        // 3 chunks (q, k, v) of the next block's attn.qkv.weight
+  const float* n1w;                  // next block's norm1.norm.weight [160]
+  const float* mod1;                 // next block's norm1 (scale | shift) of utterance 0; + b * mod_stride
+  __nv_bfloat16* qkv_out;            // [60][R][8] of the next block
+  // LT_FINAL
+  const __nv_bfloat16* w_out;        // out_proj.weight as [20][80][8]
+  const float* fn_w;                 // final_norm.weight / bias [160]
+  const float* fn_b;
+  const float* out_b;                // [80]
+  edtts_step_args step;
   int stop_phase;                    // debug: 1 = stop after attention + proj, 2 = after cross, 0 = whole block
   long long* phase_clocks;           // debug: [gridDim.x][24] cycles per phase / attention section (thread 0), or null
 };
@@ -113,6 +136,15 @@ __device__ __forceinline__ void ly_issue_gemm(uint32_t d_tmem, uint32_t a_addr, 
   for (int ks = 0; ks < 10; ++ks)
     umma_bf16(d_tmem, make_desc(a_addr + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(w_addr + ks * 2 * LY_WSLAB, LY_WSLAB, 128),
               IDESC, accumulate || ks > 0);
+}
+
+// D[128 x n] (+)= A[128 x 16 ksteps] * W[n x 16 ksteps]^T; W slabs are n rows of 16 bytes
+__device__ __forceinline__ void ly_issue_gemm_ex(uint32_t d_tmem, uint32_t a_addr, uint32_t w_addr, int ksteps, int n,
+                                                 bool accumulate) {
+  const uint32_t idesc = make_idesc(128, (uint32_t)n);
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma_bf16(d_tmem, make_desc(a_addr + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(w_addr + ks * 2 * n * 16, n * 16, 128), idesc,
+              accumulate || ks > 0);
 }
 
 struct LyTile {
@@ -500,7 +532,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   // finite shared memory everywhere (stale rows enter MMAs as 0 * x), zero pad slabs
   for (int i = tid * 16; i < LO_BAR; i += LY_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  for (int i = tid; i < LC_COUNT; i += LY_THREADS) sC[i] = a.consts[i];
+  if (a.mode == LM_BLOCK)
+    for (int i = tid; i < LC_COUNT; i += LY_THREADS) sC[i] = a.consts[i];
   if (tid == 0) {
     for (int i = 0; i < LB_WG0; ++i) mbar_init(bars + i, 1);
     for (int w = 0; w < 2; ++w) {
@@ -528,7 +561,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       const bool is_mma = (warp - 8) & 1;
       uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
       uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;       // TMA: c0 = K loads, c1 = V loads; MMA: S ops, PV ops, heads
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < ntiles && a.mode == LM_BLOCK; tile += gridDim.x) {
         const LyTile tl = ly_tile(a, tile);
         for (int ph = 0; ph < 2; ++ph) {
           if (ph == 1 && a.stop_phase == 1) break;
@@ -557,32 +590,32 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
   uint32_t ph_w0 = 0, ph_w1 = 0, ph_q = 0, ph_g = 0, cs = 0, cp = 0, co = 0;
   auto csync = [&]() { named_bar_sync(3, LY_CTHREADS); };
-  auto load_w = [&](int chunk, uint8_t* slot, uint64_t* bar) {   // tid 0 only
-    mbar_expect_tx(bar, LY_WCHUNK);
-    bulk_g2s(slot, a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, bar);
+  auto load_w = [&](const __nv_bfloat16* src, int bytes, uint8_t* slot, uint64_t* bar) {   // tid 0 only
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(slot, src, bytes, bar);
   };
+  auto load_wc = [&](int chunk, uint8_t* slot, uint64_t* bar) { load_w(a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, slot, bar); };
   auto gemm_wait = [&]() {
     mbar_wait(bar_g, ph_g);
     ph_g ^= 1;
     tc_fence_after();
   };
-  // store h (TMEM, + optional bias) of the valid rows to HBM
-  auto store_h = [&](const LyTile& tl, const float* bias) {
+  // first weight chunk of a tile (slot 0)
+  auto load_first = [&]() {
+    if (a.mode == LM_HEAD) load_w(a.w_in, LY_WCHUNK / 2, sW0, bar_w0);
+    else load_wc(WC_PROJ, sW0, bar_w0);
+  };
+  // h (TMEM) of the valid rows -> HBM, chunk-major (debug stops only; the tail stores from registers)
+  auto store_h = [&](const LyTile& tl) {
 #pragma unroll 1
     for (int i = 0; i < 5; ++i) {
       float v[16];
       tmem_ld16(trow + TM_H + cb + 16 * i, v);
       if (row < tl.nq) {
-        float4* dst = reinterpret_cast<float4*>(a.h + (tl.row0 + row) * H + cb + 16 * i);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float4 o = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          if (bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + cb + 16 * i + 4 * q);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          }
-          dst[q] = o;
-        }
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + 4 * i + q) * a.R + tl.row0 + row) * 4) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
   };
@@ -596,25 +629,75 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     pc[i] += now_ - pc_last;                          \
     pc_last = now_;                                   \
   }
+  // tail constants that do not depend on the tile
+  if (tid < H) {
+    sC[LS_TB + tid] = a.mode == LM_HEAD ? a.in_b[tid] : sC[LC_F3B + tid];
+    if (a.tail == LT_FINAL) {
+      sC[LS_TG + tid] = a.fn_w[tid];
+      sC[LS_TS + tid] = a.fn_b[tid];
+      if (tid < M) sC[LS_OB + tid] = a.out_b[tid];
+    }
+  }
   if (tid == 0 && blockIdx.x < ntiles) {
-    load_w(WC_PROJ, sW0, bar_w0);
-    mbar_arrive(bar_kvgo);                                // K/V buffers are free: first window phase may load
+    load_first();
+    if (a.mode == LM_BLOCK) mbar_arrive(bar_kvgo);        // K/V buffers are free: first window phase may load
   }
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const LyTile tl = ly_tile(a, tile);
+    const bool more = tile + (int)gridDim.x < ntiles;
 
-    // ---- tile prologue: Q -> sA, h -> TMEM, AdaLN vectors ------------------------------------------------------
+    if (tid < H) {                                        // per-utterance AdaLN vectors: gain = w * (1 + scale), shift
+      if (a.mode == LM_BLOCK) {
+        const float* m = a.mod3 + (int64_t)tl.b * a.mod_stride;
+        sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
+        sC[LS_SH3 + tid] = m[H + tid];
+      }
+      if (a.tail == LT_QKV) {
+        const float* m = a.mod1 + (int64_t)tl.b * a.mod_stride;
+        sC[LS_TG + tid] = a.n1w[tid] * (1.0f + m[tid]);
+        sC[LS_TS + tid] = m[H + tid];
+      }
+    }
+
+    if (a.mode == LM_HEAD) {
+      // ---- h = in_proj(x_t): x tile -> bf16 A operand (K = 80), one MMA chain into the h columns -----------------------
+      {
+        const float4* src = reinterpret_cast<const float4*>(a.x_t + (tl.row0 + row) * M + 40 * wg);
+        float4 x[10];
+#pragma unroll
+        for (int q = 0; q < 10; ++q) x[q] = row < tl.nq ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int g = 0; g < 5; ++g) {
+          const float o[8] = {x[2 * g].x, x[2 * g].y, x[2 * g].z, x[2 * g].w, x[2 * g + 1].x, x[2 * g + 1].y, x[2 * g + 1].z, x[2 * g + 1].w};
+          *reinterpret_cast<uint4*>(sA + (5 * wg + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      csync();
+      if (tid == 0) {
+        mbar_wait(bar_w0, ph_w0);
+        tc_fence_after();
+        ly_issue_gemm_ex(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), M / 16, H, false);
+        umma_commit(bar_g);
+      }
+      ph_w0 ^= 1;
+      gemm_wait();
+      LY_PHASE(0)
+    } else {
+    // ---- tile prologue: Q -> sA, h -> TMEM ---------------------------------------------------------------------------
     if (tid == 0) {
       mbar_expect_tx(bar_q, 20 * tl.nq * 16);
 #pragma unroll 1
       for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * a.R + tl.row0) * 8, tl.nq * 16, bar_q);
     }
     {
-      const float4* src = reinterpret_cast<const float4*>(a.h + (tl.row0 + row) * H + cb);
+      const float* src = a.hc + ((int64_t)(cb / 4) * a.R + tl.row0 + row) * 4;
       float4 x[20];
 #pragma unroll
-      for (int q = 0; q < 20; ++q) x[q] = row < tl.nq ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 0; q < 20; ++q)
+        x[q] = row < tl.nq ? *reinterpret_cast<const float4*>(src + (int64_t)q * a.R * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         float v[16];
@@ -625,11 +708,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         tmem_st16(trow + TM_H + cb + 16 * i, v);
       }
       tmem_st_wait();
-    }
-    if (tid < H) {
-      const float* m = a.mod3 + (int64_t)tl.b * a.mod_stride;
-      sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
-      sC[LS_SH3 + tid] = m[H + tid];
     }
     ly_init_pads(smem, tid);
     fence_proxy_async();
@@ -648,7 +726,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     // ---- h += O Wproj^T ------------------------------------------------------------------------------------------
     if (tid == 0) {
       if (a.stop_phase != 1) mbar_arrive(bar_kvgo);       // context K/V may stream in during the GEMM chain
-      load_w(WC_Q, sW1, bar_w1);
+      load_wc(WC_Q, sW1, bar_w1);
       mbar_wait(bar_w0, ph_w0);
       tc_fence_after();
       ly_issue_gemm(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), true);
@@ -656,7 +734,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0) load_w(WC_OUT, sW0, bar_w0);
+    if (tid == 0) load_wc(WC_OUT, sW0, bar_w0);
 
     // ---- n2 = RMSNorm(h + b_proj) * w2 -> sA ; h + b_proj back to TMEM ---------------------------------------------
     {
@@ -689,14 +767,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     csync();
     if (a.stop_phase == 1) {
       tc_fence_after();
-      store_h(tl, nullptr);
+      store_h(tl);
       // drain the prefetches so that the barrier phases stay consistent
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
       ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
-      if (tid == 0 && tile + gridDim.x < ntiles) {
-        load_w(WC_PROJ, sW0, bar_w0);
+      if (tid == 0 && more) {
+        load_first();
         mbar_arrive(bar_kvgo);
       }
       continue;
@@ -732,7 +810,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
 
     // ---- h += O Wout^T -----------------------------------------------------------------------------------------------
     if (tid == 0) {
-      load_w(WC_F0_X0, sW1, bar_w1);
+      load_wc(WC_F0_X0, sW1, bar_w1);
       mbar_wait(bar_w0, ph_w0);
       tc_fence_after();
       ly_issue_gemm(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), true);
@@ -740,7 +818,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0) load_w(WC_F0_G0, sW0, bar_w0);
+    if (tid == 0) load_wc(WC_F0_G0, sW0, bar_w0);
 
     // ---- n3 = AdaRMSNorm(h) -> sA --------------------------------------------------------------------------------------
     {
@@ -769,13 +847,13 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     csync();
     if (a.stop_phase == 2) {
       tc_fence_after();
-      store_h(tl, nullptr);
+      store_h(tl);
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
       ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
-      if (tid == 0 && tile + gridDim.x < ntiles) {
-        load_w(WC_PROJ, sW0, bar_w0);
+      if (tid == 0 && more) {
+        load_first();
         mbar_arrive(bar_kvgo);
       }
       continue;
@@ -797,8 +875,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       ph_w0 ^= 1;
       gemm_wait();
       if (tid == 0) {
-        load_w(half == 0 ? WC_F0_X1 : WC_F3_K0, sW1, bar_w1);
-        load_w(half == 0 ? WC_F0_G1 : WC_F3_K1, sW0, bar_w0);
+        load_wc(half == 0 ? WC_F0_X1 : WC_F3_K0, sW1, bar_w1);
+        load_wc(half == 0 ? WC_F0_G1 : WC_F3_K1, sW0, bar_w0);
       }
       uint8_t* dst = half == 0 ? sU : sA;                 // sA (n3) is dead once the second half's MMAs retired
       const float* bx = sC + LC_F0B + half * 320 + cb;
@@ -819,7 +897,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     LY_PHASE(6)
 
-    // ---- h += u W3^T ; h + b3 -> HBM --------------------------------------------------------------------------------------
+    // ---- h += u W3^T --------------------------------------------------------------------------------------------------------
     if (tid == 0) {
       mbar_wait(bar_w1, ph_w1);
       mbar_wait(bar_w0, ph_w0);
@@ -831,11 +909,178 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     ph_w1 ^= 1;
     ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0 && tile + gridDim.x < ntiles) {
-      load_w(WC_PROJ, sW0, bar_w0);
-      mbar_arrive(bar_kvgo);                              // overlay region is free: next tile's window K/V may load
+    if (tid == 0 && more) mbar_arrive(bar_kvgo);          // overlay K/V region is free: next tile's window K/V may load
+    }   // LM_BLOCK
+
+    // =============== tail: the finished h rows leave the SM; what consumes them next runs right here ===============
+    if (tid == 0) {                                       // both weight slots are free
+      if (a.tail == LT_QKV) {
+        load_w(a.w_qkv, LY_WCHUNK, sW1, bar_w1);
+        load_w(a.w_qkv + LY_WCHUNK / 2, LY_WCHUNK, sW0, bar_w0);
+      } else if (a.tail == LT_FINAL) {
+        load_w(a.w_out, LY_WCHUNK / 2, sW1, bar_w1);
+      }
     }
-    store_h(tl, sC + LC_F3B);
+    {
+      float v[80];
+      float s1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        tmem_ld16(trow + TM_H + cb + 16 * i, v + 16 * i);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[16 * i + j] += sC[LS_TB + cb + 16 * i + j];
+      }
+      if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
+        const float4* pp = reinterpret_cast<const float4*>(a.pe + (int64_t)(tl.t0 + row) * H + cb);
+#pragma unroll
+        for (int q = 0; q < 20; ++q) {
+          const float4 pv = pp[q];
+          v[4 * q] += pv.x; v[4 * q + 1] += pv.y; v[4 * q + 2] += pv.z; v[4 * q + 3] += pv.w;
+        }
+      }
+      if (a.tail != LT_FINAL && row < tl.nq) {
+#pragma unroll
+        for (int q = 0; q < 20; ++q)
+          *reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + q) * a.R + tl.row0 + row) * 4) =
+              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+      if (a.tail != LT_NONE) {
+        // next norm: AdaRMSNorm (LT_QKV) or LayerNorm (LT_FINAL, exact two-step variance) -> bf16 A operand
+#pragma unroll
+        for (int j = 0; j < 80; ++j) s1 += (a.tail == LT_FINAL) ? v[j] : v[j] * v[j];
+        sRed[wg * 128 + row] = s1;
+        csync();
+        const float tot = sRed[row] + sRed[128 + row];
+        float mean = 0.f, rstd;
+        if (a.tail == LT_FINAL) {
+          mean = tot * (1.0f / H);
+          float s2 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 80; ++j) s2 = fmaf(v[j] - mean, v[j] - mean, s2);
+          sRed[256 + wg * 128 + row] = s2;
+          csync();
+          rstd = rsqrtf((sRed[256 + row] + sRed[384 + row]) * (1.0f / H) + 1e-5f);
+        } else {
+          rstd = rsqrtf(tot * (1.0f / H) + 1e-6f);
+        }
+#pragma unroll
+        for (int g = 0; g < 10; ++g) {
+          float o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            o[j] = fmaf((v[8 * g + j] - mean) * rstd, sC[LS_TG + cb + 8 * g + j], sC[LS_TS + cb + 8 * g + j]);
+          *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
+        }
+        fence_proxy_async();
+      }
+    }
+    tc_fence_before();
+    csync();
+
+    if (a.tail == LT_QKV) {
+      // ---- q | k | v of the next block: three 160-column chunks into TMEM columns 0..479 (h is dead) -------------
+      if (tid == 0) {
+        mbar_wait(bar_w1, ph_w1);
+        mbar_wait(bar_w0, ph_w0);
+        tc_fence_after();
+        ly_issue_gemm(tmem_base + 0, smem_u32(sA), smem_u32(sW1), false);
+        ly_issue_gemm(tmem_base + 160, smem_u32(sA), smem_u32(sW0), false);
+        umma_commit(bar_g);
+      }
+      ph_w1 ^= 1;
+      ph_w0 ^= 1;
+      gemm_wait();
+      if (tid == 0) {
+        load_w(a.w_qkv + 2 * (LY_WCHUNK / 2), LY_WCHUNK, sW1, bar_w1);
+        mbar_wait(bar_w1, ph_w1);
+        tc_fence_after();
+        ly_issue_gemm(tmem_base + 320, smem_u32(sA), smem_u32(sW1), false);
+        umma_commit(bar_g);
+        if (more) load_first();                           // slot 0: first chunk of the next tile
+      }
+      ph_w1 ^= 1;
+#pragma unroll 1
+      for (int part = 0; part < 3; ++part) {              // q, k as bf16; v as f16 (P V operand)
+        if (part == 2) gemm_wait();
+#pragma unroll 1
+        for (int i = 0; i < 5; ++i) {
+          float v[16];
+          tmem_ld16(trow + 160 * part + cb + 16 * i, v);
+          if (row < tl.nq) {
+            __nv_bfloat16* o = a.qkv_out + ((int64_t)(20 * part + cb / 8 + 2 * i) * a.R + tl.row0 + row) * 8;
+            *reinterpret_cast<uint4*>(o) = part == 2 ? pack_f16x8(v) : pack_bf16x8(v);
+            *reinterpret_cast<uint4*>(o + a.R * 8) = part == 2 ? pack_f16x8(v + 8) : pack_bf16x8(v + 8);
+          }
+        }
+      }
+    } else if (a.tail == LT_FINAL) {
+      // ---- eps = out_proj(final_norm(h)) with the update rule applied in registers -----------------------------------
+      if (tid == 0) {
+        mbar_wait(bar_w1, ph_w1);
+        tc_fence_after();
+        ly_issue_gemm_ex(tmem_base + 0, smem_u32(sA), smem_u32(sW1), H / 16, M, false);
+        umma_commit(bar_g);
+      }
+      ph_w1 ^= 1;
+      gemm_wait();
+      if (tid == 0 && more) load_first();
+      const edtts_step_args& sa = a.step;
+      float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
+      if (sa.mode != EDTTS_STEP_EPS && row < tl.nq) {
+        const int64_t tt = sa.t[tl.b];
+        ab_t = sa.alpha_bar[tt];
+        if (sa.mode == EDTTS_STEP_DDIM) {
+          const int64_t tp = sa.t_prev[tl.b];
+          ab_p = tp >= 0 ? sa.alpha_bar[tp] : 1.0f;
+        } else {
+          al = sa.alphas[tt];
+          be = sa.betas[tt];
+          pv = sa.posterior_var[tt];
+          nzm = tt > 0 ? 1.0f : 0.0f;
+        }
+      }
+      const int c0 = 40 * wg;                             // this thread's 40 of the 80 mel columns
+      float e[40];
+      tmem_ld32(trow + c0, e);
+      tmem_ld8(trow + c0 + 32, e + 32);
+      if (row < tl.nq) {
+        const int64_t o = (tl.row0 + row) * M + c0;
+#pragma unroll
+        for (int j = 0; j < 40; ++j) e[j] += sC[LS_OB + c0 + j];
+        if (sa.eps_out) {
+#pragma unroll
+          for (int q = 0; q < 10; ++q)
+            reinterpret_cast<float4*>(sa.eps_out + o)[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
+        }
+        if (sa.mode == EDTTS_STEP_DDIM) {
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            float4 xp, x0;
+            ddim_update(x.x, e[4 * q], 0.f, ab_t, ab_p, 0.f, xp.x, x0.x);
+            ddim_update(x.y, e[4 * q + 1], 0.f, ab_t, ab_p, 0.f, xp.y, x0.y);
+            ddim_update(x.z, e[4 * q + 2], 0.f, ab_t, ab_p, 0.f, xp.z, x0.z);
+            ddim_update(x.w, e[4 * q + 3], 0.f, ab_t, ab_p, 0.f, xp.w, x0.w);
+            if (sa.x0_out) reinterpret_cast<float4*>(sa.x0_out + o)[q] = x0;
+            if (sa.write_x_prev && sa.x_prev_out) reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
+          }
+        } else if (sa.mode == EDTTS_STEP_DDPM) {
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            const float4 nz = reinterpret_cast<const float4*>(sa.noise + o)[q];
+            float4 xp;
+            xp.x = ddpm_update(x.x, e[4 * q], nz.x, al, ab_t, be, pv, nzm);
+            xp.y = ddpm_update(x.y, e[4 * q + 1], nz.y, al, ab_t, be, pv, nzm);
+            xp.z = ddpm_update(x.z, e[4 * q + 2], nz.z, al, ab_t, be, pv, nzm);
+            xp.w = ddpm_update(x.w, e[4 * q + 3], nz.w, al, ab_t, be, pv, nzm);
+            reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
+          }
+        }
+      }
+    } else {
+      if (tid == 0 && more) load_first();
+    }
     tc_fence_before();
     csync();
     LY_PHASE(7)

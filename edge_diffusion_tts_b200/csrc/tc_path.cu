@@ -178,7 +178,7 @@ using namespace tc;
 
 // ---- workspace ------------------------------------------------------------------------------
 struct TcWs {
-  int64_t h, qkv, q, o, u, total;
+  int64_t h, qkv, qkv2, q, o, u, total;
 };
 static TcWs tc_ws_layout(int64_t R) {
   TcWs w;
@@ -192,6 +192,8 @@ static TcWs tc_ws_layout(int64_t R) {
   take(ATT_PAD_BYTES);                 // finite (zeroed) slack below qkv for the band halo of row 0
   w.qkv = take(R * 3 * H * 2);
   take(ATT_PAD_BYTES);                 // and above the last row
+  w.qkv2 = take(R * 3 * H * 2);        // fused path: q | k | v of the next block (written while this one is read)
+  take(ATT_PAD_BYTES);
   w.q = take(R * H * 2);
   w.o = take(R * H * 2);
   w.u = take(R * FFN * 2);
@@ -214,7 +216,7 @@ static bool env_flag(const char* name, bool dflt) {
 // (tc_layer.cuh), otherwise 7 launches.  stop_phase != 0 stops the LAST block early (test hook, fused only).
 static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
                          void* workspace, int32_t B, int32_t T, int32_t S, int n_layers, int stop_phase, bool fused,
-                         cudaStream_t st) {
+                         const edtts_step_args* step, cudaStream_t st) {
   EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "decoder_step(bf16): weights.packed_bf16 is null; call "
                                               "edtts_pack_weights_bf16 first");
   const PackedOff po = packed_offsets();
@@ -231,8 +233,26 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
   int rc;
   // the halo slack must hold finite numbers (masked keys still enter P.V as 0 * v)
   if (cudaMemsetAsync(ws + wl.qkv - ATT_PAD_BYTES, 0, ATT_PAD_BYTES, st) != cudaSuccess ||
-      cudaMemsetAsync(ws + wl.qkv + align_up(R * 3 * H * 2, 256), 0, ATT_PAD_BYTES, st) != cudaSuccess)
+      cudaMemsetAsync(ws + wl.qkv + R * 3 * H * 2, 0, ATT_PAD_BYTES, st) != cudaSuccess ||
+      cudaMemsetAsync(ws + wl.qkv2 + R * 3 * H * 2, 0, ATT_PAD_BYTES, st) != cudaSuccess)
     return check_launch("tc workspace memset");
+  if (fused) {
+    // head: h = in_proj(x_t) + pe, q|k|v of block 0; then one launch per block, each also producing the next
+    // block's q|k|v (or, after the last block, final_norm + out_proj + the update rule when `step` is given)
+    void* qb[2] = {qkv, ws + wl.qkv2};
+    if ((rc = launch_tc_layer(w, pk + po.total, -1, n_layers > 0 ? tc::LT_QKV : tc::LT_NONE, h, nullptr, qb[0], nullptr, mod,
+                              x_t, nullptr, B, T, S, 0, st)))
+      return rc;
+    for (int l = 0; l < n_layers; ++l) {
+      const bool last = l == n_layers - 1;
+      const int tail = !last ? tc::LT_QKV : (step && stop_phase == 0 ? tc::LT_FINAL : tc::LT_NONE);
+      const __nv_bfloat16* kvl = reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H;
+      if ((rc = launch_tc_layer(w, pk + po.total, l, tail, h, qb[l & 1], qb[(l + 1) & 1], kvl, mod, x_t, step, B, T, S,
+                                last ? stop_phase : 0, st)))
+        return rc;
+    }
+    return EDTTS_OK;
+  }
   {  // h = in_proj(x_t) + pe[:T]
     TcGemmArgs g;
     g.amode = A_F32; g.A_f32 = x_t; g.R = R; g.T = T; g.W_img = img(po.in_proj); g.bias = w->in_proj_b;
@@ -249,12 +269,6 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
       g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H; g.mod_stride = 2 * NL * 2 * H;
       g.epi = TE_CHUNK; g.out_chunk = qkv; g.f16_from_chunk = 40;   // v is the f16 operand of P V
       if ((rc = launch_tc_gemm(g, H, 240, 2, st))) return rc;
-    }
-    if (fused) {
-      if ((rc = launch_tc_layer(pk + po.total, l, h, qkv, kvl, mod + (int64_t)(2 * l + 1) * 2 * H, 2 * NL * 2 * H, B, T, S,
-                                l == n_layers - 1 ? stop_phase : 0, st)))
-        return rc;
-      continue;
     }
     if ((rc = launch_tc_attn_window(qkv, o, B, T, st))) return rc;
     {  // h += attn.proj(o) + bias
@@ -300,8 +314,8 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
 int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,
                     const edtts_step_args* args, void* workspace, int32_t B, int32_t T, int32_t S, cudaStream_t st) {
   static const bool fused = env_flag("EDTTS_FUSED_LAYER", true);
-  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, NL, 0, fused, st);
-  if (rc) return rc;
+  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, NL, 0, fused, args, st);
+  if (rc || fused) return rc;
   const PackedOff po = packed_offsets();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
   const int64_t R = (int64_t)B * T;
@@ -322,10 +336,11 @@ int tc_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float
                    cudaStream_t st) {
   EDTTS_REQUIRE(n_layers >= 0 && n_layers <= NL && stop_phase >= 0 && stop_phase <= 2, EDTTS_EINVAL,
                 "test_hidden: n_layers=%d stop_phase=%d", n_layers, stop_phase);
-  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, n_layers, stop_phase, fused != 0, st);
+  int rc = tc_run_layers(w, x_t, mod, kv, workspace, B, T, S, n_layers, stop_phase, fused != 0, nullptr, st);
   if (rc) return rc;
   const int64_t R = (int64_t)B * T;
   const float* h = reinterpret_cast<const float*>(reinterpret_cast<uint8_t*>(workspace) + tc_ws_layout(R).h);
+  if (fused) return unpack_hc(h, h_out, R, st);           // the fused path keeps h chunk-major
   if (cudaMemcpyAsync(h_out, h, R * H * 4, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return check_launch("test_hidden copy");
   return EDTTS_OK;
 }

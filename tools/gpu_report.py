@@ -178,7 +178,7 @@ def hidden(shapes=((2, 100), (1, 37), (3, 400), (44, 400))):
         kv = dec.prepare_context(idx.to(DEV), None, T)
         w = dec._weights(T, S)
         nbytes = lib.edtts_decoder_workspace_bytes(B, T, S, _lib.PREC_BF16)
-        ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+        ws = torch.full((nbytes,), 0xFF, dtype=torch.uint8, device=DEV)   # NaN patterns: every byte read must have been written
         out = torch.zeros(B, T, 160, device=DEV)
         cases = [(1, 1), (1, 2), (1, 0), (4, 0)]
         for fused in (0, 1):
