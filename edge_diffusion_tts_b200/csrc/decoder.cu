@@ -39,49 +39,80 @@ int launch_attn_simt(const AttnArgs& a, int B, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 // Conditioning: t -> sinusoid -> Linear -> GELU -> Linear (+ step_emb) -> cond,
 // then the 8 AdaLayerNorm projections (decoder.py:77-80, transformer.py:64-66).
-// One block per utterance; a warp per output feature, lanes over the 160 inputs.
+// One block per CU utterances, so that every weight row fetched from L2 serves CU
+// dot products; a thread owns one output feature for 4 utterances at a time.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ float warp_dot160(const float* __restrict__ w, const float* __restrict__ x, int lane) {
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < 5; ++i) s = fmaf(w[lane + 32 * i], x[lane + 32 * i], s);
-  return warp_sum(s);
+constexpr int CU = 8;
+
+// acc[u] = bias + sum_k w[k] * x[u0 + u][k], u < 4; w is one nn.Linear row (160 floats)
+__device__ __forceinline__ void dot160x4(const float* __restrict__ w, const float (*x)[H], int u0, float bias, float* acc) {
+  float a0 = bias, a1 = bias, a2 = bias, a3 = bias;
+#pragma unroll 4
+  for (int k = 0; k < H; k += 4) {
+    const float4 wv = *reinterpret_cast<const float4*>(w + k);
+    const float4 x0 = *reinterpret_cast<const float4*>(&x[u0][k]);
+    const float4 x1 = *reinterpret_cast<const float4*>(&x[u0 + 1][k]);
+    const float4 x2 = *reinterpret_cast<const float4*>(&x[u0 + 2][k]);
+    const float4 x3 = *reinterpret_cast<const float4*>(&x[u0 + 3][k]);
+    a0 = fmaf(wv.x, x0.x, a0); a0 = fmaf(wv.y, x0.y, a0); a0 = fmaf(wv.z, x0.z, a0); a0 = fmaf(wv.w, x0.w, a0);
+    a1 = fmaf(wv.x, x1.x, a1); a1 = fmaf(wv.y, x1.y, a1); a1 = fmaf(wv.z, x1.z, a1); a1 = fmaf(wv.w, x1.w, a1);
+    a2 = fmaf(wv.x, x2.x, a2); a2 = fmaf(wv.y, x2.y, a2); a2 = fmaf(wv.z, x2.z, a2); a2 = fmaf(wv.w, x2.w, a2);
+    a3 = fmaf(wv.x, x3.x, a3); a3 = fmaf(wv.y, x3.y, a3); a3 = fmaf(wv.z, x3.z, a3); a3 = fmaf(wv.w, x3.w, a3);
+  }
+  acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
 }
 
 __global__ void __launch_bounds__(256) cond_kernel(const edtts_decoder_weights w, const int64_t* __restrict__ t,
                                                    const int64_t* __restrict__ step_idx, float* __restrict__ cond_out,
-                                                   float* __restrict__ mod_out) {
-  __shared__ float e[H], h1[H], c[H];
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const float tf = (float)t[b];
-  if (tid < H / 2) {
-    const float arg = tf * w.time_freqs[tid];        // embeddings.py:42-43
-    e[tid] = sinf(arg);
-    e[tid + H / 2] = cosf(arg);
+                                                   float* __restrict__ mod_out, int B) {
+  __shared__ __align__(16) float e[CU][H], h1[CU][H], c[CU][H];
+  const int tid = threadIdx.x;
+  const int b0 = blockIdx.x * CU;
+  const int nu = min(CU, B - b0);
+  for (int i = tid; i < CU * (H / 2); i += 256) {
+    const int u = i / (H / 2), k = i % (H / 2);
+    const float arg = u < nu ? (float)t[b0 + u] * w.time_freqs[k] : 0.f;   // embeddings.py:42-43
+    e[u][k] = sinf(arg);
+    e[u][k + H / 2] = cosf(arg);
   }
   __syncthreads();
-  for (int o = warp; o < H; o += 8) {
-    const float s = warp_dot160(w.time1_w + o * H, e, lane) + w.time1_b[o];
-    if (lane == 0) h1[o] = gelu_erf(s);
+  for (int it = tid; it < H * (CU / 4); it += 256) {
+    const int o = it % H, u0 = (it / H) * 4;
+    float acc[4];
+    dot160x4(w.time1_w + o * H, e, u0, w.time1_b[o], acc);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) h1[u0 + u][o] = gelu_erf(acc[u]);
   }
   __syncthreads();
-  for (int o = warp; o < H; o += 8) {
-    float s = warp_dot160(w.time3_w + o * H, h1, lane) + w.time3_b[o];
-    if (step_idx) s += w.step_emb[step_idx[b] * H + o];
-    if (lane == 0) {
-      c[o] = s;
-      if (cond_out) cond_out[(int64_t)b * H + o] = s;
+  for (int it = tid; it < H * (CU / 4); it += 256) {
+    const int o = it % H, u0 = (it / H) * 4;
+    float acc[4];
+    dot160x4(w.time3_w + o * H, h1, u0, w.time3_b[o], acc);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float s = acc[u];
+      if (u0 + u < nu) {
+        if (step_idx) s += w.step_emb[step_idx[b0 + u0 + u] * H + o];
+        if (cond_out && blockIdx.y == 0) cond_out[(int64_t)(b0 + u0 + u) * H + o] = s;
+      }
+      c[u0 + u][o] = s;
     }
   }
   __syncthreads();
   if (!mod_out) return;
-  for (int o = warp; o < 2 * NL * 2 * H; o += 8) {     // 8 AdaLN x 320 outputs
-    const int which = o / (2 * H), j = o % (2 * H);
+  // blockIdx.y selects one of the 8 AdaLayerNorms (the small time MLP above is recomputed per block)
+  constexpr int NOUT = 2 * H;
+  for (int it = tid; it < NOUT * (CU / 4); it += 256) {
+    const int j = it % NOUT, u0 = (it / NOUT) * 4;
+    const int which = blockIdx.y;
     const edtts_layer_weights& L = w.layers[which >> 1];
     const float* pw = (which & 1) ? L.norm3_proj_w : L.norm1_proj_w;
     const float* pb = (which & 1) ? L.norm3_proj_b : L.norm1_proj_b;
-    const float s = warp_dot160(pw + j * H, c, lane) + pb[j];
-    if (lane == 0) mod_out[((int64_t)b * 2 * NL + which) * 2 * H + j] = s;
+    float acc[4];
+    dot160x4(pw + j * H, c, u0, pb[j], acc);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (u0 + u < nu) mod_out[((int64_t)(b0 + u0 + u) * 2 * NL + which) * 2 * H + j] = acc[u];
   }
 }
 
@@ -108,7 +139,7 @@ extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t*
                                   float* cond_out, float* mod_out, int32_t B, void* stream) {
   EDTTS_REQUIRE(w && t && B > 0 && (cond_out || mod_out), EDTTS_EINVAL, "cond_prepare: null argument");
   LaunchScope ls(KC_COND, as_stream(stream));
-  cond_kernel<<<B, 256, 0, as_stream(stream)>>>(*w, t, step_idx, cond_out, mod_out);
+  cond_kernel<<<dim3((B + CU - 1) / CU, mod_out ? 2 * NL : 1), 256, 0, as_stream(stream)>>>(*w, t, step_idx, cond_out, mod_out, B);
   return check_launch("cond_kernel");
 }
 
@@ -132,8 +163,6 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
   const int64_t rows = (int64_t)B * S;
   float* ctx = reinterpret_cast<float*>(workspace);
   float* craw = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256));
-  float* kvtmp = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256) +
-                                          align_up(rows * RANK * 4, 256));
   if (sem_idx) {
     const int64_t n4 = rows * (H / 4);
     LaunchScope ls(KC_EMBED, st);
@@ -149,6 +178,8 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     int rc = launch_gemm_simt(g, st);
     if (rc) return rc;
   }
+  if (precision == EDTTS_PREC_BF16)   // kv_down -> kv_norm -> kv_up on the tensor cores, stored as the attention operand image
+    return tc_context_kv(w, ctx, craw, kv_out, rows, st);
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     GemmArgs d;   // kv_down_proj (mla.py:146)
@@ -157,15 +188,10 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     if (rc) return rc;
     GemmArgs u;   // kv_norm + kv_up_proj (mla.py:147-153)
     u.A = craw; u.rows = rows; u.K = RANK; u.lda = RANK; u.W = L.kv_up_w; u.N = 2 * H;
-    u.out = precision == EDTTS_PREC_BF16 ? kvtmp : kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
+    u.out = kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
     u.pro = PRO_RMS; u.norm_w = L.kv_norm_w; u.norm_eps = 1e-6f;
     rc = launch_gemm_simt(u, st);
     if (rc) return rc;
-    if (precision == EDTTS_PREC_BF16) {
-      rc = tc::pack_activation(kvtmp, 2 * H, reinterpret_cast<uint16_t*>(kv_out) + (int64_t)l * rows * 2 * H, rows, 2 * H,
-                                 /*v (columns 160..319) as f16:*/ H, st);
-      if (rc) return rc;
-    }
   }
   return EDTTS_OK;
 }

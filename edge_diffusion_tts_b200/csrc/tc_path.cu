@@ -13,7 +13,7 @@ namespace tc {
 // so a CTA fetches its slab with one bulk copy.  ffn.net.0 is row-permuted so that block y
 // holds the 80 "x" rows and the 80 matching "gate" rows of SwiGLU output columns 80y..80y+79.
 struct LayerOff {
-  int64_t qkv, attn_proj, q_proj, cross_out, ffn0, ffn0_bias, ffn3;
+  int64_t qkv, attn_proj, q_proj, cross_out, ffn0, ffn0_bias, ffn3, kv_down, kv_up;
 };
 struct PackedOff {
   int64_t in_proj, out_proj;
@@ -39,6 +39,8 @@ static PackedOff packed_offsets() {
     p.layer[l].ffn0 = take((int64_t)2 * FFN * H * 2);
     p.layer[l].ffn0_bias = take((int64_t)2 * FFN * 4);
     p.layer[l].ffn3 = take((int64_t)H * FFN * 2);
+    p.layer[l].kv_down = take((int64_t)RANK * H * 2);
+    p.layer[l].kv_up = take((int64_t)2 * H * RANK * 2);
   }
   p.total = o;
   return p;
@@ -331,6 +333,30 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
   return EDTTS_OK;
 }
 
+int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, void* kv_out, int64_t rows, cudaStream_t st) {
+  EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "context_prepare(bf16): weights.packed_bf16 is null");
+  const PackedOff po = packed_offsets();
+  const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
+  for (int l = 0; l < NL; ++l) {
+    const LayerOff& lo = po.layer[l];
+    int rc;
+    {  // c = kv_down_proj(ctx)   (mla.py:146)
+      TcGemmArgs g;
+      g.amode = A_F32; g.A_f32 = ctx; g.R = rows; g.T = (int)rows; g.W_img = reinterpret_cast<const __nv_bfloat16*>(pk + lo.kv_down);
+      g.epi = TE_F32; g.out_f32 = craw; g.ldo = RANK;
+      if ((rc = launch_tc_gemm(g, H, RANK, 1, st))) return rc;
+    }
+    {  // k | v = kv_up_proj(kv_norm(c)) -> chunk-major, k (chunks 0..19) bf16, v (20..39) f16   (mla.py:147-153)
+      TcGemmArgs g;
+      g.amode = A_F32; g.A_f32 = craw; g.R = rows; g.T = (int)rows; g.W_img = reinterpret_cast<const __nv_bfloat16*>(pk + lo.kv_up);
+      g.pro = PRO_RMS; g.norm_w = w->layers[l].kv_norm_w; g.norm_eps = 1e-6f;
+      g.epi = TE_CHUNK; g.out_chunk = reinterpret_cast<__nv_bfloat16*>(kv_out) + (int64_t)l * rows * 2 * H; g.f16_from_chunk = 20;
+      if ((rc = launch_tc_gemm(g, RANK, H, 2, st))) return rc;
+    }
+  }
+  return EDTTS_OK;
+}
+
 int tc_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, float* h_out,
                    void* workspace, int32_t B, int32_t T, int32_t S, int n_layers, int stop_phase, int fused,
                    cudaStream_t st) {
@@ -454,6 +480,8 @@ extern "C" int edtts_pack_weights_bf16(const edtts_decoder_weights* w, void* pac
       if ((rc = check_launch("pack_bias"))) return rc;
     }
     if ((rc = tc::pack_weight(L.ffn3_w, pk + lo.ffn3, H, FFN, M, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.kv_down_w, pk + lo.kv_down, RANK, H, RANK, 0, st))) return rc;
+    if ((rc = tc::pack_weight(L.kv_up_w, pk + lo.kv_up, 2 * H, RANK, H, 0, st))) return rc;
   }
   // images of the fused transformer-block kernel follow the per-GEMM images
   return tc::tc_layer_pack(w, pk + po.total, st);
