@@ -83,7 +83,8 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
                     const edtts_step_args* step, int B, int T, int S, int stop_phase, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tc_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
       return check_launch("tc_layer smem attribute");
     configured = true;
   }
@@ -139,7 +140,8 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
   }
   const int ntiles = B * a.tiles_per_utt;
   LaunchScope ls(KC_TC_LAYER, st);
-  tc_layer_kernel<<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
+  if (want_clocks) tc_layer_kernel<true><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
+  else tc_layer_kernel<false><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
   if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
     long long hc_[24];
     cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);

@@ -125,8 +125,12 @@ struct LayerArgs {
   long long* phase_clocks;           // debug: [gridDim.x][24] cycles per phase / attention section (thread 0), or null
 };
 
+// silu(g) = g * sigmoid(g) = 0.5 g (1 + tanh(g / 2)): one MUFU operation instead of ex2 + rcp
 __device__ __forceinline__ float fast_silu(float g) {
-  return __fdividef(g, 1.0f + ex2_approx(-1.4426950408889634f * g));
+  float t;
+  const float hg = 0.5f * g;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hg));
+  return fmaf(hg, t, hg);
 }
 
 // D[128 x 160] (+)= A[128 x 160] * W[160 x 160]^T, one elected thread
@@ -350,13 +354,13 @@ __device__ __forceinline__ void ly_init_pads(uint8_t* smem, int tid) {
   }
 }
 
-template <bool WINDOW>
+template <bool WINDOW, bool PROF>
 __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint32_t tmem_base,
                                                  uint64_t* wb, uint32_t& cs, uint32_t& cp, uint32_t& co, long long* fc) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  long long fc_last = clock64();
+  long long fc_last = PROF ? clock64() : 0;
 #define LY_FC(i)                              \
-  if (fc) {                                   \
+  if (PROF && fc) {                           \
     const long long now_ = clock64();         \
     fc[i] += now_ - fc_last;                  \
     fc_last = now_;                           \
@@ -394,6 +398,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       hi = min(LY_KB, a.S - i * LY_KB) - 1;
     }
     const bool any = hi >= lo;
+    if (!any) lo = hi = LY_KB;                            // empty: no column index below 64 passes the unsigned range test
     const int base = -lo;
     const unsigned span = (unsigned)(hi - lo);
     const int nch = (ly_nkeys<WINDOW>(a, i) + 31) >> 5;
@@ -410,16 +415,16 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       if (!need[ch]) continue;
       if (full[ch]) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          b0 = fmaxf(b0, __uint_as_float(cur[32 * ch + j]));
-          b1 = fmaxf(b1, __uint_as_float(cur[32 * ch + j + 1]));
-          b2 = fmaxf(b2, __uint_as_float(cur[32 * ch + j + 2]));
-          b3 = fmaxf(b3, __uint_as_float(cur[32 * ch + j + 3]));
+        for (int j = 0; j < 32; j += 8) {                 // FMNMX3: two scores per instruction, four chains
+          b0 = fmaxf(fmaxf(b0, __uint_as_float(cur[32 * ch + j])), __uint_as_float(cur[32 * ch + j + 1]));
+          b1 = fmaxf(fmaxf(b1, __uint_as_float(cur[32 * ch + j + 2])), __uint_as_float(cur[32 * ch + j + 3]));
+          b2 = fmaxf(fmaxf(b2, __uint_as_float(cur[32 * ch + j + 4])), __uint_as_float(cur[32 * ch + j + 5]));
+          b3 = fmaxf(fmaxf(b3, __uint_as_float(cur[32 * ch + j + 6])), __uint_as_float(cur[32 * ch + j + 7]));
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          if (any && (unsigned)(base + 32 * ch + j) <= span) b0 = fmaxf(b0, __uint_as_float(cur[32 * ch + j]));
+          b0 = fmaxf(b0, (unsigned)(base + 32 * ch + j) <= span ? __uint_as_float(cur[32 * ch + j]) : -INFINITY);
       }
     }
     const float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * c;
@@ -462,11 +467,10 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
-          float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
-          if (!(any && (unsigned)(base + 32 * ch + 2 * j) <= span)) x0 = -INFINITY;
-          if (!(any && (unsigned)(base + 32 * ch + 2 * j + 1) <= span)) x1 = -INFINITY;
-          pk[j] = ly_exp2_f16x2(x0, x1);
+          const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
+          const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
+          pk[j] = ly_exp2_f16x2((unsigned)(base + 32 * ch + 2 * j) <= span ? x0 : -INFINITY,
+                                (unsigned)(base + 32 * ch + 2 * j + 1) <= span ? x1 : -INFINITY);
         }
       }
 #pragma unroll
@@ -510,6 +514,8 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
   fence_proxy_async();
 }
 
+// PROF = true: per-phase cycle counters (debug builds of the launch only; they cost ~50 registers)
+template <bool PROF>
 __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem + LO_A;
@@ -555,7 +561,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
 
   // =========================== control warps: TMA producers and MMA issuers ===========================
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");  // registers go to the compute warpgroups
+    // register budget: the launch allocates 168 x 384 = 64,512; 128 x 88 + 256 x 208 = 64,512 (an .inc beyond the
+    // pool would block forever)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (lane == 0) {
       const int cwg = (warp - 8) >> 1;
       const bool is_mma = (warp - 8) & 1;
@@ -583,7 +591,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   }
 
   // =========================== compute warpgroups ===========================================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
   const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
   const int cb = 80 * wg;                                 // this thread's column half in the row passes
   uint64_t* wb = bars + LB_WG0 + wg * WB_COUNT;
@@ -620,11 +628,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
   };
 
-  long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long fcw[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fcx[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  long long pc_last = clock64();
+  long long pc[PROF ? 8 : 1] = {0}, fcw[PROF ? 8 : 1] = {0}, fcx[PROF ? 8 : 1] = {0};
+  long long pc_last = PROF ? clock64() : 0;
 #define LY_PHASE(i)                                   \
-  if (a.phase_clocks && tid == 0) {                   \
+  if (PROF && a.phase_clocks && tid == 0) {           \
     const long long now_ = clock64();                 \
     pc[i] += now_ - pc_last;                          \
     pc_last = now_;                                   \
@@ -719,7 +726,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     LY_PHASE(0)
 
     // ---- banded self-attention -------------------------------------------------------------------------------
-    ly_softmax_phase<true>(a, tl, smem, tmem_base, wb, cs, cp, co, (a.phase_clocks && tid == 0) ? fcw : nullptr);
+    ly_softmax_phase<true, PROF>(a, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
     csync();
     LY_PHASE(1)
 
@@ -804,7 +811,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     LY_PHASE(3)
 
     // ---- cross attention over the context tokens ---------------------------------------------------------------------
-    ly_softmax_phase<false>(a, tl, smem, tmem_base, wb, cs, cp, co, (a.phase_clocks && tid == 0) ? fcx : nullptr);
+    ly_softmax_phase<false, PROF>(a, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
     csync();
     LY_PHASE(4)
 
@@ -1085,7 +1092,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     csync();
     LY_PHASE(7)
   }
-  if (a.phase_clocks && tid == 0)
+  if (PROF && a.phase_clocks && tid == 0)
     for (int i = 0; i < 8; ++i) {
       a.phase_clocks[blockIdx.x * 24 + i] = pc[i];
       a.phase_clocks[blockIdx.x * 24 + 8 + i] = fcw[i];

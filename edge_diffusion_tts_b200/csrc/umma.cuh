@@ -32,14 +32,16 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One probe of the phase with the given parity.  The suspend-time hint lets the hardware park the thread until the
+// phase completes (wake-up on completion is immediate) instead of returning to a software spin loop.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
   return ok != 0;
 }
@@ -47,7 +49,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // CUDA call), never a hung GPU.  (-DEDTTS_MBAR_DEBUG prints the barrier before trapping.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 22)) {
+    if (spin > (1u << 20)) {
 #ifdef EDTTS_MBAR_DEBUG
       printf("edtts: mbarrier wait timed out (block %d thread %d, barrier @%u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
