@@ -48,7 +48,7 @@ def flops_per_generate(B: int, T: int, S: int, steps: int) -> dict:
     win = B * 4 * (129 * T - 4160) * 40 * 2 * 2 * 4           # 4 layers
     cross = B * 4 * T * S * 40 * 2 * 2 * 4
     ctx = 2 * B * S * 4 * (H * 80 + 80 * 2 * H)
-    return dict(gemm=gemm_step * steps + ctx, attn_window=win * steps, attn_cross=cross * steps,
+    return dict(gemm=gemm_step * steps + ctx, attn_window=win * steps, attn_cross=cross * steps, ctx=ctx,
                 total=(gemm_step + win + cross) * steps + ctx)
 
 
@@ -257,7 +257,9 @@ def main():
         pass
     tensor_peak = peaks.get("bf16_tflops_sustained", 1590.0 * 0.88)
     peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback"
-    class_flops = {"gemm_simt_fp32": fl["gemm"], "tc_gemm_bf16": fl["gemm"],
+    # the fused kernel (tc_layer_bf16) executes every decoder FLOP of the step: GEMMs, window and cross attention
+    class_flops = {"gemm_simt_fp32": fl["gemm"], "tc_gemm_bf16": fl["ctx"] if "tc_layer_bf16" in kernels else fl["gemm"],
+                   "tc_layer_bf16": fl["total"] - fl["ctx"],
                    "attn_window_simt_fp32": fl["attn_window"], "tc_attn_window_bf16": fl["attn_window"],
                    "attn_cross_simt_fp32": fl["attn_cross"], "tc_attn_cross_bf16": fl["attn_cross"]}
     dom = next((k for k in kernels if k in class_flops), None)
@@ -270,7 +272,14 @@ def main():
             traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
         except Exception:
             pass
+        # the kernel's real limiter is the MUFU pipe (softmax ex2: 16 ops/clk/SM, measured in tools/ubench/mufu.cu)
+        n_exp = B * T_MEL * 4 * 4 * ((129 * T_MEL - 4160) / T_MEL + S_TOK) * N_STEPS + B * T_MEL * 320 * 4 * N_STEPS
+        sm_mhz = (clocks.get("sm_mhz") or 1965) * 1e6
+        mufu_floor_ms = n_exp / (16 * 148 * sm_mhz) * 1e3
         roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": tensor_peak, "unit": "TFLOP/s",
+                    "mufu": {"ops_per_step": n_exp, "floor_ms_per_step": mufu_floor_ms,
+                             "frac_of_mufu_floor": mufu_floor_ms / k["ms_per_step"],
+                             "note": "exp2 (softmax) + tanh (SiLU) operations / (16 per clk per SM x 148 SMs x SM clock)"},
                     "frac": achieved / tensor_peak, "traffic": traffic, "peak_source": peak_src,
                     "avg_launch_ms": k["ms_per_step"] / max(k["launches_per_step"], 1),
                     "share_of_step": k["share"], "flops_per_step": class_flops[dom]}
