@@ -135,7 +135,7 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
   static long long* clk_buf = nullptr;
   static const bool want_clocks = getenv("EDTTS_LAYER_CLOCKS") != nullptr;
   if (want_clocks) {
-    if (!clk_buf) cudaMalloc(&clk_buf, 148 * 24 * sizeof(long long));
+    if (!clk_buf) cudaMalloc(&clk_buf, 148 * 32 * sizeof(long long));
     a.phase_clocks = clk_buf;
   }
   const int ntiles = B * a.tiles_per_utt;
@@ -143,10 +143,12 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
   if (want_clocks) tc_layer_kernel<true><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
   else tc_layer_kernel<false><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
   if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
-    long long hc_[24];
+    long long hc_[32];
     cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc_layer clocks L%d] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3+tail %lld\n",
+    fprintf(stderr, "[tc_layer clocks L%d] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3 %lld\n",
             layer, hc_[0], hc_[1], hc_[2], hc_[3], hc_[4], hc_[5], hc_[6], hc_[7]);
+    fprintf(stderr, "[tc_layer tail] norm+store_h %lld mma01 %lld issue2 %lld cvt_qk %lld wait2 %lld cvt_v+sync %lld\n", hc_[24], hc_[25],
+            hc_[26], hc_[27], hc_[28], hc_[29]);
     for (int k = 1; k < 3; ++k)
       fprintf(stderr, "[tc_layer %s] other %lld waitS+load %lld max %lld exp+store %lld arriveP %lld - %lld head %lld waitO %lld\n",
               k == 1 ? "window" : "cross ", hc_[8 * k], hc_[8 * k + 1], hc_[8 * k + 2], hc_[8 * k + 3], hc_[8 * k + 4],

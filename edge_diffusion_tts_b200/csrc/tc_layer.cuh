@@ -49,6 +49,10 @@ constexpr int LY_WSLAB = 160 * 16;            // one 8-wide K slab of a 160-row 
 constexpr int LY_WCHUNK = 20 * LY_WSLAB;      // 51,200 B: W[160 out][160 in] bf16
 constexpr int LY_NCHUNK = 9;                  // proj, q_proj, out_proj, ffn0 x4, ffn3 x2
 enum LyChunk : int { WC_PROJ = 0, WC_Q, WC_OUT, WC_F0_X0, WC_F0_G0, WC_F0_X1, WC_F0_G1, WC_F3_K0, WC_F3_K1 };
+#ifndef LY_POLY_EVERY
+#define LY_POLY_EVERY 0                       // n > 0: every n-th pair of scores takes 2^x on the FMA pipe instead of MUFU
+                                              // (measured: no gain once the MUFU path is f32, the pass is issue-bound)
+#endif
 constexpr int LY_KB = 64;                     // keys per attention block
 constexpr int LY_KSLAB = LY_KB * 16;          // one 8-wide slab of a 64-key K / V block
 constexpr int LY_KBUF = 6 * LY_KSLAB;         // K (or V) block, head_dim padded 40 -> 48
@@ -299,15 +303,31 @@ __device__ __forceinline__ void ly_warp_arrive(uint64_t* bar, int lane) {
 //
 // Per 64-key block and thread (= frame): 64 scores come out of TMEM into registers (the TMEM block is released
 // at once, so the next S = Q K^T runs under this block's arithmetic), the running maximum is checked, and
-//     p = ex2.approx.f16x2(cvt.f16x2(s * c - m))
+//     p = cvt.f16x2(ex2(s * c - m))
 // goes straight to the P operand (f16, 8 keys = one 16-byte store).  Two scores per MUFU operation and no
 // running sum: V carries a constant 1 in its padding dimension 40 (ly_init_pads), so the tensor core delivers
 // the row sum of exactly the rounded p as column 40 of O.
+// two probabilities -> one packed f16x2.  MUFU.EX2 on f32 and one F2FP pack: measured 4.5-5 cycles per score and
+// sub-partition (tools/ubench/expmix.cu); ex2.approx.f16x2 splits into two half-rate MUFU.EX2.F16 (8.1 per score).
 __device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
-  const __half2 h = __floats2half2_rn(x_lo, x_hi);
-  uint32_t in = *reinterpret_cast<const uint32_t*>(&h), out;
-  asm("ex2.approx.f16x2 %0, %1;" : "=r"(out) : "r"(in));
-  return out;
+  const __half2 h = __floats2half2_rn(ex2_approx(x_lo), ex2_approx(x_hi));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + r, r in [-0.5, 0.5]; 2^r by a cubic (max relative error 7.5e-5, below
+// the f16 rounding of P), 2^n by adding n to the exponent field.  9 issue slots per score against 8 MUFU cycles: every
+// third pair of scores takes this route, which balances the MUFU pipe against the sub-partition's issue slots.
+__device__ __forceinline__ float ly_exp2_poly(float x) {
+  x = fmaxf(x, -30.0f);                                   // 2^-30 is far below the smallest f16: no exponent underflow
+  const float t = x + 12582912.0f;                        // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(0.05517164245247841f, r, 0.2426111251115799f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ uint32_t ly_pack_f16x2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 // TMEM -> registers, 64 columns, NOT waited for
 __device__ __forceinline__ void ly_s_issue(uint32_t taddr, uint32_t (&r)[64]) {
@@ -359,10 +379,11 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
                                                  uint64_t* wb, uint32_t& cs, uint32_t& cp, uint32_t& co, long long* fc) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long fc_last = PROF ? clock64() : 0;
+  long long fcr[PROF ? 8 : 1] = {0};                      // register-resident (static indices); flushed at the end
 #define LY_FC(i)                              \
-  if (PROF && fc) {                           \
+  if (PROF) {                                 \
     const long long now_ = clock64();         \
-    fc[i] += now_ - fc_last;                  \
+    fcr[i] += now_ - fc_last;                 \
     fc_last = now_;                           \
   }
   const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
@@ -461,9 +482,12 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
         for (int j = 0; j < 16; ++j) pk[j] = 0u;
       } else if (full[ch]) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          pk[j] = ly_exp2_f16x2(fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use),
-                                fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use));
+        for (int j = 0; j < 16; ++j) {
+          const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
+          const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
+          pk[j] = (LY_POLY_EVERY > 0 && j % LY_POLY_EVERY == LY_POLY_EVERY - 1) ? ly_pack_f16x2(ly_exp2_poly(x0), ly_exp2_poly(x1))
+                                                                                : ly_exp2_f16x2(x0, x1);
+        }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -512,6 +536,8 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     }
   }
   fence_proxy_async();
+  if (PROF && fc)
+    for (int i = 0; i < 8; ++i) fc[i] += fcr[i];
 }
 
 // PROF = true: per-phase cycle counters (debug builds of the launch only; they cost ~50 registers)
@@ -628,7 +654,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
   };
 
-  long long pc[PROF ? 8 : 1] = {0}, fcw[PROF ? 8 : 1] = {0}, fcx[PROF ? 8 : 1] = {0};
+  long long pc[PROF ? 16 : 1] = {0}, fcw[PROF ? 8 : 1] = {0}, fcx[PROF ? 8 : 1] = {0};
   long long pc_last = PROF ? clock64() : 0;
 #define LY_PHASE(i)                                   \
   if (PROF && a.phase_clocks && tid == 0) {           \
@@ -918,6 +944,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     gemm_wait();
     if (tid == 0 && more) mbar_arrive(bar_kvgo);          // overlay K/V region is free: next tile's window K/V may load
     }   // LM_BLOCK
+    LY_PHASE(7)
 
     // =============== tail: the finished h rows leave the SM; what consumes them next runs right here ===============
     if (tid == 0) {                                       // both weight slots are free
@@ -983,6 +1010,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     tc_fence_before();
     csync();
+    LY_PHASE(8)
 
     if (a.tail == LT_QKV) {
       // ---- q | k | v of the next block: three 160-column chunks into TMEM columns 0..479 (h is dead) -------------
@@ -997,6 +1025,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       ph_w1 ^= 1;
       ph_w0 ^= 1;
       gemm_wait();
+      LY_PHASE(9)
       if (tid == 0) {
         load_w(a.w_qkv + 2 * (LY_WCHUNK / 2), LY_WCHUNK, sW1, bar_w1);
         mbar_wait(bar_w1, ph_w1);
@@ -1006,9 +1035,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         if (more) load_first();                           // slot 0: first chunk of the next tile
       }
       ph_w1 ^= 1;
+      LY_PHASE(10)
 #pragma unroll 1
       for (int part = 0; part < 3; ++part) {              // q, k as bf16; v as f16 (P V operand)
-        if (part == 2) gemm_wait();
+        if (part == 2) {
+          LY_PHASE(11)
+          gemm_wait();
+          LY_PHASE(12)
+        }
 #pragma unroll 1
         for (int i = 0; i < 5; ++i) {
           float v[16];
@@ -1090,13 +1124,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     tc_fence_before();
     csync();
-    LY_PHASE(7)
+    LY_PHASE(13)
   }
   if (PROF && a.phase_clocks && tid == 0)
     for (int i = 0; i < 8; ++i) {
-      a.phase_clocks[blockIdx.x * 24 + i] = pc[i];
-      a.phase_clocks[blockIdx.x * 24 + 8 + i] = fcw[i];
-      a.phase_clocks[blockIdx.x * 24 + 16 + i] = fcx[i];
+      a.phase_clocks[blockIdx.x * 32 + i] = pc[i];
+      a.phase_clocks[blockIdx.x * 32 + 8 + i] = fcw[i];
+      a.phase_clocks[blockIdx.x * 32 + 16 + i] = fcx[i];
+      a.phase_clocks[blockIdx.x * 32 + 24 + i] = pc[8 + i];
     }
 
   csync();
