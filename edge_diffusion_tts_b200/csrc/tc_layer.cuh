@@ -49,14 +49,9 @@ constexpr int LY_WSLAB = 160 * 16;            // one 8-wide K slab of a 160-row 
 constexpr int LY_WCHUNK = 20 * LY_WSLAB;      // 51,200 B: W[160 out][160 in] bf16
 constexpr int LY_NCHUNK = 9;                  // proj, q_proj, out_proj, ffn0 x4, ffn3 x2
 enum LyChunk : int { WC_PROJ = 0, WC_Q, WC_OUT, WC_F0_X0, WC_F0_G0, WC_F0_X1, WC_F0_G1, WC_F3_K0, WC_F3_K1 };
-#ifndef LY_POLY_EVERY
-#define LY_POLY_EVERY 0                       // n > 0: every n-th pair of scores takes 2^x on the FMA pipe instead of MUFU
-                                              // (measured: no gain once the MUFU path is f32, the pass is issue-bound)
-#endif
 constexpr int LY_KB = 64;                     // keys per attention block
 constexpr int LY_KSLAB = LY_KB * 16;          // one 8-wide slab of a 64-key K / V block
 constexpr int LY_KBUF = 6 * LY_KSLAB;         // K (or V) block, head_dim padded 40 -> 48
-constexpr int LY_PBUF = (LY_KB / 8) * LY_SLAB;   // P block: 128 frames x 64 keys bf16
 
 // per-layer constant vector (floats), packed by tc_layer.cu
 constexpr int LC_PROJ_B = 0, LC_N2W = 160, LC_N3W = 320, LC_F0B = 480, LC_F3B = 1120, LC_COUNT = 1280;
@@ -71,16 +66,16 @@ constexpr int LO_W0 = LO_A + 21 * LY_SLAB;                // weight slot 0
 constexpr int LO_X = LO_W0 + LY_WCHUNK;                   // overlay region
 constexpr int LO_W1 = LO_X;                               //   GEMM chain: weight slot 1
 constexpr int LO_U = LO_X + LY_WCHUNK;                    //   GEMM chain: u half (128 x 160 bf16)
-constexpr int LO_P = LO_X;                                //   attention: P[wg][buf]
 constexpr int LY_KST = 3, LY_VST = 2;                     //   K / V stages per warpgroup
-constexpr int LO_KV = LO_P + 4 * LY_PBUF;                 //   attention: wg: K0 | K1 | K2 | V0 | V1
+constexpr int LO_KV = LO_U;                               //   attention: wg: K0 | K1 | K2 | V0 | V1 (K/V stream in while
+                                                          //   weight slot 1 is in use, so they only overlay the u half)
 constexpr int LO_X_END = LO_KV + 2 * (LY_KST + LY_VST) * LY_KBUF;
+static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay region");
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
 constexpr int LO_BAR = LO_RED + 4 * 128 * 4;
 constexpr int LY_NBAR = 8 + 2 * 20;
 constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
-static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay region");
 static_assert(LY_SMEM <= 232448, "shared memory budget");
 
 // mbarrier indices
@@ -91,7 +86,8 @@ enum LyWgBar : int { WB_KFULL = 0, WB_KFREE = 3, WB_VFULL = 6, WB_VFREE = 8, WB_
 // tensor memory map (columns)
 constexpr uint32_t TM_H = 0;                              // residual stream, 160 columns
 constexpr uint32_t TM_G = 160;                            // GEMM chain scratch, 320 columns
-constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention, per warpgroup: S0 (64) | S1 (64) | O (48)
+constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention, per warpgroup: S0 (64) | S1 (64) | O (48); the f16
+                                                          // probabilities P(i) overwrite columns 0..31 of their S block
 
 
 struct LayerArgs {
@@ -244,14 +240,14 @@ __device__ __forceinline__ void ly_mma_phase(const LayerArgs& a, const LyTile& t
                                              uint64_t* wb, int wg, uint32_t& ns, uint32_t& nv, uint32_t& nh) {
   const LyPlan pl = ly_plan<WINDOW>(a, tl);
   const uint32_t sA = smem_u32(smem + LO_A);
-  const uint32_t sP = smem_u32(smem + LO_P + wg * (2 * LY_PBUF));
   const uint32_t sKV = smem_u32(smem + LO_KV + wg * ((LY_KST + LY_VST) * LY_KBUF));
   const uint32_t dS = tmem_base + TM_S0 + wg * TM_WG;
   const uint32_t dO = dS + 2 * LY_KB;
   auto s_op = [&](int head, int i) {
     const uint32_t sbuf = ns & 1, kbuf = ns % LY_KST;
     mbar_wait(wb + WB_KFULL + kbuf, (ns / LY_KST) & 1);
-    mbar_wait(wb + WB_SFREE + sbuf, ((ns >> 1) & 1) ^ 1);
+    // S block sbuf is free: its last reader is P V (ns - 2) (P lives in the block), issued before this MMA by this
+    // very thread, and the tensor core executes its MMAs in issue order.
     tc_fence_after();
     const uint32_t idesc = make_idesc(128, (uint32_t)ly_nkeys<WINDOW>(a, i));
     const uint32_t qa = sA + head * 5 * LY_SLAB, ka = sKV + kbuf * LY_KBUF;
@@ -270,11 +266,11 @@ __device__ __forceinline__ void ly_mma_phase(const LayerArgs& a, const LyTile& t
     if (i == 0) mbar_wait(wb + WB_OFREE, (nh & 1) ^ 1);
     tc_fence_after();
     constexpr uint32_t IDESC_O = make_idesc_f16(128, 48, /*b_mn_major=*/true);   // P, V are f16
-    const uint32_t pa = sP + buf * LY_PBUF, va = sKV + (LY_KST + buf) * LY_KBUF;
+    const uint32_t pa = dS + buf * LY_KB, va = sKV + (LY_KST + buf) * LY_KBUF;   // P: A operand in tensor memory
     const int nks = ly_nkeys<WINDOW>(a, i) >> 4;
     for (int ks = 0; ks < nks; ++ks)
-      umma_bf16(dO, make_desc(pa + ks * 2 * LY_SLAB, LY_SLAB, 128),
-                make_desc(va + ks * 2 * 128, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_KSLAB), IDESC_O, i > 0 || ks > 0);
+      umma_f16_ts(dO, pa + ks * 8, make_desc(va + ks * 2 * 128, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_KSLAB),
+                  IDESC_O, i > 0 || ks > 0);
     umma_commit(wb + WB_PFREE + buf);
     umma_commit(wb + WB_VFREE + buf);
     if (last) umma_commit(wb + WB_OFULL);
@@ -311,22 +307,6 @@ __device__ __forceinline__ void ly_warp_arrive(uint64_t* bar, int lane) {
 // sub-partition (tools/ubench/expmix.cu); ex2.approx.f16x2 splits into two half-rate MUFU.EX2.F16 (8.1 per score).
 __device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
   const __half2 h = __floats2half2_rn(ex2_approx(x_lo), ex2_approx(x_hi));
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-// 2^x on the FMA / ALU pipes (no MUFU): x = n + r, r in [-0.5, 0.5]; 2^r by a cubic (max relative error 7.5e-5, below
-// the f16 rounding of P), 2^n by adding n to the exponent field.  9 issue slots per score against 8 MUFU cycles: every
-// third pair of scores takes this route, which balances the MUFU pipe against the sub-partition's issue slots.
-__device__ __forceinline__ float ly_exp2_poly(float x) {
-  x = fmaxf(x, -30.0f);                                   // 2^-30 is far below the smallest f16: no exponent underflow
-  const float t = x + 12582912.0f;                        // 1.5 * 2^23: the low mantissa bits of t hold round(x)
-  const float r = x - (t - 12582912.0f);
-  float p = fmaf(0.05517164245247841f, r, 0.2426111251115799f);
-  p = fmaf(p, r, 0.6932609677314758f);
-  p = fmaf(p, r, 0.9999280571937561f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
-}
-__device__ __forceinline__ uint32_t ly_pack_f16x2(float lo, float hi) {
-  const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 // TMEM -> registers, 64 columns, NOT waited for
@@ -389,7 +369,6 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
   const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
   const LyPlan pl = ly_plan<WINDOW>(a, tl);
   uint8_t* sA = smem + LO_A;
-  uint8_t* sP = smem + LO_P + wg * (2 * LY_PBUF);
   const uint32_t tS = tmem_base + ((uint32_t)(lq * 32) << 16) + TM_S0 + wg * TM_WG;
   const uint32_t tO = tS + 2 * LY_KB;
   const float c = a.scale_log2e;
@@ -404,8 +383,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     tc_fence_after();
     ly_s_issue(tS + (cs & 1) * LY_KB, cur);               // both 32-column loads in flight, one wait
     ly_s_wait(cur);
-    tc_fence_before();
-    ly_warp_arrive(wb + WB_SFREE + (cs & 1), lane);       // the TMEM block is free again at once
+    const uint32_t tP = tS + (cs & 1) * LY_KB;            // P(i) replaces S(i) in place (this thread's lane only)
     ++cs;
     LY_FC(1)
     // valid key columns [lo, hi] of this thread's row inside block i (empty if hi < lo)
@@ -470,9 +448,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     }
     const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
     LY_FC(2)
-    // ---- p -> P (f16, shared memory).  The P buffer is free: S(i) was issued after P V (i-2), and the tensor
-    //      core retires its work in issue order, so S(i) complete implies P V (i-2) complete. ----------------------
-    uint8_t* prow = sP + pbuf * LY_PBUF + row * 16;
+    // ---- p -> P (f16x2 per 32-bit column, tensor memory): the A operand of P V, no shared-memory round trip ----
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       if (ch >= nch) continue;
@@ -485,8 +461,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
         for (int j = 0; j < 16; ++j) {
           const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
           const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
-          pk[j] = (LY_POLY_EVERY > 0 && j % LY_POLY_EVERY == LY_POLY_EVERY - 1) ? ly_pack_f16x2(ly_exp2_poly(x0), ly_exp2_poly(x1))
-                                                                                : ly_exp2_f16x2(x0, x1);
+          pk[j] = ly_exp2_f16x2(x0, x1);
         }
       } else {
 #pragma unroll
@@ -497,12 +472,10 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
                                 (unsigned)(base + 32 * ch + 2 * j + 1) <= span ? x1 : -INFINITY);
         }
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g)
-        *reinterpret_cast<uint4*>(prow + (ch * 4 + g) * LY_SLAB) = make_uint4(pk[4 * g], pk[4 * g + 1], pk[4 * g + 2], pk[4 * g + 3]);
+      tmem_st16u(tP + 16 * ch, pk);
     }
     LY_FC(3)
-    fence_proxy_async();
+    tmem_st_wait();
     tc_fence_before();
     ly_warp_arrive(wb + WB_PFULL + pbuf, lane);
     ++cp;
@@ -571,7 +544,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     for (int w = 0; w < 2; ++w) {
       uint64_t* wbi = bars + LB_WG0 + w * WB_COUNT;
       for (int i = 0; i < WB_COUNT; ++i) {
-        const bool per_warp = (i >= WB_SFREE && i < WB_SFREE + 2) || (i >= WB_PFULL && i < WB_PFULL + 2) || i == WB_OFREE;
+        const bool per_warp = (i >= WB_PFULL && i < WB_PFULL + 2) || i == WB_OFREE;
         mbar_init(wbi + i, per_warp ? 4 : 1);
       }
     }
