@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libedtts.so")
+# EDTTS_LIB: development override to A/B a differently compiled build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("EDTTS_LIB") or os.path.join(_HERE, "lib", "libedtts.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 STEP_EPS, STEP_DDIM, STEP_DDPM = 0, 1, 2

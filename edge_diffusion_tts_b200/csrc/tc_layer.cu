@@ -139,9 +139,34 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
     a.phase_clocks = clk_buf;
   }
   const int ntiles = B * a.tiles_per_utt;
+#ifdef LY_TRACE
+  static long long* tr_buf = nullptr;
+  static int tr_done = 0;
+  const bool tr_now = layer == 1 && tr_done < 1 && B >= 64;
+  if (tr_now) {
+    if (!tr_buf) cudaMalloc(&tr_buf, 4 * 1024 * sizeof(long long));
+    cudaMemsetAsync(tr_buf, 0, 4 * 1024 * sizeof(long long), st);
+    a.phase_clocks = tr_buf;
+  }
+#endif
   LaunchScope ls(KC_TC_LAYER, st);
   if (want_clocks) tc_layer_kernel<true><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
   else tc_layer_kernel<false><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
+#ifdef LY_TRACE
+  if (tr_now) {
+    static long long hb[4 * 1024];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(hb, tr_buf, sizeof(hb), cudaMemcpyDeviceToHost);
+    ++tr_done;
+    long long t0 = -1;
+    for (int s_ = 0; s_ < 4; ++s_)
+      for (long long e = 0; e < hb[s_ * 1024]; ++e)
+        if (t0 < 0 || hb[s_ * 1024 + 3 + 2 * e] < t0) t0 = hb[s_ * 1024 + 3 + 2 * e];
+    for (int s_ = 0; s_ < 4; ++s_)
+      for (long long e = 0; e < hb[s_ * 1024]; ++e)
+        fprintf(stderr, "TRACE %d %lld %lld\n", s_, hb[s_ * 1024 + 2 + 2 * e], hb[s_ * 1024 + 3 + 2 * e] - t0);
+  }
+#endif
   if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
     long long hc_[32];
     cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);

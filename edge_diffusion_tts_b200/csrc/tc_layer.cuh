@@ -66,7 +66,7 @@ constexpr int LO_W0 = LO_A + 21 * LY_SLAB;                // weight slot 0
 constexpr int LO_X = LO_W0 + LY_WCHUNK;                   // overlay region
 constexpr int LO_W1 = LO_X;                               //   GEMM chain: weight slot 1
 constexpr int LO_U = LO_X + LY_WCHUNK;                    //   GEMM chain: u half (128 x 160 bf16)
-constexpr int LY_KST = 3, LY_VST = 2;                     //   K / V stages per warpgroup
+constexpr int LY_KST = 4, LY_VST = 2;                     //   K / V stages per warpgroup (S blocks: 2, so K stage = S op % 4)
 constexpr int LO_KV = LO_U;                               //   attention: wg: K0 | K1 | K2 | V0 | V1 (K/V stream in while
                                                           //   weight slot 1 is in use, so they only overlay the u half)
 constexpr int LO_X_END = LO_KV + 2 * (LY_KST + LY_VST) * LY_KBUF;
@@ -74,14 +74,16 @@ static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay r
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
 constexpr int LO_BAR = LO_RED + 4 * 128 * 4;
-constexpr int LY_NBAR = 8 + 2 * 20;
+constexpr int LY_NBAR = 8 + 2 * 16;
 constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
 static_assert(LY_SMEM <= 232448, "shared memory budget");
 
 // mbarrier indices
 enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_WG0 = 8 };
-enum LyWgBar : int { WB_KFULL = 0, WB_KFREE = 3, WB_VFULL = 6, WB_VFREE = 8, WB_SFULL = 10, WB_SFREE = 12, WB_PFULL = 14,
-                     WB_PFREE = 16, WB_OFULL = 18, WB_OFREE = 19, WB_COUNT = 20 };
+// One commit per MMA group: WB_SK[n % 4] = "S op n retired" tells the softmax warps that S block n % 2 is full AND the TMA
+// producer that K stage n % 4 is free; WB_PV[n % 2] = "P V op n retired" frees V stage / P block n % 2 (lazy rescale).
+enum LyWgBar : int { WB_KFULL = 0, WB_SK = 4, WB_VFULL = 8, WB_PV = 10, WB_PFULL = 12, WB_OFULL = 14, WB_OFREE = 15, WB_COUNT = 16 };
+static_assert(LY_KST == 4 && LY_VST == 2, "barrier indexing assumes 4 K stages, 2 V stages, 2 S blocks");
 
 // tensor memory map (columns)
 constexpr uint32_t TM_H = 0;                              // residual stream, 160 columns
@@ -124,6 +126,19 @@ struct LayerArgs {
   int stop_phase;                    // debug: 1 = stop after attention + proj, 2 = after cross, 0 = whole block
   long long* phase_clocks;           // debug: [gridDim.x][24] cycles per phase / attention section (thread 0), or null
 };
+
+// Development trace (-DLY_TRACE): CTA 0 records (event id, clock) pairs of four threads -- compute warp 0 / warp 4 lane 0,
+// MMA issuer and TMA producer of warpgroup 0 -- into phase_clocks[slot * 1024 ..]; the launcher prints them.
+#ifdef LY_TRACE
+#define LY_TR(slot, id)                                                              \
+  { if (blockIdx.x == 0 && a.phase_clocks && (threadIdx.x & 31) == 0) {                \
+    long long* tb_ = a.phase_clocks + (slot) * 1024;                                 \
+    const long long n_ = tb_[0];                                                     \
+    if (n_ < 510) { tb_[2 + 2 * n_] = (id); tb_[3 + 2 * n_] = clock64(); tb_[0] = n_ + 1; } \
+  } }
+#else
+#define LY_TR(slot, id) {}
+#endif
 
 // silu(g) = g * sigmoid(g) = 0.5 g (1 + tanh(g / 2)): one MUFU operation instead of ex2 + rcp
 __device__ __forceinline__ float fast_silu(float g) {
@@ -199,14 +214,19 @@ __device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& t
     const uint32_t nst = is_v ? LY_VST : LY_KST;
     const uint32_t buf = cnt % nst, use = cnt / nst;
     uint64_t* full = wb + (is_v ? WB_VFULL : WB_KFULL) + buf;
-    mbar_wait(wb + (is_v ? WB_VFREE : WB_KFREE) + buf, (use & 1) ^ 1);
+    mbar_wait(wb + (is_v ? WB_PV : WB_SK) + buf, (use & 1) ^ 1);
+    if (wg == 0) LY_TR(3, is_v ? 31 : 30)
     uint8_t* dst = kv + ((is_v ? LY_KST : 0) + buf) * LY_KBUF;
     if (WINDOW) {
       const int64_t g0 = tl.row0 - WIN + LY_KB * (pl.kb0 + i);
       const int c0 = (is_v ? 40 : 20) + head * 5;
+#ifdef LY_KO_KV   // timing experiment only (wrong results): no K/V copies
+      mbar_arrive(full);
+#else
       mbar_expect_tx(full, 5 * LY_KSLAB);
 #pragma unroll
       for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.qkv + ((int64_t)(c0 + g) * a.R + g0) * 8, LY_KSLAB, full);
+#endif
     } else {
       const int nvalid = min(LY_KB, a.S - i * LY_KB);
       const int64_t g0 = (int64_t)tl.b * a.S + i * LY_KB;
@@ -217,9 +237,13 @@ __device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& t
           for (int g = 0; g < 5; ++g) *reinterpret_cast<uint4*>(dst + g * LY_KSLAB + r * 16) = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
       }
+#ifdef LY_KO_KV
+      mbar_arrive(full);
+#else
       mbar_expect_tx(full, 5 * nvalid * 16);
 #pragma unroll
       for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.kvx + ((int64_t)(c0 + g) * a.RS + g0) * 8, nvalid * 16, full);
+#endif
     }
     ++cnt;
   };
@@ -234,46 +258,69 @@ __device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& t
   }
 }
 
-// ---- MMA issuer of one warpgroup, one attention phase (one thread) ------------------------------------------------
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
+// ---- MMA issuer of one warpgroup, one attention phase (a converged warp; one elected lane issues) ------------------
 template <bool WINDOW>
 __device__ __forceinline__ void ly_mma_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint32_t tmem_base,
                                              uint64_t* wb, int wg, uint32_t& ns, uint32_t& nv, uint32_t& nh) {
   const LyPlan pl = ly_plan<WINDOW>(a, tl);
-  const uint32_t sA = smem_u32(smem + LO_A);
   const uint32_t sKV = smem_u32(smem + LO_KV + wg * ((LY_KST + LY_VST) * LY_KBUF));
   const uint32_t dS = tmem_base + TM_S0 + wg * TM_WG;
   const uint32_t dO = dS + 2 * LY_KB;
+  // operand descriptors are built once per phase; a k-step only adds its byte offset (>> 4) to the start-address field
+  const uint64_t dq0 = make_desc(smem_u32(smem + LO_A), LY_SLAB, 128);
+  const uint64_t dk0 = make_desc(sKV, LY_KSLAB, 128);
+  const uint64_t dv0 = make_desc(sKV + LY_KST * LY_KBUF, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_KSLAB);
+  constexpr uint32_t IDESC_S = make_idesc(128, LY_KB);
+  constexpr uint32_t IDESC_O = make_idesc_f16(128, 48, /*b_mn_major=*/true);     // P, V are f16
   auto s_op = [&](int head, int i) {
-    const uint32_t sbuf = ns & 1, kbuf = ns % LY_KST;
-    mbar_wait(wb + WB_KFULL + kbuf, (ns / LY_KST) & 1);
+    const uint32_t sbuf = ns & 1, kbuf = ns & 3;
+    mbar_wait(wb + WB_KFULL + kbuf, (ns >> 2) & 1);
+    if (wg == 0) LY_TR(2, 20)
     // S block sbuf is free: its last reader is P V (ns - 2) (P lives in the block), issued before this MMA by this
     // very thread, and the tensor core executes its MMAs in issue order.
     tc_fence_after();
-    const uint32_t idesc = make_idesc(128, (uint32_t)ly_nkeys<WINDOW>(a, i));
-    const uint32_t qa = sA + head * 5 * LY_SLAB, ka = sKV + kbuf * LY_KBUF;
+    const int nk = ly_nkeys<WINDOW>(a, i);
+    const uint32_t idesc = (WINDOW || nk == LY_KB) ? IDESC_S : make_idesc(128, (uint32_t)nk);
+    const uint64_t qa = dq0 + (uint64_t)(head * 5 * (LY_SLAB >> 4)), ka = dk0 + (uint64_t)(kbuf * (LY_KBUF >> 4));
+    if (elect_one()) {
+#ifndef LY_KO_AMMA   // (timing experiment only: no attention MMAs)
 #pragma unroll
-    for (int ks = 0; ks < 3; ++ks)
-      umma_bf16(dS + sbuf * LY_KB, make_desc(qa + ks * 2 * LY_SLAB, LY_SLAB, 128),
-                make_desc(ka + ks * 2 * LY_KSLAB, LY_KSLAB, 128), idesc, ks > 0);
-    umma_commit(wb + WB_SFULL + sbuf);
-    umma_commit(wb + WB_KFREE + kbuf);
+      for (int ks = 0; ks < 3; ++ks)
+        umma_bf16(dS + sbuf * LY_KB, qa + (uint64_t)(ks * 2 * (LY_SLAB >> 4)), ka + (uint64_t)(ks * 2 * (LY_KSLAB >> 4)), idesc, ks > 0);
+#endif
+      umma_commit(wb + WB_SK + kbuf);
+    }
+    if (wg == 0) LY_TR(2, 21)
     ++ns;
   };
   auto pv_op = [&](int i, bool last) {
     const uint32_t buf = nv & 1, par = (nv >> 1) & 1;
     mbar_wait(wb + WB_PFULL + buf, par);
+    if (wg == 0) LY_TR(2, 22)
     mbar_wait(wb + WB_VFULL + buf, par);
+    if (wg == 0) LY_TR(2, 23)
     if (i == 0) mbar_wait(wb + WB_OFREE, (nh & 1) ^ 1);
     tc_fence_after();
-    constexpr uint32_t IDESC_O = make_idesc_f16(128, 48, /*b_mn_major=*/true);   // P, V are f16
-    const uint32_t pa = dS + buf * LY_KB, va = sKV + (LY_KST + buf) * LY_KBUF;   // P: A operand in tensor memory
+    const uint32_t pa = dS + buf * LY_KB;                 // P: A operand in tensor memory
+    const uint64_t va = dv0 + (uint64_t)(buf * (LY_KBUF >> 4));
     const int nks = ly_nkeys<WINDOW>(a, i) >> 4;
-    for (int ks = 0; ks < nks; ++ks)
-      umma_f16_ts(dO, pa + ks * 8, make_desc(va + ks * 2 * 128, /*LBO: next 8 keys*/ 128, /*SBO: next 8 dims*/ LY_KSLAB),
-                  IDESC_O, i > 0 || ks > 0);
-    umma_commit(wb + WB_PFREE + buf);
-    umma_commit(wb + WB_VFREE + buf);
-    if (last) umma_commit(wb + WB_OFULL);
+    if (elect_one()) {
+#ifdef LY_KO_AMMA
+      for (int ks = 0; ks < (i == 0 ? 1 : 0); ++ks)
+#else
+      for (int ks = 0; ks < nks; ++ks)
+#endif
+        umma_f16_ts(dO, pa + ks * 8, va + (uint64_t)(ks * (2 * 128 >> 4)), IDESC_O, i > 0 || ks > 0);
+      umma_commit(wb + WB_PV + buf);
+      if (last) umma_commit(wb + WB_OFULL);
+    }
+    if (wg == 0) LY_TR(2, 24)
     ++nv;
   };
   for (int hh = 0; hh < 2; ++hh) {
@@ -306,7 +353,30 @@ __device__ __forceinline__ void ly_warp_arrive(uint64_t* bar, int lane) {
 // two probabilities -> one packed f16x2.  MUFU.EX2 on f32 and one F2FP pack: measured 4.5-5 cycles per score and
 // sub-partition (tools/ubench/expmix.cu); ex2.approx.f16x2 splits into two half-rate MUFU.EX2.F16 (8.1 per score).
 __device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
+#ifdef LY_KO_EXP   // timing experiment only (wrong results): no MUFU
+  const __half2 h = __floats2half2_rn(x_lo * 0.001f, x_hi * 0.001f);
+#else
   const __half2 h = __floats2half2_rn(ex2_approx(x_lo), ex2_approx(x_hi));
+#endif
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 2^x on the FMA / ALU pipes (no MUFU): x = n + r, r in [-0.5, 0.5]; 2^r by a cubic (max relative error 7.5e-5, below
+// the f16 rounding of P), 2^n by adding n to the exponent field.  MUFU.EX2 issues once per 8 cycles per sub-partition
+// (tools/ubench/expord.cu), so moving every LY_POLY_EVERY-th pair of scores here shortens the MUFU-bound pass.
+#ifndef LY_POLY_EVERY
+#define LY_POLY_EVERY 4
+#endif
+__device__ __forceinline__ float ly_exp2_poly(float x) {
+  x = fmaxf(x, -30.0f);                                   // 2^-30 is far below the smallest f16: no exponent underflow
+  const float t = x + 12582912.0f;                        // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float r = x - (t - 12582912.0f);
+  float p = fmaf(0.05517164245247841f, r, 0.2426111251115799f);
+  p = fmaf(p, r, 0.6932609677314758f);
+  p = fmaf(p, r, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ uint32_t ly_pack_f16x2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 // TMEM -> registers, 64 columns, NOT waited for
@@ -379,12 +449,15 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
   auto step = [&](uint32_t (&cur)[64], int i) {
     const uint32_t pbuf = cp & 1;
     LY_FC(0)
-    mbar_wait(wb + WB_SFULL + (cs & 1), (cs >> 1) & 1);
+    if (lq == 0) LY_TR(wg, 1)
+    mbar_wait(wb + WB_SK + (cs & 3), (cs >> 2) & 1);
+    if (lq == 0) LY_TR(wg, 2)
     tc_fence_after();
     ly_s_issue(tS + (cs & 1) * LY_KB, cur);               // both 32-column loads in flight, one wait
     ly_s_wait(cur);
     const uint32_t tP = tS + (cs & 1) * LY_KB;            // P(i) replaces S(i) in place (this thread's lane only)
     ++cs;
+    if (lq == 0) LY_TR(wg, 3)
     LY_FC(1)
     // valid key columns [lo, hi] of this thread's row inside block i (empty if hi < lo)
     int lo, hi;
@@ -426,13 +499,17 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
           b0 = fmaxf(b0, (unsigned)(base + 32 * ch + j) <= span ? __uint_as_float(cur[32 * ch + j]) : -INFINITY);
       }
     }
+#ifdef LY_KO_MAX   // timing experiment only (wrong results): no block maximum
+    const float bmax = (i == 0 ? 8.0f : m_run);
+#else
     const float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * c;
+#endif
     const bool grow = bmax > m_run + 6.0f;                // also true for the first finite block maximum
     if (__any_sync(0xffffffffu, grow)) {
       const float m_upd = grow ? bmax : m_run;
       if (i > 0) {                                        // rescale this warp's O rows (and the row sum in column 40):
         const float f = (m_upd == m_run) ? 1.0f : ex2_approx(m_run - m_upd);     // m_run = -inf -> 0
-        mbar_wait(wb + WB_PFREE + (pbuf ^ 1), ((cp - 1) >> 1) & 1);              // P V (i-1) must have retired
+        mbar_wait(wb + WB_PV + (pbuf ^ 1), ((cp - 1) >> 1) & 1);                 // P V (i-1) must have retired
         tc_fence_after();
 #pragma unroll
         for (int q = 0; q < 3; ++q) {
@@ -461,7 +538,8 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
         for (int j = 0; j < 16; ++j) {
           const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
           const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
-          pk[j] = ly_exp2_f16x2(x0, x1);
+          if (LY_POLY_EVERY > 0 && j % (LY_POLY_EVERY > 0 ? LY_POLY_EVERY : 1) == 0) pk[j] = ly_pack_f16x2(ly_exp2_poly(x0), ly_exp2_poly(x1));
+          else pk[j] = ly_exp2_f16x2(x0, x1);
         }
       } else {
 #pragma unroll
@@ -475,9 +553,12 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       tmem_st16u(tP + 16 * ch, pk);
     }
     LY_FC(3)
+    if (lq == 0) LY_TR(wg, 4)
     tmem_st_wait();
     tc_fence_before();
+    if (lq == 0) LY_TR(wg, 5)
     ly_warp_arrive(wb + WB_PFULL + pbuf, lane);
+    if (lq == 0) LY_TR(wg, 6)
     ++cp;
     LY_FC(4)
   };
@@ -490,7 +571,9 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
 
     // ---- head done: O / l replaces Q_h in sA ---------------------------------------------------------------------
     LY_FC(6)
+    if (lq == 0) LY_TR(wg, 7)
     mbar_wait(wb + WB_OFULL, co & 1);
+    if (lq == 0) LY_TR(wg, 8)
     tc_fence_after();
     LY_FC(7)
     float ob[48];
@@ -563,9 +646,15 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     // register budget: the launch allocates 168 x 384 = 64,512; 128 x 88 + 256 x 208 = 64,512 (an .inc beyond the
     // pool would block forever)
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    if (lane == 0) {
-      const int cwg = (warp - 8) >> 1;
-      const bool is_mma = (warp - 8) & 1;
+    // The MMA issuer warps run CONVERGED (all 32 lanes walk the loop, one elected lane issues): the compiler then keeps
+    // descriptors and barrier addresses in uniform registers and a tcgen05.mma costs its hardware floor to issue (24-48
+    // cycles for these shapes) instead of ~56 cycles through per-instruction R2UR moves inside a divergent single-thread
+    // branch (tools/ubench/mmarate.cu).  The warp index is made provably warp-uniform with a shuffle.
+    const int cw = __shfl_sync(0xffffffffu, warp, 0) - 8;
+    const int cwg = cw >> 1;
+    const bool is_mma = cw & 1;
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+    if (is_mma || lane == 0) {
       uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
       uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;       // TMA: c0 = K loads, c1 = V loads; MMA: S ops, PV ops, heads
       for (int tile = blockIdx.x; tile < ntiles && a.mode == LM_BLOCK; tile += gridDim.x) {
@@ -579,8 +668,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           } else {
             mbar_wait(bar_attgo, n_phase & 1);
             tc_fence_after();
-            if (ph == 0) ly_mma_phase<true>(a, tl, smem, tmem_base, cwb, cwg, c0, c1, c2);
-            else ly_mma_phase<false>(a, tl, smem, tmem_base, cwb, cwg, c0, c1, c2);
+            if (ph == 0) ly_mma_phase<true>(a, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
+            else ly_mma_phase<false>(a, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
           }
           ++n_phase;
         }
