@@ -835,9 +835,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     {
       float v[80];
       float ss = 0.f;
+      tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
-        tmem_ld16(trow + TM_H + cb + 16 * i, v + 16 * i);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           v[16 * i + j] += sC[LC_PROJ_B + cb + 16 * i + j];
@@ -885,12 +885,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
     ph_w1 ^= 1;
     gemm_wait();
-#pragma unroll 1
-    for (int i = 0; i < 5; ++i) {
-      float v[16];
-      tmem_ld16(trow + TM_G + cb + 16 * i, v);
-      *reinterpret_cast<uint4*>(sA + (cb / 8 + 2 * i) * LY_SLAB + row * 16) = pack_bf16x8(v);
-      *reinterpret_cast<uint4*>(sA + (cb / 8 + 2 * i + 1) * LY_SLAB + row * 16) = pack_bf16x8(v + 8);
+    {
+      float v[80];
+      tmem_ld80(trow + TM_G + cb, v);
+#pragma unroll
+      for (int g = 0; g < 10; ++g) *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(v + 8 * g);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -919,12 +918,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     {
       float v[80];
       float ss = 0.f;
+      tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        tmem_ld16(trow + TM_H + cb + 16 * i, v + 16 * i);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) ss = fmaf(v[16 * i + j], v[16 * i + j], ss);
-      }
+      for (int j = 0; j < 80; ++j) ss = fmaf(v[j], v[j], ss);
       sRed[wg * 128 + row] = ss;
       csync();
       const float rstd = rsqrtf((sRed[row] + sRed[128 + row]) * (1.0f / H) + 1e-6f);
@@ -979,8 +975,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
 #pragma unroll 1
       for (int i = 0; i < 5; ++i) {
         float x[16], g[16];
-        tmem_ld16(trow + TM_G + cb + 16 * i, x);
-        tmem_ld16(trow + TM_G + 160 + cb + 16 * i, g);
+        tmem_ld16x2(trow + TM_G + cb + 16 * i, x, trow + TM_G + 160 + cb + 16 * i, g);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = (x[j] + bx[16 * i + j]) * fast_silu(g[j] + bg[16 * i + j]);
         *reinterpret_cast<uint4*>(dst + (cb / 8 + 2 * i) * LY_SLAB + row * 16) = pack_bf16x8(x);
@@ -1020,12 +1015,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     {
       float v[80];
       float s1 = 0.f;
+      tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
-      for (int i = 0; i < 5; ++i) {
-        tmem_ld16(trow + TM_H + cb + 16 * i, v + 16 * i);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[16 * i + j] += sC[LS_TB + cb + 16 * i + j];
-      }
+      for (int j = 0; j < 80; ++j) v[j] += sC[LS_TB + cb + j];
       if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
         const float4* pp = reinterpret_cast<const float4*>(a.pe + (int64_t)(tl.t0 + row) * H + cb);
 #pragma unroll
@@ -1105,14 +1097,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           gemm_wait();
           LY_PHASE(12)
         }
-#pragma unroll 1
-        for (int i = 0; i < 5; ++i) {
-          float v[16];
-          tmem_ld16(trow + 160 * part + cb + 16 * i, v);
+        {
+          float v[80];
+          tmem_ld80(trow + 160 * part + cb, v);
           if (row < tl.nq) {
-            __nv_bfloat16* o = a.qkv_out + ((int64_t)(20 * part + cb / 8 + 2 * i) * a.R + tl.row0 + row) * 8;
-            *reinterpret_cast<uint4*>(o) = part == 2 ? pack_f16x8(v) : pack_bf16x8(v);
-            *reinterpret_cast<uint4*>(o + a.R * 8) = part == 2 ? pack_f16x8(v + 8) : pack_bf16x8(v + 8);
+            __nv_bfloat16* o = a.qkv_out + ((int64_t)(20 * part + cb / 8) * a.R + tl.row0 + row) * 8;
+#pragma unroll
+            for (int g = 0; g < 10; ++g)
+              *reinterpret_cast<uint4*>(o + (int64_t)g * a.R * 8) = part == 2 ? pack_f16x8(v + 8 * g) : pack_bf16x8(v + 8 * g);
           }
         }
       }
