@@ -367,5 +367,101 @@ def ddpm_loop(sd: State, tab: State, sem_idx: Tensor, x_T: Tensor, noises, t_sta
     return x
 
 
+# ----------------------------------------------------------------------------
+# schedule.py:269-531  DPMSolverPP (the sampler train_v2.py / inference_pipeline.py use)
+# ----------------------------------------------------------------------------
+def dpm_time_steps(tab: State, num_steps: int, max_t: Optional[int] = None) -> Tensor:
+    """DPMSolverPP.get_time_steps (schedule.py:299-324): timesteps uniformly spaced in lambda = log(alpha/sigma)."""
+    lam = tab["lambda_t"]
+    max_t = max_t or (lam.shape[0] - 1)
+    lambda_max = lam[1].item()
+    lambda_min = lam[max_t].item()
+    lambdas = torch.linspace(lambda_min, lambda_max, num_steps + 1)
+    ts = []
+    for l in lambdas[:-1]:
+        t = (lam - l).abs().argmin().item()
+        ts.append(max(1, min(t, max_t)))
+    return torch.tensor(ts, dtype=torch.long)
+
+
+def dpm_coefficients(tab: State, t: Tensor, t_prev: Tensor, t_prev2: Optional[Tensor] = None) -> Dict[str, Tensor]:
+    """The [B] scalars of the three update rules (schedule.py:339-438), each built with the reference's op order:
+    c0 = sigma_prev / sigma_t, c1 = alpha_prev (1 - e^-h), c2 = alpha_prev ((1 - e^-h) / h + 1),
+    c3 = alpha_prev ((1 - e^-h) / h^2 + 0.5 / h + 0.5), inv_r = 1 / (h_prev / h) (second order only)."""
+    alpha_prev = tab["sqrt_alpha_bar"][t_prev]
+    sigma_t = tab["sqrt_one_minus_alpha_bar"][t]
+    sigma_prev = tab["sqrt_one_minus_alpha_bar"][t_prev]
+    lambda_t = tab["lambda_t"][t]
+    lambda_prev = tab["lambda_t"][t_prev]
+    h = lambda_prev - lambda_t
+    out = {
+        "sa": tab["sqrt_alpha_bar"][t], "sb": tab["sqrt_one_minus_alpha_bar"][t],
+        "c0": sigma_prev / sigma_t,
+        "c1": alpha_prev * (1 - torch.exp(-h)),
+        "c2": alpha_prev * ((1 - torch.exp(-h)) / h + 1),
+        "c3": alpha_prev * ((1 - torch.exp(-h)) / (h ** 2) + 0.5 / h + 0.5),
+    }
+    if t_prev2 is not None:
+        h_prev = tab["lambda_t"][t_prev2] - lambda_prev
+        r = h_prev / h
+        out["inv_r"] = 1 / r
+    return out
+
+
+def dpm_update(x: Tensor, x0_pred: Tensor, hist: list, co: Dict[str, Tensor], order_used: int) -> Tensor:
+    """first / second / third_order_update (schedule.py:339-438) given the per-row coefficients.
+    ``hist`` is x0_history as the reference keeps it (oldest first)."""
+    b = lambda v: v[:, None, None]
+    if order_used == 1:
+        return b(co["c0"]) * x + b(co["c1"]) * x0_pred
+    if order_used == 2:
+        D1 = b(co["inv_r"]) * (x0_pred - hist[-1])
+        return b(co["c0"]) * x + b(co["c1"]) * x0_pred + b(co["c2"]) * D1 * 0.5
+    p = [x0_pred] + hist[-2:]                         # the reference's list order: [now, older, newer] (schedule.py:510)
+    D1 = p[0] - p[1]
+    D2 = p[0] - 2 * p[1] + p[2]
+    return (b(co["c0"]) * x + b(co["c1"]) * p[0] + b(co["c2"]) * D1 * 0.5 + b(co["c3"]) * D2 / 6)
+
+
+def dpm_sample(sd: State, tab: State, x_T: Tensor, sem_features: Tensor, num_steps: int = 10, order: int = 2,
+               predict_x0: bool = False, max_t: Optional[int] = None, trace: Optional[list] = None) -> Tensor:
+    """DPMSolverPP.sample (schedule.py:440-527) with the decoder's sem_features conditioning (decoder.py:83-85).
+    ``trace`` receives (x_t, model_output, x0_pred, x_next, order_used) per step for teacher-forced parity."""
+    max_t = max_t or 950
+    ts = dpm_time_steps(tab, num_steps, max_t)
+    x = x_T
+    B = x.shape[0]
+    x0_hist, t_hist = [], []
+    with torch.no_grad():
+        for i, t in enumerate(ts):
+            tt = torch.full((B,), t.item(), dtype=torch.long)
+            si = torch.full((B,), i, dtype=torch.long)
+            out = decoder_forward(sd, x, tt, None, si, sem_features=sem_features)
+            n = min(out.shape[1], x.shape[1])
+            out, x = out[:, :n], x[:, :n]
+            if predict_x0:
+                x0 = out
+            else:
+                x0 = tab["sqrt_alpha_bar"][tt][:, None, None] * x - tab["sqrt_one_minus_alpha_bar"][tt][:, None, None] * out
+            x0 = torch.clamp(x0, -3, 3)
+            tp = torch.full((B,), ts[i + 1].item() if i < len(ts) - 1 else 0, dtype=torch.long)
+            if order == 1 or len(x0_hist) == 0:
+                used, co = 1, dpm_coefficients(tab, tt, tp)
+            elif order == 2 or len(x0_hist) == 1:
+                used, co = 2, dpm_coefficients(tab, tt, tp, t_hist[-1])
+            else:
+                used, co = 3, dpm_coefficients(tab, tt, tp)
+            x_in = x
+            x = dpm_update(x, x0, x0_hist, co, used)
+            if trace is not None:
+                trace.append((x_in, out, x0, x, used))
+            x0_hist.append(x0)
+            t_hist.append(tp)
+            if len(x0_hist) > 2:
+                x0_hist.pop(0)
+                t_hist.pop(0)
+    return x
+
+
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
