@@ -8,7 +8,7 @@ arithmetic on the path is hand-written CUDA in ``lib/libedtts.so`` behind the C
 ABI of ``include/edtts.h``.  No CPU fallback, no Triton, no torch.compile.
 """
 from .config import CFG, get_device, set_seed
-from .schedule import DiffusionSchedule
+from .schedule import DiffusionSchedule, DPMSolverPP
 from .vq import VectorQuantizer
 from .decoder import EdgeDiffusionDecoder
 from .encoder import SemanticEncoder
@@ -17,5 +17,5 @@ from .conv import DepthwiseSeparableConv
 from . import dist
 
 __version__ = "0.1.0"
-__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "VectorQuantizer", "EdgeDiffusionDecoder",
+__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "EdgeDiffusionDecoder",
            "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "dist"]

@@ -70,6 +70,56 @@ __global__ void __launch_bounds__(256) ddpm_kernel(const float* __restrict__ x, 
   }
 }
 
+// DPM-Solver++ update (schedule.py:339-438) with torch's operation order, one rounding per operation (no FMA contraction).
+template <int VEC>
+__global__ void __launch_bounds__(256) dpm_kernel(const float* __restrict__ x, const float* __restrict__ mo,
+                                                  const float* __restrict__ h1, const float* __restrict__ h2,
+                                                  const float* __restrict__ coef, int order, int predict_x0,
+                                                  float* __restrict__ x_prev, float* __restrict__ x0_out, int64_t total,
+                                                  int64_t n) {
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total;
+       i += (int64_t)gridDim.x * blockDim.x * VEC) {
+    const float* c = coef + (i / n) * 8;
+    const float sa = c[0], sb = c[1], c0 = c[2], c1 = c[3], c2 = c[4], inv_r = c[5], c3 = c[6];
+    float xv[VEC], mv[VEC], av[VEC], bv[VEC], xp[VEC], xz[VEC];
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + i);
+      *reinterpret_cast<float4*>(mv) = *reinterpret_cast<const float4*>(mo + i);
+      if (order >= 2) *reinterpret_cast<float4*>(av) = *reinterpret_cast<const float4*>(h1 + i);
+      if (order >= 3) *reinterpret_cast<float4*>(bv) = *reinterpret_cast<const float4*>(h2 + i);
+    } else {
+      xv[0] = x[i];
+      mv[0] = mo[i];
+      if (order >= 2) av[0] = h1[i];
+      if (order >= 3) bv[0] = h2[i];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float p0 = predict_x0 ? mv[j] : __fsub_rn(__fmul_rn(sa, xv[j]), __fmul_rn(sb, mv[j]));
+      if (predict_x0 != 2) p0 = fminf(fmaxf(p0, -3.0f), 3.0f);
+      xz[j] = p0;
+      float r = __fadd_rn(__fmul_rn(c0, xv[j]), __fmul_rn(c1, p0));
+      if (order == 2) {
+        const float d1 = __fmul_rn(inv_r, __fsub_rn(p0, av[j]));
+        r = __fadd_rn(r, __fmul_rn(__fmul_rn(c2, d1), 0.5f));
+      } else if (order >= 3) {
+        const float d1 = __fsub_rn(p0, av[j]);
+        const float d2 = __fadd_rn(__fsub_rn(p0, __fmul_rn(2.0f, av[j])), bv[j]);
+        r = __fadd_rn(r, __fmul_rn(__fmul_rn(c2, d1), 0.5f));
+        r = __fadd_rn(r, __fdiv_rn(__fmul_rn(c3, d2), 6.0f));
+      }
+      xp[j] = r;
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
+      if (x0_out) *reinterpret_cast<float4*>(x0_out + i) = *reinterpret_cast<float4*>(xz);
+    } else {
+      x_prev[i] = xp[0];
+      if (x0_out) x0_out[i] = xz[0];
+    }
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned stream_grid(int64_t work_items) {
   const int64_t blocks = (work_items + 255) / 256;
@@ -117,4 +167,24 @@ extern "C" int edtts_ddpm_step(const float* x_t, const float* eps, const float* 
     ddpm_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, eps, noise, alphas, alpha_bar, betas,
                                                                       posterior_var, t, x_prev_out, total, n);
   return check_launch("ddpm_step");
+}
+
+extern "C" int edtts_dpm_step(const float* x_t, const float* model_out, const float* hist1, const float* hist2,
+                              const float* coef, int32_t order_used, int32_t predict_x0, float* x_prev_out, float* x0_out,
+                              int32_t B, int64_t n, void* stream) {
+  EDTTS_REQUIRE(x_t && model_out && coef && x_prev_out && B > 0 && n > 0, EDTTS_EINVAL, "dpm_step: null argument");
+  EDTTS_REQUIRE(order_used >= 1 && order_used <= 3, EDTTS_EINVAL, "dpm_step: order_used=%d", order_used);
+  EDTTS_REQUIRE((order_used < 2 || hist1) && (order_used < 3 || hist2), EDTTS_EINVAL,
+                "dpm_step: order %d needs %d history tensor(s)", order_used, order_used - 1);
+  const int64_t total = (int64_t)B * n;
+  const bool vec = n % 4 == 0 && aligned16(x_t) && aligned16(model_out) && (!hist1 || aligned16(hist1)) &&
+                   (!hist2 || aligned16(hist2)) && aligned16(x_prev_out) && (!x0_out || aligned16(x0_out));
+  LaunchScope ls(KC_SCHEDULE, as_stream(stream));
+  if (vec)
+    dpm_kernel<4><<<stream_grid(total / 4), 256, 0, as_stream(stream)>>>(x_t, model_out, hist1, hist2, coef, order_used,
+                                                                         predict_x0, x_prev_out, x0_out, total, n);
+  else
+    dpm_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, model_out, hist1, hist2, coef, order_used,
+                                                                     predict_x0, x_prev_out, x0_out, total, n);
+  return check_launch("dpm_step");
 }

@@ -111,3 +111,157 @@ class DiffusionSchedule:
         for k in _TABLES:
             setattr(self, k, getattr(self, k).to(device).contiguous())
         return self
+
+
+class DPMSolverPP:
+    """DPM-Solver++ sampler with the reference's constructor, methods and arithmetic (schedule.py:269-531): lambda-spaced
+    timesteps, v-prediction -> x0, first / second / third order updates with the reference's history handling.
+
+    Each update (model_to_x0 + clamp + the order's update rule) is ONE streaming CUDA kernel (``edtts_dpm_step``).  The
+    per-step scalars (sigma ratio, alpha_prev (1 - e^-h), ...) are evaluated with the reference's own tensor expressions
+    on the CPU copy of the schedule tables -- like the tables themselves, because exp/log differ by ulps
+    between CPU and CUDA and parity is defined against the CPU reference -- and uploaded as an [B, 8] coefficient block.
+    """
+
+    def __init__(self, schedule: DiffusionSchedule, order: int = 2, predict_x0: bool = False):
+        self.schedule = schedule
+        self.order = order
+        self.predict_x0 = predict_x0
+        self.device = schedule.device
+        self._host = None
+
+    # CPU copies of the three tables the solver reads (bit-identical: the tables were built on the CPU and moved)
+    def _tables(self):
+        if self._host is None:
+            self._host = {k: getattr(self.schedule, k).detach().cpu() for k in
+                          ("sqrt_alpha_bar", "sqrt_one_minus_alpha_bar", "lambda_t")}
+        return self._host
+
+    def get_time_steps(self, num_steps: int, max_t: Optional[int] = None) -> torch.Tensor:
+        """schedule.py:299-324."""
+        lam = self._tables()["lambda_t"]
+        max_t = max_t or (self.schedule.T - 1)
+        lambda_max = lam[1].item()
+        lambda_min = lam[max_t].item()
+        lambdas = torch.linspace(lambda_min, lambda_max, num_steps + 1)
+        timesteps = []
+        for l in lambdas[:-1]:
+            t = (lam - l).abs().argmin().item()
+            timesteps.append(max(1, min(t, max_t)))
+        return torch.tensor(timesteps, device=self.device, dtype=torch.long)
+
+    def model_to_x0(self, model_output, x_t, t):
+        """schedule.py:326-337."""
+        if self.predict_x0:
+            return model_output
+        return self.schedule.predict_x0_from_v(x_t, t, model_output)
+
+    def _coef(self, t: torch.Tensor, t_prev: torch.Tensor, t_prev2: Optional[torch.Tensor]) -> torch.Tensor:
+        """[B, 8] fp32 coefficient block of edtts_dpm_step (include/edtts.h), reference op order (schedule.py:350-431)."""
+        tb = self._tables()
+        t, t_prev = t.detach().cpu(), t_prev.detach().cpu()
+        alpha_prev = tb["sqrt_alpha_bar"][t_prev]
+        sigma_t = tb["sqrt_one_minus_alpha_bar"][t]
+        sigma_prev = tb["sqrt_one_minus_alpha_bar"][t_prev]
+        lambda_t = tb["lambda_t"][t]
+        lambda_prev = tb["lambda_t"][t_prev]
+        h = lambda_prev - lambda_t
+        co = torch.zeros(t.shape[0], 8, dtype=torch.float32)
+        co[:, 0] = tb["sqrt_alpha_bar"][t]
+        co[:, 1] = sigma_t
+        co[:, 2] = sigma_prev / sigma_t
+        co[:, 3] = alpha_prev * (1 - torch.exp(-h))
+        co[:, 4] = alpha_prev * ((1 - torch.exp(-h)) / h + 1)
+        if t_prev2 is not None:
+            h_prev = tb["lambda_t"][t_prev2.detach().cpu()] - lambda_prev
+            r = h_prev / h
+            co[:, 5] = 1 / r
+        co[:, 6] = alpha_prev * ((1 - torch.exp(-h)) / (h ** 2) + 0.5 / h + 0.5)
+        return co
+
+    def _step(self, x, model_output, hist, co, order_used, mode, want_x0=True):
+        """mode 0: model_output is v; 1: x0 (to be clamped); 2: x0 used as given."""
+        lib = _lib.load()
+        x, model_output = _lib.f32(x), _lib.f32(model_output)
+        if x.device.type != "cuda":
+            raise RuntimeError("DPMSolverPP runs on CUDA tensors only (no CPU fallback)")
+        co = co.to(x.device, non_blocking=True).contiguous()
+        x_prev = torch.empty_like(x)
+        x0 = torch.empty_like(x) if want_x0 else None
+        h1 = _lib.f32(hist[0]) if order_used >= 2 else None
+        h2 = _lib.f32(hist[1]) if order_used >= 3 else None
+        _lib.check(lib.edtts_dpm_step(_lib.ptr(x), _lib.ptr(model_output), _lib.ptr(h1) if h1 is not None else None,
+                                      _lib.ptr(h2) if h2 is not None else None, _lib.ptr(co), order_used,
+                                      mode, _lib.ptr(x_prev), _lib.ptr(x0) if want_x0 else None,
+                                      x.shape[0], x[0].numel(), _lib.stream_ptr(x.device)), "dpm_step")
+        return x_prev, x0
+
+    # the three update rules on a given x0 prediction (schedule.py:339-438)
+    def first_order_update(self, x, x0_pred, t, t_prev):
+        return self._step(x, x0_pred, [], self._coef(t, t_prev, None), 1, 2, want_x0=False)[0]
+
+    def second_order_update(self, x, x0_pred, x0_prev, t, t_prev, t_prev2):
+        return self._step(x, x0_pred, [x0_prev], self._coef(t, t_prev, t_prev2), 2, 2, want_x0=False)[0]
+
+    def third_order_update(self, x, x0_preds, t, t_prev, ts_history):
+        return self._step(x, x0_preds[0], [x0_preds[1], x0_preds[2]], self._coef(t, t_prev, None), 3, 2, want_x0=False)[0]
+
+    @torch.no_grad()
+    def sample(self, model, x_T, sem_features, num_steps: int = 10, max_t: Optional[int] = None,
+               return_intermediates: bool = False):
+        """schedule.py:440-527.  Per step: one decoder forward (sem_features conditioning, step_idx = i) and one fused
+        update kernel; the +-3 clamp of the x0 prediction is part of that kernel.  Note the reference's clamp on the
+        *unclamped* x0 happens before the update, which is what the kernel does."""
+        max_t = max_t or 950
+        timesteps = self.get_time_steps(num_steps, max_t)
+        ts = timesteps.tolist()
+        x = x_T
+        x0_history, t_history, intermediates = [], [], []
+        B = x.shape[0]
+        # The reference re-projects sem_features and the cross-attention K/V inside every model call (decoder.py:83-93);
+        # they do not depend on the step, so with this package's decoder they are prepared once (same kernels, same bits).
+        kv, S_ctx = None, 0
+        if hasattr(model, "prepare_context") and hasattr(model, "step") and x.dim() == 3 and x.is_cuda:
+            x = _lib.f32(x)
+            S_ctx = sem_features.shape[1]
+            kv = model.prepare_context(None, sem_features, x.shape[1])
+        for i, t in enumerate(ts):
+            t_tensor = torch.full((B,), t, device=x.device, dtype=torch.long)
+            step_idx = torch.full((B,), i, device=x.device, dtype=torch.long)
+            if kv is not None:                            # our decoder: context K/V computed once (identical every step)
+                mod = model.prepare_cond(t_tensor, step_idx, x.shape[1], S_ctx)
+                model_output = torch.empty_like(x)
+                args = _lib.StepArgs()
+                args.mode = _lib.STEP_EPS
+                args.eps_out = model_output.data_ptr()
+                model.step(x, mod, kv, S_ctx, args)
+            else:
+                model_output = model(x, t_tensor, sem_features=sem_features, step_idx=step_idx)
+            min_len = min(model_output.shape[1], x.shape[1])
+            model_output = model_output[:, :min_len, :]
+            x = x[:, :min_len, :]
+            t_prev = ts[i + 1] if i < len(ts) - 1 else 0
+            t_prev_tensor = torch.full((B,), t_prev, device=x.device, dtype=torch.long)
+            if self.order == 1 or len(x0_history) == 0:
+                used, hist, tp2 = 1, [], None
+            elif self.order == 2 or len(x0_history) == 1:
+                used, hist, tp2 = 2, [x0_history[-1]], t_history[-1]
+            else:
+                used, hist, tp2 = 3, x0_history[-2:], None
+            x, x0_pred = self._step(x, model_output, hist, self._coef(t_tensor, t_prev_tensor, tp2), used,
+                                    1 if self.predict_x0 else 0)
+            if return_intermediates:
+                intermediates.append(x0_pred.clone())
+            x0_history.append(x0_pred)
+            t_history.append(t_prev_tensor)
+            if len(x0_history) > 2:
+                x0_history.pop(0)
+                t_history.pop(0)
+        if return_intermediates:
+            return x, intermediates
+        return x
+
+    def to(self, device) -> "DPMSolverPP":
+        self.device = device
+        self.schedule.to(device)
+        return self

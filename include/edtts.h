@@ -201,6 +201,18 @@ int edtts_ddpm_step(const float* x_t, const float* eps, const float* noise, cons
                     const float* alpha_bar, const float* betas, const float* posterior_var, const int64_t* t,
                     float* x_prev_out, int32_t B, int64_t n, void* stream);
 
+/* DPMSolverPP first / second / third_order_update fused with model_to_x0 and the +-3 clamp (schedule.py:326-438,
+ * 479-481).  coef is [B][8] fp32 per batch row: {sqrt_alpha_bar[t], sqrt_one_minus_alpha_bar[t], c0 = sigma_prev /
+ * sigma_t, c1 = alpha_prev (1 - e^-h), c2 = alpha_prev ((1 - e^-h) / h + 1), 1 / r, c3 = alpha_prev ((1 - e^-h) / h^2 +
+ * 0.5 / h + 0.5), unused}; the caller builds them with the reference's own tensor expressions so that the update is
+ * bit-identical.  order_used 1: no history; 2: hist1 = x0_history[-1]; 3: hist1 = x0_history[-2] (older), hist2 =
+ * x0_history[-1] (the reference's list order, schedule.py:510).  predict_x0 = 0: model_out is v (x0 = sa x - sb v,
+ * clamped to +-3); 1: model_out is x0 (clamped); 2: model_out is an x0 that is used as given (the stand-alone
+ * *_order_update methods).  Writes x_prev_out and, if non-NULL, x0_out; n = elements per batch row. */
+int edtts_dpm_step(const float* x_t, const float* model_out, const float* hist1, const float* hist2, const float* coef,
+                   int32_t order_used, int32_t predict_x0, float* x_prev_out, float* x0_out, int32_t B, int64_t n,
+                   void* stream);
+
 /* --- DepthwiseSeparableConv (layers/conv.py:10-64), operator level ---------- */
 /* x [B,C_in,T] -> y [B,C_out,T_out], T_out = (T + 2*(k/2) - k)/stride + 1:
  * depthwise k taps (no bias) -> pointwise 1x1 (+bias) -> GroupNorm(min(8,C_out)) -> GELU.

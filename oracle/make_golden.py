@@ -18,7 +18,36 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 ROWS = [0, 1, 63, 64, 65, 127, 128, 129, 198, 199]   # band-edge rows kept from hidden states
 
 
-def main():
+def make_dpm(ref, meta):
+    """DPMSolverPP.sample (schedule.py:440-527) through the reference decoder's sem_features path: final sample and the
+    per-step (x_t, model_output) trace for orders 1-3, plus the lambda-spaced timesteps."""
+    import importlib
+    S = importlib.import_module("edge_diffusion_tts.schedule")
+    dec, sched = ref["decoder"], ref["schedule"]
+    feats = synth.synth_features(21, 2, 20, 128)
+    xT = synth.synth_noise(21, 2, 40)
+    runs = {}
+    for order, steps in ((1, 5), (2, 5), (3, 5), (2, 3), (3, 10)):
+        solver = S.DPMSolverPP(sched, order=order)
+        trace = []
+
+        def spy(x, t, sem_idx=None, step_idx=None, sem_features=None):
+            out = dec(x, t, sem_idx, step_idx, sem_features=sem_features)
+            trace.append(dict(x_t=x.clone(), t=int(t[0]), step=int(step_idx[0]), out=out.clone()))
+            return out
+
+        with torch.no_grad():
+            x, inter = solver.sample(spy, xT, feats, num_steps=steps, return_intermediates=True)
+        if steps == 10:
+            trace, inter = [trace[0], trace[-1]], [inter[0], inter[-1]]
+        elif (order, steps) not in ((2, 5), (3, 5)):      # full traces only where the tests teacher-force
+            trace, inter = [], []
+        runs[(order, steps)] = dict(x=x, trace=trace, x0=inter, timesteps=solver.get_time_steps(steps, 950))
+    ts = {n: S.DPMSolverPP(sched).get_time_steps(n) for n in (1, 4, 10, 20)}
+    torch.save(dict(meta=meta, seed=21, B=2, S=20, runs=runs, timesteps_full=ts), os.path.join(OUT, "dpm.pt"))
+
+
+def main(only=None):
     torch.manual_seed(0)
     torch.set_num_threads(1)          # fixed summation order for the recorded outputs
     os.makedirs(OUT, exist_ok=True)
@@ -26,6 +55,9 @@ def main():
     E, dec, sched = ref["E"], ref["decoder"], ref["schedule"]
     sd = synth.synth_decoder_state(0)
     meta = dict(weights=synth.state_checksum(sd), torch=torch.__version__)
+    if only == "dpm":                 # fixtures added later are generated alone; the older files stay byte-identical
+        make_dpm(ref, meta)
+        return
 
     # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
     B, S = 2, 100
@@ -126,9 +158,11 @@ def main():
             conv[name] = dict(shape=(cin, cout, k, stride, B, T), y=m(xin))
     torch.save(dict(meta=meta, seed=16, cases=conv), os.path.join(OUT, "dsconv.pt"))
 
+    make_dpm(ref, meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(sys.argv[1] if len(sys.argv) > 1 else None)

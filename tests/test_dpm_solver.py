@@ -1,0 +1,191 @@
+"""DPM-Solver++ (reference schedule.py:269-531) with the decoder's sem_features path.
+
+CPU part: the oracle restatement (oracle/edtts_oracle.py::dpm_*) against the fixture recorded from the unmodified reference
+(tests/golden/dpm.pt, oracle/make_golden.py::make_dpm) -- bit-equal update rules and timesteps.
+GPU part: edtts_dpm_step / DPMSolverPP against the oracle:
+  * update kernel given identical (x, model_output, history): bit-exact, all three orders, ragged sizes
+  * sample(), teacher-forced per step (the reference's x_t fed to the decoder): fp32 max-abs <= 1e-4, bf16 rel-L2 <= 1e-2
+  * sample(), free-running: fp32 rel-L2 <= 1e-3, bf16 rel-L2 <= 5e-2 (sampling starts at t = 950, not 999: no 64,000x gain)
+"""
+import pytest
+import torch
+
+from oracle import edtts_oracle as O
+from oracle import synth
+
+DEV = "cuda:0"
+TOL = 2e-5   # fixtures were recorded single-threaded; thread count changes fp32 summation order
+
+
+def rel_l2(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+# ------------------------------------------------------------------ CPU: oracle vs reference fixture
+def test_oracle_time_steps(golden):
+    g = golden("dpm")
+    tab = O.cosine_schedule(1000)
+    for n, ts in g["timesteps_full"].items():
+        assert torch.equal(O.dpm_time_steps(tab, n), ts), n
+    for (order, steps), r in g["runs"].items():
+        assert torch.equal(O.dpm_time_steps(tab, steps, 950), r["timesteps"])
+
+
+def test_oracle_update_rules_bit_equal(golden):
+    """Teacher-forced: given the reference's own (x_t, model_output) per step the oracle's x0 and next x are bit-equal."""
+    g = golden("dpm")
+    tab = O.cosine_schedule(1000)
+    for (order, steps) in ((2, 5), (3, 5)):
+        r = g["runs"][(order, steps)]
+        ts = r["timesteps"]
+        hist, t_hist = [], []
+        for i, tr in enumerate(r["trace"]):
+            B = tr["x_t"].shape[0]
+            tt = torch.full((B,), int(ts[i]), dtype=torch.long)
+            tp = torch.full((B,), int(ts[i + 1]) if i < steps - 1 else 0, dtype=torch.long)
+            x0 = torch.clamp(tab["sqrt_alpha_bar"][tt][:, None, None] * tr["x_t"]
+                             - tab["sqrt_one_minus_alpha_bar"][tt][:, None, None] * tr["out"], -3, 3)
+            assert torch.equal(x0, r["x0"][i]), (order, i)
+            if order == 1 or not hist:
+                used, co = 1, O.dpm_coefficients(tab, tt, tp)
+            elif order == 2 or len(hist) == 1:
+                used, co = 2, O.dpm_coefficients(tab, tt, tp, t_hist[-1])
+            else:
+                used, co = 3, O.dpm_coefficients(tab, tt, tp)
+            x_next = O.dpm_update(tr["x_t"], x0, hist, co, used)
+            ref_next = r["trace"][i + 1]["x_t"] if i + 1 < steps else r["x"]
+            assert torch.equal(x_next, ref_next), (order, i, used)
+            hist.append(x0)
+            t_hist.append(tp)
+            if len(hist) > 2:
+                hist.pop(0)
+                t_hist.pop(0)
+
+
+def test_oracle_sample_vs_reference(golden):
+    g = golden("dpm")
+    sd = synth.synth_decoder_state(0)
+    tab = O.cosine_schedule(1000)
+    feats = synth.synth_features(g["seed"], g["B"], g["S"], 128)
+    xT = synth.synth_noise(g["seed"], g["B"], 2 * g["S"])
+    for (order, steps), r in g["runs"].items():
+        if steps == 10:
+            continue
+        x = O.dpm_sample(sd, tab, xT, feats, steps, order)
+        assert (x - r["x"]).abs().max().item() < 1e-4, (order, steps)
+
+
+# ------------------------------------------------------------------ GPU
+@pytest.fixture(scope="module")
+def gpu(lib):
+    import edge_diffusion_tts_b200 as E
+    assert torch.cuda.is_available() and lib.edtts_device_supported() == 1, "needs an sm_100 device"
+    cfg = E.CFG(device=DEV)
+    sd = synth.synth_decoder_state(0)
+    dec = E.EdgeDiffusionDecoder(cfg).to(DEV).eval()
+    dec.load_state_dict(sd, strict=True)
+    sched = E.DiffusionSchedule(cfg.diff_steps, device=DEV)
+    return dict(E=E, cfg=cfg, sd=sd, dec=dec, sched=sched, tab=O.cosine_schedule(cfg.diff_steps))
+
+
+@pytest.mark.gpu
+def test_time_steps_match_reference(gpu, golden):
+    g = golden("dpm")
+    solver = gpu["E"].DPMSolverPP(gpu["sched"])
+    for n, ts in g["timesteps_full"].items():
+        assert torch.equal(solver.get_time_steps(n).cpu(), ts), n
+    assert torch.equal(solver.get_time_steps(5, 950).cpu(), g["runs"][(2, 5)]["timesteps"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,D", [(3, 7, 80), (2, 801, 80), (1, 1, 3), (5, 64, 80)])
+def test_update_kernel_bit_exact(gpu, B, T, D):
+    """first / second / third_order_update on random tensors against the oracle's torch expressions."""
+    E, tab = gpu["E"], gpu["tab"]
+    gen = torch.Generator().manual_seed(B * 1000 + T)
+    x, p0, p1, p2 = (torch.randn(B, T, D, generator=gen) for _ in range(4))
+    t = torch.randint(200, 951, (B,), generator=gen)
+    tp = (t - torch.randint(1, 150, (B,), generator=gen)).clamp_min(0)
+    tp2 = torch.randint(1, 1000, (B,), generator=gen)
+    solver = E.DPMSolverPP(gpu["sched"], order=3)
+    d = lambda v: v.to(DEV)
+    got1 = solver.first_order_update(d(x), d(p0), d(t), d(tp))
+    assert torch.equal(got1.cpu(), O.dpm_update(x, p0, [], O.dpm_coefficients(tab, t, tp), 1))
+    got2 = solver.second_order_update(d(x), d(p0), d(p1), d(t), d(tp), d(tp2))
+    assert torch.equal(got2.cpu(), O.dpm_update(x, p0, [p1], O.dpm_coefficients(tab, t, tp, tp2), 2))
+    got3 = solver.third_order_update(d(x), [d(p0), d(p1), d(p2)], d(t), d(tp), [d(tp2), d(tp2)])
+    assert torch.equal(got3.cpu(), O.dpm_update(x, p0, [p1, p2], O.dpm_coefficients(tab, t, tp), 3))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("order,steps", [(2, 5), (3, 5)])
+def test_sample_teacher_forced_vs_reference_fixture(gpu, golden, precision, order, steps):
+    """The reference's x_t of every step goes through our decoder (sem_features path) and the fused update kernel."""
+    g = golden("dpm")
+    r = g["runs"][(order, steps)]
+    E, dec = gpu["E"], gpu["dec"]
+    dec.precision = precision
+    try:
+        solver = E.DPMSolverPP(gpu["sched"], order=order)
+        feats = synth.synth_features(g["seed"], g["B"], g["S"], 128).to(DEV)
+        ts = r["timesteps"]
+        hist, t_hist = [], []
+        for i, tr in enumerate(r["trace"]):
+            B = tr["x_t"].shape[0]
+            tt = torch.full((B,), int(ts[i]), dtype=torch.long, device=DEV)
+            si = torch.full((B,), i, dtype=torch.long, device=DEV)
+            tp = torch.full((B,), int(ts[i + 1]) if i < steps - 1 else 0, dtype=torch.long, device=DEV)
+            out = dec(tr["x_t"].to(DEV), tt, sem_features=feats, step_idx=si)
+            if precision == "fp32":
+                assert (out.cpu() - tr["out"]).abs().max().item() <= 1e-4, (order, i)
+            else:
+                assert rel_l2(out, tr["out"]) <= 1e-2, (order, i)
+            # the update given the REFERENCE's model output: bit-exact
+            if order == 1 or not hist:
+                used, h, tp2 = 1, [], None
+            elif order == 2 or len(hist) == 1:
+                used, h, tp2 = 2, [hist[-1]], t_hist[-1]
+            else:
+                used, h, tp2 = 3, hist[-2:], None
+            x_next, x0 = solver._step(tr["x_t"].to(DEV), tr["out"].to(DEV), h, solver._coef(tt, tp, tp2), used, 0)
+            assert torch.equal(x0.cpu(), r["x0"][i]), (order, i)
+            ref_next = r["trace"][i + 1]["x_t"] if i + 1 < steps else r["x"]
+            assert torch.equal(x_next.cpu(), ref_next), (order, i, used)
+            hist.append(x0)
+            t_hist.append(tp)
+            if len(hist) > 2:
+                hist.pop(0)
+                t_hist.pop(0)
+    finally:
+        dec.precision = "fp32"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision,bar", [("fp32", 1e-3), ("bf16", 5e-2)])
+def test_sample_free_running(gpu, golden, precision, bar):
+    g = golden("dpm")
+    E, dec = gpu["E"], gpu["dec"]
+    dec.precision = precision
+    try:
+        feats = synth.synth_features(g["seed"], g["B"], g["S"], 128).to(DEV)
+        xT = synth.synth_noise(g["seed"], g["B"], 2 * g["S"]).to(DEV)
+        for (order, steps), r in g["runs"].items():
+            solver = E.DPMSolverPP(gpu["sched"], order=order)
+            x, inter = solver.sample(dec, xT, feats, num_steps=steps, return_intermediates=True)
+            assert len(inter) == steps and x.shape == xT.shape
+            assert rel_l2(x, r["x"]) <= bar, (order, steps, rel_l2(x, r["x"]))
+    finally:
+        dec.precision = "fp32"
+
+
+@pytest.mark.gpu
+def test_sample_larger_batch_vs_oracle(gpu):
+    """B = 6, S = 150 (T = 300, three tiles per utterance), 4 steps, order 2, fp32, against the oracle sampler."""
+    E, dec = gpu["E"], gpu["dec"]
+    feats = synth.synth_features(31, 6, 150, 128)
+    xT = synth.synth_noise(31, 6, 300)
+    ref = O.dpm_sample(gpu["sd"], gpu["tab"], xT, feats, 4, 2)
+    x = E.DPMSolverPP(gpu["sched"], order=2).sample(dec, xT.to(DEV), feats.to(DEV), num_steps=4)
+    assert rel_l2(x, ref) <= 1e-3

@@ -57,3 +57,20 @@ def test_vq_and_conv(ref):
     x = synth.synth_noise(2, 2, 32, 61, tag="c")
     with torch.no_grad():
         assert (m(x) - O.dsconv_forward(sd, x, 2)).abs().max().item() < 1e-6
+
+
+def test_dpm_solver(ref):
+    """DPMSolverPP.sample of the live reference (schedule.py:440-527) == the oracle restatement, bit for bit."""
+    import importlib
+    S = importlib.import_module("edge_diffusion_tts.schedule")
+    sd = synth.synth_decoder_state(0)
+    tab = O.cosine_schedule(1000)
+    feats = synth.synth_features(41, 1, 12, 128)
+    xT = synth.synth_noise(41, 1, 24)
+    for order, steps in ((1, 3), (2, 4), (3, 6)):
+        solver = S.DPMSolverPP(ref["schedule"], order=order)
+        with torch.no_grad():
+            want = solver.sample(ref["decoder"], xT, feats, num_steps=steps)
+        assert torch.equal(solver.get_time_steps(steps, 950), O.dpm_time_steps(tab, steps, 950))
+        got = O.dpm_sample(sd, tab, xT, feats, steps, order)
+        assert (got - want).abs().max().item() < 2e-5, (order, steps)
