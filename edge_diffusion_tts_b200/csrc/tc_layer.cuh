@@ -477,9 +477,15 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     bool need[2], full[2];
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-      need[ch] = ch < nch && __any_sync(0xffffffffu, any && lo <= ch * 32 + 31 && hi >= ch * 32);   // warp-uniform
-      full[ch] = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
+      if (WINDOW) {
+        need[ch] = ch < nch && __any_sync(0xffffffffu, any && lo <= ch * 32 + 31 && hi >= ch * 32);   // warp-uniform
+        full[ch] = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
+      } else {                                            // context keys: the same range for every row, no votes needed
+        need[ch] = ch < nch;
+        full[ch] = hi >= ch * 32 + 31;
+      }
     }
+    if (lq == 0) LY_TR(wg, 9)
     // ---- block maximum, lazy update of the running maximum ------------------------------------------------
     float b0 = -INFINITY, b1 = -INFINITY, b2 = -INFINITY, b3 = -INFINITY;
 #pragma unroll
@@ -504,6 +510,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
 #else
     const float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * c;
 #endif
+    if (lq == 0) LY_TR(wg, 10)
     const bool grow = bmax > m_run + 6.0f;                // also true for the first finite block maximum
     if (__any_sync(0xffffffffu, grow)) {
       const float m_upd = grow ? bmax : m_run;
@@ -524,8 +531,14 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       m_run = m_upd;
     }
     const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+    if (lq == 0) LY_TR(wg, 11)
     LY_FC(2)
     // ---- p -> P (f16x2 per 32-bit column, tensor memory): the A operand of P V, no shared-memory round trip ----
+#ifdef LY_PINGPONG
+    // The two warps of a sub-partition (same lane quarter, warpgroups 0 / 1) take turns on the MUFU-bound section: while
+    // one exponentiates, the other runs its barrier / TMEM-load / maximum work.  Token barrier 4 + 2 lq + wg.
+    named_bar_sync(4 + 2 * lq + wg, 64);
+#endif
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       if (ch >= nch) continue;
@@ -552,6 +565,9 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       }
       tmem_st16u(tP + 16 * ch, pk);
     }
+#ifdef LY_PINGPONG
+    named_bar_arrive(4 + 2 * lq + (wg ^ 1), 64);          // pass the token to the partner warp
+#endif
     LY_FC(3)
     if (lq == 0) LY_TR(wg, 4)
     tmem_st_wait();
@@ -716,6 +732,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
   };
 
+#ifdef LY_PINGPONG
+  if (wg == 1) named_bar_arrive(4 + 2 * lq, 64);          // the token starts with warpgroup 0
+#endif
   long long pc[PROF ? 16 : 1] = {0}, fcw[PROF ? 8 : 1] = {0}, fcx[PROF ? 8 : 1] = {0};
   long long pc_last = PROF ? clock64() : 0;
 #define LY_PHASE(i)                                   \
