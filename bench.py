@@ -161,6 +161,8 @@ def main():
     dev = torch.device("cuda", local)
     import torch.distributed as dist
     if world > 1:
+        # NCCL writes its version banner / debug log to stdout by default: keep stdout to the ONE JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as ge
