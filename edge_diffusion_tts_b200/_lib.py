@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("EDTTS_LIB") or os.path.join(_HERE, "lib", "libedtts.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
-STEP_EPS, STEP_DDIM, STEP_DDPM = 0, 1, 2
+STEP_EPS, STEP_DDIM, STEP_DDPM, STEP_DPM = 0, 1, 2, 3
 N_LAYERS = 4
 
 _f = C.c_void_p  # device pointers travel as void*
@@ -42,7 +42,8 @@ class DecoderWeights(C.Structure):
 class StepArgs(C.Structure):
     _fields_ = [("mode", C.c_int32), ("write_x_prev", C.c_int32), ("t", _f), ("t_prev", _f), ("alpha_bar", _f),
                 ("alphas", _f), ("betas", _f), ("posterior_var", _f), ("noise", _f), ("eps_out", _f),
-                ("x_prev_out", _f), ("x0_out", _f)]
+                ("x_prev_out", _f), ("x0_out", _f), ("dpm_coef", _f), ("dpm_hist1", _f), ("dpm_hist2", _f),
+                ("dpm_order", C.c_int32), ("dpm_predict_x0", C.c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/edtts.h

@@ -91,4 +91,24 @@ __device__ __forceinline__ float ddpm_update(float x, float e, float nz, float a
   return __fadd_rn(mean, __fmul_rn(__fmul_rn(nonzero, __fsqrt_rn(var)), nz));
 }
 
+// DPM-Solver++ update (schedule.py:326-438, 479-481), torch operation order, one rounding per operation.
+// c = {sa, sb, c0, c1, c2, 1/r, c3, -}; mode 0: mo is v, 1: mo is x0 (both clamped to +-3), 2: mo is x0 used as given.
+__device__ __forceinline__ void dpm_update(float x, float mo, float h1, float h2, const float* c, int order, int mode,
+                                           float& x_prev, float& x0) {
+  float p0 = mode ? mo : __fsub_rn(__fmul_rn(c[0], x), __fmul_rn(c[1], mo));
+  if (mode != 2) p0 = fminf(fmaxf(p0, -3.0f), 3.0f);
+  x0 = p0;
+  float r = __fadd_rn(__fmul_rn(c[2], x), __fmul_rn(c[3], p0));
+  if (order == 2) {
+    const float d1 = __fmul_rn(c[5], __fsub_rn(p0, h1));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(c[4], d1), 0.5f));
+  } else if (order >= 3) {
+    const float d1 = __fsub_rn(p0, h1);
+    const float d2 = __fadd_rn(__fsub_rn(p0, __fmul_rn(2.0f, h1)), h2);
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(c[4], d1), 0.5f));
+    r = __fadd_rn(r, __fdiv_rn(__fmul_rn(c[6], d2), 6.0f));
+  }
+  x_prev = r;
+}
+
 }  // namespace edtts

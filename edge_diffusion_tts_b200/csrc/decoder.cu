@@ -301,6 +301,11 @@ extern "C" int edtts_decoder_step(const edtts_decoder_weights* w, const float* x
                         args->noise && args->x_prev_out,
                     EDTTS_EINVAL, "decoder_step: DDPM needs t, tables, noise and x_prev_out");
       break;
+    case EDTTS_STEP_DPM:
+      EDTTS_REQUIRE(args->dpm_coef && args->x_prev_out && args->dpm_order >= 1 && args->dpm_order <= 3 &&
+                        (args->dpm_order < 2 || args->dpm_hist1) && (args->dpm_order < 3 || args->dpm_hist2),
+                    EDTTS_EINVAL, "decoder_step: DPM needs coefficients, x_prev_out and order-1 history tensors");
+      break;
     default:
       set_error("decoder_step: unknown mode %d", args->mode);
       return EDTTS_EINVAL;

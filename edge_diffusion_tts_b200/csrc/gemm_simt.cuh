@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(const GemmArgs g) 
     const int64_t row = row0 + ty * 8 + i;
     if (row >= g.rows) continue;
     float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
-    if (g.epi == EPI_STEP && g.step.mode != EDTTS_STEP_EPS) {
+    if (g.epi == EPI_STEP && (g.step.mode == EDTTS_STEP_DDIM || g.step.mode == EDTTS_STEP_DDPM)) {
       const int b = (int)(row / g.rows_per_batch);
       const int64_t t = g.step.t[b];
       ab_t = g.step.alpha_bar[t];
@@ -214,6 +214,13 @@ __global__ void __launch_bounds__(G_THREADS) gemm_simt_kernel(const GemmArgs g) 
           if (g.step.write_x_prev && g.step.x_prev_out) g.step.x_prev_out[o] = xp;
         } else if (g.step.mode == EDTTS_STEP_DDPM) {
           g.step.x_prev_out[o] = ddpm_update(g.x_t[o], v, g.step.noise[o], al, ab_t, be, pv, nzm);
+        } else if (g.step.mode == EDTTS_STEP_DPM) {
+          const int ord = g.step.dpm_order;
+          float xp, x0;
+          dpm_update(g.x_t[o], v, ord >= 2 ? g.step.dpm_hist1[o] : 0.f, ord >= 3 ? g.step.dpm_hist2[o] : 0.f,
+                     g.step.dpm_coef + (row / g.rows_per_batch) * 8, ord, g.step.dpm_predict_x0 ? 1 : 0, xp, x0);
+          if (g.step.x0_out) g.step.x0_out[o] = x0;
+          g.step.x_prev_out[o] = xp;
         }
       } else {
         g.out[o] = v;

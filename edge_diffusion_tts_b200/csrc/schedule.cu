@@ -80,7 +80,6 @@ __global__ void __launch_bounds__(256) dpm_kernel(const float* __restrict__ x, c
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < total;
        i += (int64_t)gridDim.x * blockDim.x * VEC) {
     const float* c = coef + (i / n) * 8;
-    const float sa = c[0], sb = c[1], c0 = c[2], c1 = c[3], c2 = c[4], inv_r = c[5], c3 = c[6];
     float xv[VEC], mv[VEC], av[VEC], bv[VEC], xp[VEC], xz[VEC];
     if (VEC == 4) {
       *reinterpret_cast<float4*>(xv) = *reinterpret_cast<const float4*>(x + i);
@@ -94,22 +93,8 @@ __global__ void __launch_bounds__(256) dpm_kernel(const float* __restrict__ x, c
       if (order >= 3) bv[0] = h2[i];
     }
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float p0 = predict_x0 ? mv[j] : __fsub_rn(__fmul_rn(sa, xv[j]), __fmul_rn(sb, mv[j]));
-      if (predict_x0 != 2) p0 = fminf(fmaxf(p0, -3.0f), 3.0f);
-      xz[j] = p0;
-      float r = __fadd_rn(__fmul_rn(c0, xv[j]), __fmul_rn(c1, p0));
-      if (order == 2) {
-        const float d1 = __fmul_rn(inv_r, __fsub_rn(p0, av[j]));
-        r = __fadd_rn(r, __fmul_rn(__fmul_rn(c2, d1), 0.5f));
-      } else if (order >= 3) {
-        const float d1 = __fsub_rn(p0, av[j]);
-        const float d2 = __fadd_rn(__fsub_rn(p0, __fmul_rn(2.0f, av[j])), bv[j]);
-        r = __fadd_rn(r, __fmul_rn(__fmul_rn(c2, d1), 0.5f));
-        r = __fadd_rn(r, __fdiv_rn(__fmul_rn(c3, d2), 6.0f));
-      }
-      xp[j] = r;
-    }
+    for (int j = 0; j < VEC; ++j)
+      dpm_update(xv[j], mv[j], order >= 2 ? av[j] : 0.f, order >= 3 ? bv[j] : 0.f, c, order, predict_x0, xp[j], xz[j]);
     if (VEC == 4) {
       *reinterpret_cast<float4*>(x_prev + i) = *reinterpret_cast<float4*>(xp);
       if (x0_out) *reinterpret_cast<float4*>(x0_out + i) = *reinterpret_cast<float4*>(xz);

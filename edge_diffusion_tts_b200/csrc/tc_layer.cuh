@@ -1140,7 +1140,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       if (tid == 0 && more) load_first();
       const edtts_step_args& sa = a.step;
       float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
-      if (sa.mode != EDTTS_STEP_EPS && row < tl.nq) {
+      if ((sa.mode == EDTTS_STEP_DDIM || sa.mode == EDTTS_STEP_DDPM) && row < tl.nq) {
         const int64_t tt = sa.t[tl.b];
         ab_t = sa.alpha_bar[tt];
         if (sa.mode == EDTTS_STEP_DDIM) {
@@ -1188,6 +1188,22 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
             xp.y = ddpm_update(x.y, e[4 * q + 1], nz.y, al, ab_t, be, pv, nzm);
             xp.z = ddpm_update(x.z, e[4 * q + 2], nz.z, al, ab_t, be, pv, nzm);
             xp.w = ddpm_update(x.w, e[4 * q + 3], nz.w, al, ab_t, be, pv, nzm);
+            reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
+          }
+        } else if (sa.mode == EDTTS_STEP_DPM) {
+          const float* dc = sa.dpm_coef + tl.b * 8;
+          const int ord = sa.dpm_order, pm = sa.dpm_predict_x0 ? 1 : 0;
+#pragma unroll
+          for (int q = 0; q < 10; ++q) {
+            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            const float4 ha = ord >= 2 ? reinterpret_cast<const float4*>(sa.dpm_hist1 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 hb = ord >= 3 ? reinterpret_cast<const float4*>(sa.dpm_hist2 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 xp, x0;
+            dpm_update(x.x, e[4 * q], ha.x, hb.x, dc, ord, pm, xp.x, x0.x);
+            dpm_update(x.y, e[4 * q + 1], ha.y, hb.y, dc, ord, pm, xp.y, x0.y);
+            dpm_update(x.z, e[4 * q + 2], ha.z, hb.z, dc, ord, pm, xp.z, x0.z);
+            dpm_update(x.w, e[4 * q + 3], ha.w, hb.w, dc, ord, pm, xp.w, x0.w);
+            if (sa.x0_out) reinterpret_cast<float4*>(sa.x0_out + o)[q] = x0;
             reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
           }
         }

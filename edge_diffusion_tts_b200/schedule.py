@@ -209,47 +209,29 @@ class DPMSolverPP:
     @torch.no_grad()
     def sample(self, model, x_T, sem_features, num_steps: int = 10, max_t: Optional[int] = None,
                return_intermediates: bool = False):
-        """schedule.py:440-527.  Per step: one decoder forward (sem_features conditioning, step_idx = i) and one fused
-        update kernel; the +-3 clamp of the x0 prediction is part of that kernel.  Note the reference's clamp on the
-        *unclamped* x0 happens before the update, which is what the kernel does."""
+        """schedule.py:440-527.  With this package's decoder the whole loop runs fused and graph-captured
+        (``_sample_fused``); any other callable model takes the reference's step-by-step route with one update kernel
+        per step."""
         max_t = max_t or 950
-        timesteps = self.get_time_steps(num_steps, max_t)
-        ts = timesteps.tolist()
+        ts = self.get_time_steps(num_steps, max_t).tolist()
+        if (hasattr(model, "prepare_context") and hasattr(model, "step") and x_T.dim() == 3 and x_T.is_cuda
+                and sem_features.shape[0] == x_T.shape[0]):
+            return self._sample_fused(model, x_T, sem_features, ts, return_intermediates)
         x = x_T
         x0_history, t_history, intermediates = [], [], []
         B = x.shape[0]
-        # The reference re-projects sem_features and the cross-attention K/V inside every model call (decoder.py:83-93);
-        # they do not depend on the step, so with this package's decoder they are prepared once (same kernels, same bits).
-        kv, S_ctx = None, 0
-        if hasattr(model, "prepare_context") and hasattr(model, "step") and x.dim() == 3 and x.is_cuda:
-            x = _lib.f32(x)
-            S_ctx = sem_features.shape[1]
-            kv = model.prepare_context(None, sem_features, x.shape[1])
         for i, t in enumerate(ts):
             t_tensor = torch.full((B,), t, device=x.device, dtype=torch.long)
             step_idx = torch.full((B,), i, device=x.device, dtype=torch.long)
-            if kv is not None:                            # our decoder: context K/V computed once (identical every step)
-                mod = model.prepare_cond(t_tensor, step_idx, x.shape[1], S_ctx)
-                model_output = torch.empty_like(x)
-                args = _lib.StepArgs()
-                args.mode = _lib.STEP_EPS
-                args.eps_out = model_output.data_ptr()
-                model.step(x, mod, kv, S_ctx, args)
-            else:
-                model_output = model(x, t_tensor, sem_features=sem_features, step_idx=step_idx)
+            model_output = model(x, t_tensor, sem_features=sem_features, step_idx=step_idx)
             min_len = min(model_output.shape[1], x.shape[1])
             model_output = model_output[:, :min_len, :]
             x = x[:, :min_len, :]
             t_prev = ts[i + 1] if i < len(ts) - 1 else 0
             t_prev_tensor = torch.full((B,), t_prev, device=x.device, dtype=torch.long)
-            if self.order == 1 or len(x0_history) == 0:
-                used, hist, tp2 = 1, [], None
-            elif self.order == 2 or len(x0_history) == 1:
-                used, hist, tp2 = 2, [x0_history[-1]], t_history[-1]
-            else:
-                used, hist, tp2 = 3, x0_history[-2:], None
-            x, x0_pred = self._step(x, model_output, hist, self._coef(t_tensor, t_prev_tensor, tp2), used,
-                                    1 if self.predict_x0 else 0)
+            used, nh, tp2 = self._order_used(len(x0_history), t_history)
+            x, x0_pred = self._step(x, model_output, x0_history[-nh:] if nh else [],
+                                    self._coef(t_tensor, t_prev_tensor, tp2), used, 1 if self.predict_x0 else 0)
             if return_intermediates:
                 intermediates.append(x0_pred.clone())
             x0_history.append(x0_pred)
@@ -259,6 +241,93 @@ class DPMSolverPP:
                 t_history.pop(0)
         if return_intermediates:
             return x, intermediates
+        return x
+
+    def _order_used(self, n_hist: int, t_history):
+        """The reference's choice of update rule (schedule.py:495-508) -> (order used, history tensors, t_prev2)."""
+        if self.order == 1 or n_hist == 0:
+            return 1, 0, None
+        if self.order == 2 or n_hist == 1:
+            return 2, 1, t_history[-1]
+        return 3, 2, None
+
+    use_cuda_graph = True
+
+    def _sample_fused(self, dec, x_T, sem_features, ts, return_intermediates):
+        """The same loop with (a) the context K/V prepared once -- the reference re-projects sem_features inside every
+        model call (decoder.py:83-93) although they do not depend on the step, (b) model_to_x0 + clamp + update rule
+        fused into the last decoder kernel of each step (EDTTS_STEP_DPM), x updated in place, x0 history in a ring of
+        buffers, and (c) the whole loop replayed from a CUDA graph (per-shape plan, like EdgeInference.generate_mel)."""
+        dev = x_T.device
+        B, T, _ = x_T.shape
+        S = sem_features.shape[1]
+        n = len(ts)
+        key = (B, T, S, tuple(ts), self.order, self.predict_x0, bool(return_intermediates), dec.precision, str(dev))
+        plans = self.__dict__.setdefault("_plans", {})
+        p = plans.get(key)
+        if p is None:
+            p = {"graph": None, "epoch": None}
+            p["x"] = torch.empty(B, T, x_T.shape[2], dtype=torch.float32, device=dev)
+            p["feats"] = torch.empty(B, S, sem_features.shape[2], dtype=torch.float32, device=dev)
+            p["x0"] = [torch.empty_like(p["x"]) for _ in range(n if return_intermediates else min(n, 3))]
+            cfg = dec.cfg
+            p["kv"] = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, dtype=torch.float32, device=dev)
+            p["mods"] = [torch.empty(B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=dev) for _ in range(n)]
+            nb_ctx, nb_step = dec.workspace_bytes(B, T, S)
+            p["ws_ctx"] = torch.empty(max(nb_ctx, 256), dtype=torch.uint8, device=dev)
+            p["ws_step"] = torch.empty(max(nb_step, 256), dtype=torch.uint8, device=dev)
+            p["t"], p["si"], p["coef"], p["used"] = [], [], [], []
+            t_hist, n_hist = [], 0
+            for i, t in enumerate(ts):
+                tt = torch.full((B,), t, dtype=torch.long)
+                tp = torch.full((B,), ts[i + 1] if i < n - 1 else 0, dtype=torch.long)
+                used, nh, tp2 = self._order_used(n_hist, t_hist)
+                p["t"].append(tt.to(dev))
+                p["si"].append(torch.full((B,), i, dtype=torch.long, device=dev))
+                p["coef"].append(self._coef(tt, tp, tp2).to(dev).contiguous())
+                p["used"].append(used)
+                t_hist = (t_hist + [tp])[-2:]
+                n_hist = min(n_hist + 1, 2)
+            plans[key] = p
+
+        def run():
+            dec.prepare_context(None, p["feats"], T, out=p["kv"], ws=p["ws_ctx"])
+            for i in range(n):
+                dec.prepare_cond(p["t"][i], p["si"][i], T, S, out=p["mods"][i])
+            nb = len(p["x0"])
+            for i in range(n):
+                a = _lib.StepArgs()
+                a.mode = _lib.STEP_DPM
+                a.dpm_coef = p["coef"][i].data_ptr()
+                a.dpm_order = p["used"][i]
+                a.dpm_predict_x0 = 1 if self.predict_x0 else 0
+                if p["used"][i] == 2:
+                    a.dpm_hist1 = p["x0"][(i - 1) % nb].data_ptr()
+                elif p["used"][i] == 3:                               # the reference's order: [older, newer]
+                    a.dpm_hist1 = p["x0"][(i - 2) % nb].data_ptr()
+                    a.dpm_hist2 = p["x0"][(i - 1) % nb].data_ptr()
+                a.x_prev_out = p["x"].data_ptr()                      # in place: element-wise read-then-write
+                a.x0_out = p["x0"][i % nb].data_ptr()
+                dec.step(p["x"], p["mods"][i], p["kv"], S, a, ws=p["ws_step"])
+
+        p["feats"].copy_(sem_features)
+        p["x"].copy_(x_T)
+        if not self.use_cuda_graph:
+            run()
+        else:
+            if p["graph"] is None or p["epoch"] != dec.weights_epoch:
+                run()                                                 # warm-up: builds weight views / packed images
+                p["x"].copy_(x_T)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    run()
+                p["graph"], p["epoch"] = g, dec.weights_epoch
+                p["x"].copy_(x_T)
+            p["graph"].replay()
+        x = p["x"].clone()
+        if return_intermediates:
+            return x, [b.clone() for b in p["x0"]]
         return x
 
     def to(self, device) -> "DPMSolverPP":

@@ -59,6 +59,7 @@ extern "C" {
 #define EDTTS_STEP_EPS 0     /* write eps only           (decoder.py:109)          */
 #define EDTTS_STEP_DDIM 1    /* eps -> x_prev, x0        (schedule.py:179-202)     */
 #define EDTTS_STEP_DDPM 2    /* eps -> x_prev with noise (schedule.py:221-238)     */
+#define EDTTS_STEP_DPM 3     /* v / x0 -> x0 (clamped), x_prev: DPM-Solver++ (schedule.py:326-438, 479-481) */
 
 /* One DiffusionTransformerBlock (layers/transformer.py:71-160).  Names follow the
  * reference state-dict keys `layers.<i>.<...>`. */
@@ -174,7 +175,13 @@ typedef struct edtts_step_args {
   const float* noise;           /* [B,T,80] N(0,1) draws (DDPM)                          */
   float* eps_out;               /* [B,T,80] or NULL                                      */
   float* x_prev_out;            /* [B,T,80] or NULL                                      */
-  float* x0_out;                /* [B,T,80] or NULL (DDIM)                               */
+  float* x0_out;                /* [B,T,80] or NULL (DDIM, DPM)                          */
+  /* EDTTS_STEP_DPM (same meaning as the arguments of edtts_dpm_step) */
+  const float* dpm_coef;        /* [B][8] per-row coefficients                           */
+  const float* dpm_hist1;       /* [B,T,80] x0 history (order >= 2) or NULL              */
+  const float* dpm_hist2;       /* [B,T,80] x0 history (order 3) or NULL                 */
+  int32_t dpm_order;            /* 1, 2 or 3: the update rule used for this step         */
+  int32_t dpm_predict_x0;       /* 0: the decoder output is v; 1: it is x0               */
 } edtts_step_args;
 
 /* One decoder evaluation (decoder.py:96-109) with the update rule fused into the

@@ -189,3 +189,27 @@ def test_sample_larger_batch_vs_oracle(gpu):
     ref = O.dpm_sample(gpu["sd"], gpu["tab"], xT, feats, 4, 2)
     x = E.DPMSolverPP(gpu["sched"], order=2).sample(dec, xT.to(DEV), feats.to(DEV), num_steps=4)
     assert rel_l2(x, ref) <= 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_fused_graph_loop_equals_stepwise(gpu, precision, order):
+    """The fused route (update rule in the last decoder kernel, context hoisted, CUDA graph) gives the bits of the
+    step-by-step route (decoder -> eps in memory -> edtts_dpm_step), with and without graph replay."""
+    E, dec = gpu["E"], gpu["dec"]
+    dec.precision = precision
+    try:
+        feats = synth.synth_features(51, 3, 70, 128).to(DEV)
+        xT = synth.synth_noise(51, 3, 140).to(DEV)
+        solver = E.DPMSolverPP(gpu["sched"], order=order)
+        stepwise = lambda x, t, sem_features=None, step_idx=None: dec(x, t, sem_features=sem_features, step_idx=step_idx)
+        want, want_i = solver.sample(stepwise, xT, feats, num_steps=6, return_intermediates=True)
+        for graph in (False, True, True):                     # second graph call = replay of the cached plan
+            solver.use_cuda_graph = graph
+            got, got_i = solver.sample(dec, xT, feats, num_steps=6, return_intermediates=True)
+            assert torch.equal(got, want), (graph, order)
+            assert all(torch.equal(a, b) for a, b in zip(got_i, want_i))
+            assert torch.equal(solver.sample(dec, xT, feats, num_steps=6), want)
+    finally:
+        dec.precision = "fp32"
