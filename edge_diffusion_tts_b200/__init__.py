@@ -10,6 +10,7 @@ ABI of ``include/edtts.h``.  No CPU fallback, no Triton, no torch.compile.
 from .config import CFG, get_device, set_seed
 from .schedule import DiffusionSchedule, DPMSolverPP
 from .vq import VectorQuantizer
+from .fsq import FSQ
 from .decoder import EdgeDiffusionDecoder
 from .encoder import SemanticEncoder
 from .inference import EdgeInference
@@ -17,5 +18,5 @@ from .conv import DepthwiseSeparableConv
 from . import dist
 
 __version__ = "0.1.0"
-__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "EdgeDiffusionDecoder",
+__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "FSQ", "EdgeDiffusionDecoder",
            "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "dist"]

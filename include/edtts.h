@@ -220,6 +220,16 @@ int edtts_dpm_step(const float* x_t, const float* model_out, const float* hist1,
                    int32_t order_used, int32_t predict_x0, float* x_prev_out, float* x0_out, int32_t B, int64_t n,
                    void* stream);
 
+/* --- FSQ (models/fsq.py:18-132), the reference's alternative quantiser ------- */
+/* forward (fsq.py:84-108): z [rows, dim] -> z_q = tanh(z) + (quantise(tanh(z)) - tanh(z)) and the flat index per row
+ * (basis = cumprod([1] + levels[:-1]), first dimension fastest).  levels is a HOST array of dim (<= 8) ints.
+ * codes_only != 0: codes_to_indices (fsq.py:110-119) of already quantised codes; zq_out unused. */
+int edtts_fsq_forward(const float* z, const int32_t* levels_host, int32_t dim, int32_t codes_only, float* zq_out,
+                      int64_t* idx_out, int64_t rows, void* stream);
+/* indices_to_codes (fsq.py:121-132): last dimension fastest, as the reference decodes. */
+int edtts_fsq_decode(const int64_t* idx, const int32_t* levels_host, int32_t dim, float* codes_out, int64_t rows,
+                     void* stream);
+
 /* --- DepthwiseSeparableConv (layers/conv.py:10-64), operator level ---------- */
 /* x [B,C_in,T] -> y [B,C_out,T_out], T_out = (T + 2*(k/2) - k)/stride + 1:
  * depthwise k taps (no bias) -> pointwise 1x1 (+bias) -> GroupNorm(min(8,C_out)) -> GELU.

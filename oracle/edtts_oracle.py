@@ -463,5 +463,33 @@ def dpm_sample(sd: State, tab: State, x_T: Tensor, sem_features: Tensor, num_ste
     return x
 
 
+# ----------------------------------------------------------------------------
+# models/fsq.py:18-132  FSQ
+# ----------------------------------------------------------------------------
+def fsq_forward(levels, z: Tensor):
+    """FSQ.forward (fsq.py:84-108) -> (z_q, indices, z_scaled): z_scaled = (tanh(z) + 1) * half is returned so that tests
+    can exclude inputs that sit on a rounding boundary (tanh differs by ulps between CPU and CUDA)."""
+    lv = torch.tensor(levels, dtype=torch.int32)
+    basis = torch.cumprod(torch.tensor([1] + list(levels[:-1]), dtype=torch.int64), dim=0)
+    half = (lv.float() - 1) / 2
+    zb = torch.tanh(z)
+    zs = (zb + 1) * half
+    q = torch.minimum(torch.clamp(torch.round(zs), min=0), lv.float() - 1) / half - 1
+    z_q = zb + (q - zb)
+    idx = (((z_q + 1) * half).round().long() * basis).sum(dim=-1)
+    return z_q, idx, zs
+
+
+def fsq_indices_to_codes(levels, indices: Tensor) -> Tensor:
+    """FSQ.indices_to_codes (fsq.py:121-132): last dimension fastest (not the inverse of the forward basis)."""
+    lv = torch.tensor(levels, dtype=torch.int32)
+    codes = []
+    for i in range(len(levels) - 1, -1, -1):
+        codes.append(indices % lv[i])
+        indices = indices // lv[i]
+    codes = torch.stack(codes[::-1], dim=-1)
+    return codes.float() / ((lv.float() - 1) / 2) - 1
+
+
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

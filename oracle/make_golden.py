@@ -47,6 +47,19 @@ def make_dpm(ref, meta):
     torch.save(dict(meta=meta, seed=21, B=2, S=20, runs=runs, timesteps_full=ts), os.path.join(OUT, "dpm.pt"))
 
 
+def make_fsq(ref, meta):
+    """FSQ.forward / indices_to_codes of the reference (models/fsq.py) on seeded inputs."""
+    import importlib
+    F = importlib.import_module("edge_diffusion_tts.models.fsq")
+    cases = {}
+    for levels in ([8, 8, 8], [8, 6, 5, 5, 5], [5, 5]):
+        m = F.FSQ(levels)
+        z = torch.randn(3, 41, len(levels), generator=torch.Generator().manual_seed(17 + len(levels))) * 1.5
+        z_q, idx = m(z)
+        cases[tuple(levels)] = dict(z_q=z_q, idx=idx, codes=m.indices_to_codes(idx), seed=17 + len(levels))
+    torch.save(dict(meta=meta, cases=cases), os.path.join(OUT, "fsq.pt"))
+
+
 def main(only=None):
     torch.manual_seed(0)
     torch.set_num_threads(1)          # fixed summation order for the recorded outputs
@@ -57,6 +70,9 @@ def main(only=None):
     meta = dict(weights=synth.state_checksum(sd), torch=torch.__version__)
     if only == "dpm":                 # fixtures added later are generated alone; the older files stay byte-identical
         make_dpm(ref, meta)
+        return
+    if only == "fsq":
+        make_fsq(ref, meta)
         return
 
     # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
@@ -159,6 +175,7 @@ def main(only=None):
     torch.save(dict(meta=meta, seed=16, cases=conv), os.path.join(OUT, "dsconv.pt"))
 
     make_dpm(ref, meta)
+    make_fsq(ref, meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
