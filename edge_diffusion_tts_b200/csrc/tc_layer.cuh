@@ -23,15 +23,17 @@
 //                     phases warpgroup g owns heads g and g+2; in the row passes it handles columns
 //                     80g .. 80g+79 of every row.  Thread 0 also issues the GEMM-chain MMAs and
 //                     weight-chunk copies (they are strictly ordered with the row passes anyway).
-//   warp 8 / 10       TMA producer of warpgroup 0 / 1: K (3 stages) and V (2 stages) blocks of 64 keys
-//   warp 9 / 11       MMA issuer of warpgroup 0 / 1:  S = Q K^T into a double-buffered TMEM block,
-//                     O += P V accumulating in TMEM
+//   warp 8 / 10       TMA producer of warpgroup 0 / 1: K (4 stages) and V (2 stages) blocks of 64 keys
+//   warp 9 / 11       MMA issuer of warpgroup 0 / 1 (converged warp, elected lane):  S = Q K^T into a
+//                     double-buffered TMEM block, O += P V accumulating in TMEM
 // Attention is a single streaming pass per head in which no thread waits for a tensor-core round
-// trip: S blocks (64 keys) arrive in a double-buffered TMEM block, p = exp2(s*c - m) goes to shared
-// memory as bf16 (double buffered) and P V ACCUMULATES in TMEM.  m is a lazily updated running row
-// maximum: only when a block raises it by more than 2^8 does the warp rescale its O rows in TMEM
-// (tcgen05.ld / st) -- after the first block or two of a head that never happens -- so O is read
-// once per head and the result is exact (O and the row sum carry the same factor).
+// trip: S blocks (64 keys) arrive in a double-buffered TMEM block, p = exp2(s*c - m) is written back as
+// f16x2 over the first 32 columns of the SAME S block (tcgen05.st) and feeds O += P V as a tensor-memory
+// A operand, so P never touches shared memory.  m is a lazily updated running row maximum: only when a
+// block raises it by more than 2^6 does the warp rescale its O rows in TMEM (tcgen05.ld / st) -- after
+// the first block or two of a head that never happens -- so O is read once per head and the result is
+// exact (O and the row sum, delivered by the tensor core through V's constant-one column, carry the same
+// factor).
 // All hand-offs are mbarriers (full/free pairs per buffer); the only CTA-wide barriers are the
 // named barriers between GEMM-chain stages.  Weights are streamed from L2 in 160 x 160 bf16 chunks
 // (51,200 B, pre-packed UMMA operand images) through two slots, prefetched one GEMM ahead.
