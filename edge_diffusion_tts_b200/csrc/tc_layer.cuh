@@ -513,25 +513,11 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     const float bmax = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3)) * c;
 #endif
     if (lq == 0) LY_TR(wg, 10)
+    // The new running maximum is a per-thread decision, so the exponentials below start at once; whether the WARP has
+    // to rescale its O rows (tcgen05.ld / st are warp-collective) is voted on after the P store, off the critical chain.
     const bool grow = bmax > m_run + 6.0f;                // also true for the first finite block maximum
-    if (__any_sync(0xffffffffu, grow)) {
-      const float m_upd = grow ? bmax : m_run;
-      if (i > 0) {                                        // rescale this warp's O rows (and the row sum in column 40):
-        const float f = (m_upd == m_run) ? 1.0f : ex2_approx(m_run - m_upd);     // m_run = -inf -> 0
-        mbar_wait(wb + WB_PV + (pbuf ^ 1), ((cp - 1) >> 1) & 1);                 // P V (i-1) must have retired
-        tc_fence_after();
-#pragma unroll
-        for (int q = 0; q < 3; ++q) {
-          float ob[16];
-          tmem_ld16(tO + 16 * q, ob);
-#pragma unroll
-          for (int d = 0; d < 16; ++d) ob[d] *= f;
-          tmem_st16(tO + 16 * q, ob);
-        }
-        tmem_st_wait();
-      }
-      m_run = m_upd;
-    }
+    const float m_old = m_run;
+    m_run = grow ? bmax : m_run;
     const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
     if (lq == 0) LY_TR(wg, 11)
     LY_FC(2)
@@ -572,6 +558,19 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
 #endif
     LY_FC(3)
     if (lq == 0) LY_TR(wg, 4)
+    if (__any_sync(0xffffffffu, grow) && i > 0) {         // rescale this warp's O rows (and the row sum in column 40)
+      const float f = (m_run == m_old) ? 1.0f : ex2_approx(m_old - m_run);       // m_old = -inf -> 0
+      mbar_wait(wb + WB_PV + (pbuf ^ 1), ((cp - 1) >> 1) & 1);                   // P V (i-1) must have retired
+      tc_fence_after();
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        float ob[16];
+        tmem_ld16(tO + 16 * q, ob);
+#pragma unroll
+        for (int d = 0; d < 16; ++d) ob[d] *= f;
+        tmem_st16(tO + 16 * q, ob);
+      }
+    }
     tmem_st_wait();
     tc_fence_before();
     if (lq == 0) LY_TR(wg, 5)
