@@ -446,6 +446,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
   const float c = a.scale_log2e;
 
   float m_run = -INFINITY;                                // running row maximum in exp2 units (s * c), lazily updated
+  const int row0u = __shfl_sync(0xffffffffu, lq, 0) * 32; // first row of the warp, provably warp-uniform
 
   // one block of 64 keys
   auto step = [&](uint32_t (&cur)[64], int i) {
@@ -471,6 +472,14 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       lo = 0;
       hi = min(LY_KB, a.S - i * LY_KB) - 1;
     }
+    int lo_a = 0, lo_b = 0, hi_a = 0, hi_b = 0;           // the same bounds for the warp's first (a) and last (b) row
+    if (WINDOW) {
+      const int off0 = LY_KB * (pl.kb0 + i);
+      lo_a = max(max(row0u, WIN - tl.t0) - off0, 0);
+      lo_b = max(max(row0u + 31, WIN - tl.t0) - off0, 0);
+      hi_a = min(min(row0u + 2 * WIN, a.T - 1 - tl.t0 + WIN) - off0, LY_KB - 1);
+      hi_b = min(min(row0u + 31 + 2 * WIN, a.T - 1 - tl.t0 + WIN) - off0, LY_KB - 1);
+    }
     const bool any = hi >= lo;
     if (!any) lo = hi = LY_KB;                            // empty: no column index below 64 passes the unsigned range test
     const int base = -lo;
@@ -480,8 +489,10 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       if (WINDOW) {
-        need[ch] = ch < nch && __any_sync(0xffffffffu, any && lo <= ch * 32 + 31 && hi >= ch * 32);   // warp-uniform
-        full[ch] = __all_sync(0xffffffffu, lo <= ch * 32 && hi >= ch * 32 + 31);
+        // warp-uniform without votes: lo and hi are non-decreasing in the row, so the warp's first / last row bound them.
+        // need may be true for a chunk no single row touches (then every p is masked to 0); full is exact.
+        need[ch] = ch < nch && lo_a <= ch * 32 + 31 && hi_b >= ch * 32 && hi_b >= lo_a;
+        full[ch] = lo_b <= ch * 32 && hi_a >= ch * 32 + 31;
       } else {                                            // context keys: the same range for every row, no votes needed
         need[ch] = ch < nch;
         full[ch] = hi >= ch * 32 + 31;
