@@ -381,6 +381,16 @@ __device__ __forceinline__ uint32_t ly_pack_f16x2(float lo, float hi) {
   const __half2 h = __floats2half2_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
+// (x0, x1) = (s0, s1) * c - m in ONE instruction: packed fp32 FMA (fma.rn.f32x2, sm_100)
+__device__ __forceinline__ void ly_scale2(uint32_t s0, uint32_t s1, float c, float m, float& x0, float& x1) {
+  uint64_t sp, cp2, mp, d;
+  const float nm = -m;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(sp) : "r"(s0), "r"(s1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cp2) : "f"(c));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(mp) : "f"(nm));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(sp), "l"(cp2), "l"(mp));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+}
 // TMEM -> registers, 64 columns, NOT waited for
 __device__ __forceinline__ void ly_s_issue(uint32_t taddr, uint32_t (&r)[64]) {
 #pragma unroll
@@ -548,8 +558,8 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       } else if (full[ch]) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
-          const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
+          float x0, x1;
+          ly_scale2(cur[32 * ch + 2 * j], cur[32 * ch + 2 * j + 1], c, m_use, x0, x1);
           if (LY_POLY_EVERY > 0 && j % (LY_POLY_EVERY > 0 ? LY_POLY_EVERY : 1) == 0) pk[j] = ly_pack_f16x2(ly_exp2_poly(x0), ly_exp2_poly(x1));
           else pk[j] = ly_exp2_f16x2(x0, x1);
         }
