@@ -366,7 +366,7 @@ __device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
 // the f16 rounding of P), 2^n by adding n to the exponent field.  MUFU.EX2 issues once per 8 cycles per sub-partition
 // (tools/ubench/expord.cu), so moving every LY_POLY_EVERY-th pair of scores here shortens the MUFU-bound pass.
 #ifndef LY_POLY_EVERY
-#define LY_POLY_EVERY 4
+#define LY_POLY_EVERY 0
 #endif
 __device__ __forceinline__ float ly_exp2_poly(float x) {
   x = fmaxf(x, -30.0f);                                   // 2^-30 is far below the smallest f16: no exponent underflow
@@ -390,6 +390,44 @@ __device__ __forceinline__ void ly_scale2(uint32_t s0, uint32_t s1, float c, flo
   asm("mov.b64 %0, {%1, %1};" : "=l"(mp) : "f"(nm));
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(sp), "l"(cp2), "l"(mp));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(d));
+}
+// ---- packed fp32 pairs (sm_100: add / mul / fma .f32x2 issue once for two values) -------------------------------------
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// 2^x for a pair on the FMA / ALU pipes (no MUFU), see ly_exp2_poly: 2 FMNMX + 3 packed adds + 3 packed FMAs + 2 exponent
+// inserts for two results (11 issue slots with the pack, against 16 MUFU cycles for the same two on the MUFU pipe)
+__device__ __forceinline__ uint32_t ly_exp2_poly2_f16x2(float x0, float x1) {
+  const uint64_t x = f2_pack(fmaxf(x0, -30.0f), fmaxf(x1, -30.0f));
+  const uint64_t magic = f2_pack(12582912.0f, 12582912.0f), nmagic = f2_pack(-12582912.0f, -12582912.0f);
+  const uint64_t t = f2_add(x, magic);                    // low mantissa bits of t: round(x)
+  const uint64_t tn = f2_add(t, nmagic);                  // round(x) as a float
+  float tn0, tn1;
+  f2_unpack(tn, tn0, tn1);
+  const uint64_t r = f2_add(x, f2_pack(-tn0, -tn1));      // x - round(x) in [-0.5, 0.5]
+  uint64_t p = f2_fma(f2_pack(0.05517164245247841f, 0.05517164245247841f), r, f2_pack(0.2426111251115799f, 0.2426111251115799f));
+  p = f2_fma(p, r, f2_pack(0.6932609677314758f, 0.6932609677314758f));
+  p = f2_fma(p, r, f2_pack(0.9999280571937561f, 0.9999280571937561f));
+  float p0, p1, t0, t1;
+  f2_unpack(p, p0, p1);
+  f2_unpack(t, t0, t1);
+  const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+  const __half2 h = __floats2half2_rn(e0, e1);
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 // TMEM -> registers, 64 columns, NOT waited for
 __device__ __forceinline__ void ly_s_issue(uint32_t taddr, uint32_t (&r)[64]) {
@@ -560,14 +598,14 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
         for (int j = 0; j < 16; ++j) {
           float x0, x1;
           ly_scale2(cur[32 * ch + 2 * j], cur[32 * ch + 2 * j + 1], c, m_use, x0, x1);
-          if (LY_POLY_EVERY > 0 && j % (LY_POLY_EVERY > 0 ? LY_POLY_EVERY : 1) == 0) pk[j] = ly_pack_f16x2(ly_exp2_poly(x0), ly_exp2_poly(x1));
+          if (LY_POLY_EVERY > 0 && j % (LY_POLY_EVERY > 0 ? LY_POLY_EVERY : 1) == 0) pk[j] = ly_exp2_poly2_f16x2(x0, x1);
           else pk[j] = ly_exp2_f16x2(x0, x1);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float x0 = fmaf(__uint_as_float(cur[32 * ch + 2 * j]), c, -m_use);
-          const float x1 = fmaf(__uint_as_float(cur[32 * ch + 2 * j + 1]), c, -m_use);
+          float x0, x1;
+          ly_scale2(cur[32 * ch + 2 * j], cur[32 * ch + 2 * j + 1], c, m_use, x0, x1);
           pk[j] = ly_exp2_f16x2((unsigned)(base + 32 * ch + 2 * j) <= span ? x0 : -INFINITY,
                                 (unsigned)(base + 32 * ch + 2 * j + 1) <= span ? x1 : -INFINITY);
         }
