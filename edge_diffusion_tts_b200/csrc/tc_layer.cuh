@@ -408,6 +408,34 @@ __device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// row-pass arithmetic on PAIRS of columns (one issue slot for two values)
+__device__ __forceinline__ void f2_add_to(float* v, const float* b) {           // v[0..1] += b[0..1]
+  f2_unpack(f2_add(f2_pack(v[0], v[1]), f2_pack(b[0], b[1])), v[0], v[1]);
+}
+__device__ __forceinline__ uint64_t f2_sq_acc(const float* v, uint64_t acc) {    // acc += v * v (two partial sums)
+  const uint64_t p = f2_pack(v[0], v[1]);
+  return f2_fma(p, p, acc);
+}
+__device__ __forceinline__ float f2_hsum(uint64_t acc) {
+  float a, b;
+  f2_unpack(acc, a, b);
+  return a + b;
+}
+// (x + bx) * silu(g + bg) for two columns: 5 packed operations + 2 tanh instead of 12 scalar ones
+__device__ __forceinline__ void swiglu2(float* x, const float* g, const float* bx, const float* bg) {
+  const uint64_t xb = f2_add(f2_pack(x[0], x[1]), f2_pack(bx[0], bx[1]));
+  const uint64_t hg = f2_mul(f2_add(f2_pack(g[0], g[1]), f2_pack(bg[0], bg[1])), f2_pack(0.5f, 0.5f));
+  float h0, h1, t0, t1;
+  f2_unpack(hg, h0, h1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(h0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(h1));
+  f2_unpack(f2_mul(xb, f2_fma(hg, f2_pack(t0, t1), hg)), x[0], x[1]);             // silu(g) = hg * tanh(hg) + hg
+}
 // 2^x for a pair on the FMA / ALU pipes (no MUFU), see ly_exp2_poly: 2 FMNMX + 3 packed adds + 3 packed FMAs + 2 exponent
 // inserts for two results (11 issue slots with the pack, against 16 MUFU cycles for the same two on the MUFU pipe)
 __device__ __forceinline__ uint32_t ly_exp2_poly2_f16x2(float x0, float x1) {
@@ -913,17 +941,18 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     // ---- n2 = RMSNorm(h + b_proj) * w2 -> sA ; h + b_proj back to TMEM ---------------------------------------------
     {
       float v[80];
-      float ss = 0.f;
+      uint64_t ss2 = 0;
       tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          v[16 * i + j] += sC[LC_PROJ_B + cb + 16 * i + j];
-          ss = fmaf(v[16 * i + j], v[16 * i + j], ss);
+        for (int j = 0; j < 16; j += 2) {
+          f2_add_to(v + 16 * i + j, sC + LC_PROJ_B + cb + 16 * i + j);
+          ss2 = f2_sq_acc(v + 16 * i + j, ss2);
         }
         tmem_st16(trow + TM_H + cb + 16 * i, v + 16 * i);
       }
+      const float ss = f2_hsum(ss2);
       sRed[wg * 128 + row] = ss;
       tmem_st_wait();
       csync();
@@ -932,7 +961,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       for (int g = 0; g < 10; ++g) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = v[8 * g + j] * rstd * sC[LC_N2W + cb + 8 * g + j];
+        for (int j = 0; j < 8; j += 2)
+          f2_unpack(f2_mul(f2_mul(f2_pack(v[8 * g + j], v[8 * g + j + 1]), f2_pack(rstd, rstd)),
+                           f2_pack(sC[LC_N2W + cb + 8 * g + j], sC[LC_N2W + cb + 8 * g + j + 1])), o[j], o[j + 1]);
         *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
       }
     }
@@ -996,19 +1027,21 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     // ---- n3 = AdaRMSNorm(h) -> sA --------------------------------------------------------------------------------------
     {
       float v[80];
-      float ss = 0.f;
+      uint64_t ss2 = 0;
       tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
-      for (int j = 0; j < 80; ++j) ss = fmaf(v[j], v[j], ss);
-      sRed[wg * 128 + row] = ss;
+      for (int j = 0; j < 80; j += 2) ss2 = f2_sq_acc(v + j, ss2);
+      sRed[wg * 128 + row] = f2_hsum(ss2);
       csync();
       const float rstd = rsqrtf((sRed[row] + sRed[128 + row]) * (1.0f / H) + 1e-6f);
 #pragma unroll
       for (int g = 0; g < 10; ++g) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = fmaf(v[8 * g + j] * rstd, sC[LS_G3 + cb + 8 * g + j], sC[LS_SH3 + cb + 8 * g + j]);
+        for (int j = 0; j < 8; j += 2)
+          f2_unpack(f2_fma(f2_mul(f2_pack(v[8 * g + j], v[8 * g + j + 1]), f2_pack(rstd, rstd)),
+                           f2_pack(sC[LS_G3 + cb + 8 * g + j], sC[LS_G3 + cb + 8 * g + j + 1]),
+                           f2_pack(sC[LS_SH3 + cb + 8 * g + j], sC[LS_SH3 + cb + 8 * g + j + 1])), o[j], o[j + 1]);
         *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
       }
     }
@@ -1056,7 +1089,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         float x[16], g[16];
         tmem_ld16x2(trow + TM_G + cb + 16 * i, x, trow + TM_G + 160 + cb + 16 * i, g);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) x[j] = (x[j] + bx[16 * i + j]) * fast_silu(g[j] + bg[16 * i + j]);
+        for (int j = 0; j < 16; j += 2) swiglu2(x + j, g + j, bx + 16 * i + j, bg + 16 * i + j);
         *reinterpret_cast<uint4*>(dst + (cb / 8 + 2 * i) * LY_SLAB + row * 16) = pack_bf16x8(x);
         *reinterpret_cast<uint4*>(dst + (cb / 8 + 2 * i + 1) * LY_SLAB + row * 16) = pack_bf16x8(x + 8);
       }
@@ -1096,13 +1129,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       float s1 = 0.f;
       tmem_ld80(trow + TM_H + cb, v);
 #pragma unroll
-      for (int j = 0; j < 80; ++j) v[j] += sC[LS_TB + cb + j];
+      for (int j = 0; j < 80; j += 2) f2_add_to(v + j, sC + LS_TB + cb + j);
       if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
         const float4* pp = reinterpret_cast<const float4*>(a.pe + (int64_t)(tl.t0 + row) * H + cb);
 #pragma unroll
         for (int q = 0; q < 20; ++q) {
           const float4 pv = pp[q];
-          v[4 * q] += pv.x; v[4 * q + 1] += pv.y; v[4 * q + 2] += pv.z; v[4 * q + 3] += pv.w;
+          f2_add_to(v + 4 * q, &pv.x);
+          f2_add_to(v + 4 * q + 2, &pv.z);
         }
       }
       if (a.tail != LT_FINAL && row < tl.nq) {
@@ -1113,8 +1147,15 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       }
       if (a.tail != LT_NONE) {
         // next norm: AdaRMSNorm (LT_QKV) or LayerNorm (LT_FINAL, exact two-step variance) -> bf16 A operand
+        if (a.tail == LT_FINAL) {
 #pragma unroll
-        for (int j = 0; j < 80; ++j) s1 += (a.tail == LT_FINAL) ? v[j] : v[j] * v[j];
+          for (int j = 0; j < 80; ++j) s1 += v[j];
+        } else {
+          uint64_t ss2 = 0;
+#pragma unroll
+          for (int j = 0; j < 80; j += 2) ss2 = f2_sq_acc(v + j, ss2);
+          s1 = f2_hsum(ss2);
+        }
         sRed[wg * 128 + row] = s1;
         csync();
         const float tot = sRed[row] + sRed[128 + row];
@@ -1134,8 +1175,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         for (int g = 0; g < 10; ++g) {
           float o[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            o[j] = fmaf((v[8 * g + j] - mean) * rstd, sC[LS_TG + cb + 8 * g + j], sC[LS_TS + cb + 8 * g + j]);
+          for (int j = 0; j < 8; j += 2)
+            f2_unpack(f2_fma(f2_mul(f2_add(f2_pack(v[8 * g + j], v[8 * g + j + 1]), f2_pack(-mean, -mean)), f2_pack(rstd, rstd)),
+                             f2_pack(sC[LS_TG + cb + 8 * g + j], sC[LS_TG + cb + 8 * g + j + 1]),
+                             f2_pack(sC[LS_TS + cb + 8 * g + j], sC[LS_TS + cb + 8 * g + j + 1])), o[j], o[j + 1]);
           *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
         }
         fence_proxy_async();
