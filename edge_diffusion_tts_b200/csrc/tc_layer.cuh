@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   // =========================== compute warpgroups ===========================================================
   asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
   const int wg = warp >> 2, lq = warp & 3, row = lq * 32 + lane;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);   // the warp index, provably warp-uniform
   const int cb = 80 * wg;                                 // this thread's column half in the row passes
   uint64_t* wb = bars + LB_WG0 + wg * WB_COUNT;
   const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
@@ -889,10 +890,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       LY_PHASE(0)
     } else {
     // ---- tile prologue: Q -> sA, h -> TMEM ---------------------------------------------------------------------------
-    if (tid == 0) {
-      mbar_expect_tx(bar_q, 20 * tl.nq * 16);
-#pragma unroll 1
-      for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * a.R + tl.row0) * 8, tl.nq * 16, bar_q);
+    if (lq == 0) LY_TR(wg, 40)
+    if (warp_u == 1) {                                    // converged warp + elected lane: uniform-register addressing
+      if (elect_one()) {
+        mbar_expect_tx(bar_q, 20 * tl.nq * 16);
+#pragma unroll
+        for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * a.R + tl.row0) * 8, tl.nq * 16, bar_q);
+      }
+      __syncwarp();
     }
     {
       const float* src = a.hc + ((int64_t)(cb / 4) * a.R + tl.row0 + row) * 4;
@@ -909,14 +914,19 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         }
         tmem_st16(trow + TM_H + cb + 16 * i, v);
       }
+      if (lq == 0) LY_TR(wg, 41)
       tmem_st_wait();
     }
+    if (lq == 0) LY_TR(wg, 42)
     ly_init_pads(smem, tid);
     fence_proxy_async();
+    if (lq == 0) LY_TR(wg, 43)
     mbar_wait(bar_q, ph_q);
     ph_q ^= 1;
     tc_fence_before();
+    if (lq == 0) LY_TR(wg, 44)
     csync();
+    if (lq == 0) LY_TR(wg, 45)
     if (tid == 0) mbar_arrive(bar_attgo);                 // Q in place, attention TMEM columns and P buffers free
     LY_PHASE(0)
 
@@ -1124,10 +1134,12 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         load_w(a.w_out, LY_WCHUNK / 2, sW1, bar_w1);
       }
     }
+    if (lq == 0) LY_TR(wg, 50)
     {
       float v[80];
       float s1 = 0.f;
       tmem_ld80(trow + TM_H + cb, v);
+      if (lq == 0) LY_TR(wg, 51)
 #pragma unroll
       for (int j = 0; j < 80; j += 2) f2_add_to(v + j, sC + LS_TB + cb + j);
       if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
@@ -1139,12 +1151,15 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           f2_add_to(v + 4 * q + 2, &pv.z);
         }
       }
+      // h -> HBM: 20 x 16 bytes per thread (the LSU queue makes this ~3 k cycles per tile; interleaving the stores with the
+      // normalisation below was measured slower)
       if (a.tail != LT_FINAL && row < tl.nq) {
 #pragma unroll
         for (int q = 0; q < 20; ++q)
           *reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + q) * a.R + tl.row0 + row) * 4) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
+      if (lq == 0) LY_TR(wg, 52)
       if (a.tail != LT_NONE) {
         // next norm: AdaRMSNorm (LT_QKV) or LayerNorm (LT_FINAL, exact two-step variance) -> bf16 A operand
         if (a.tail == LT_FINAL) {
@@ -1157,7 +1172,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           s1 = f2_hsum(ss2);
         }
         sRed[wg * 128 + row] = s1;
+        if (lq == 0) LY_TR(wg, 53)
         csync();
+        if (lq == 0) LY_TR(wg, 54)
         const float tot = sRed[row] + sRed[128 + row];
         float mean = 0.f, rstd;
         if (a.tail == LT_FINAL) {
@@ -1181,11 +1198,14 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
                              f2_pack(sC[LS_TS + cb + 8 * g + j], sC[LS_TS + cb + 8 * g + j + 1])), o[j], o[j + 1]);
           *reinterpret_cast<uint4*>(sA + (cb / 8 + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
         }
+        if (lq == 0) LY_TR(wg, 55)
         fence_proxy_async();
       }
     }
     tc_fence_before();
+    if (lq == 0) LY_TR(wg, 56)
     csync();
+    if (lq == 0) LY_TR(wg, 57)
     LY_PHASE(8)
 
     if (a.tail == LT_QKV) {
