@@ -904,7 +904,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       float4 x[20];
 #pragma unroll
       for (int q = 0; q < 20; ++q)
-        x[q] = row < tl.nq ? *reinterpret_cast<const float4*>(src + (int64_t)q * a.R * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[q] = row < tl.nq ? __ldcs(reinterpret_cast<const float4*>(src + (int64_t)q * a.R * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         float v[16];
@@ -1156,8 +1156,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       if (a.tail != LT_FINAL && row < tl.nq) {
 #pragma unroll
         for (int q = 0; q < 20; ++q)
-          *reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + q) * a.R + tl.row0 + row) * 4) =
-              make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          __stcs(reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + q) * a.R + tl.row0 + row) * 4),
+                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));    // streaming: read next by another SM's launch
       }
       if (lq == 0) LY_TR(wg, 52)
       if (a.tail != LT_NONE) {
