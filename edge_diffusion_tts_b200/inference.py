@@ -61,8 +61,8 @@ class EdgeInference:
         B, T, _ = p.x.shape
         dec.prepare_context(p.sem_idx, None, T, out=p.kv, ws=p.ws_ctx)
         n = len(p.t)
-        for i in range(n):
-            dec.prepare_cond(p.t[i], p.step_idx[i], T, S, out=p.mods[i])
+        # conditioning of ALL steps in one launch (rows are independent: [n * B] timesteps -> [n * B, 8, 320])
+        dec.prepare_cond(p.t_all, p.step_all, T, S, out=p.mod_all)
         for i in range(n):
             a = _lib.StepArgs()
             a.mode = _lib.STEP_DDIM
@@ -93,7 +93,10 @@ class EdgeInference:
             p.t.append(torch.full((B,), t, dtype=torch.int64, device=device))
             p.t_prev.append(torch.full((B,), tp, dtype=torch.int64, device=device))
             p.step_idx.append(torch.full((B,), i, dtype=torch.int64, device=device))
-            p.mods.append(torch.empty(B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device))
+        p.t_all = torch.cat(p.t)
+        p.step_all = torch.cat(p.step_idx)
+        p.mod_all = torch.empty(num_steps * B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
+        p.mods = [p.mod_all[i * B:(i + 1) * B] for i in range(num_steps)]
         self._plans[key] = p
         return p
 

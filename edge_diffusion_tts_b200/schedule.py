@@ -272,7 +272,8 @@ class DPMSolverPP:
             p["x0"] = [torch.empty_like(p["x"]) for _ in range(n if return_intermediates else min(n, 3))]
             cfg = dec.cfg
             p["kv"] = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, dtype=torch.float32, device=dev)
-            p["mods"] = [torch.empty(B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=dev) for _ in range(n)]
+            p["mod_all"] = torch.empty(n * B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=dev)
+            p["mods"] = [p["mod_all"][i * B:(i + 1) * B] for i in range(n)]
             nb_ctx, nb_step = dec.workspace_bytes(B, T, S)
             p["ws_ctx"] = torch.empty(max(nb_ctx, 256), dtype=torch.uint8, device=dev)
             p["ws_step"] = torch.empty(max(nb_step, 256), dtype=torch.uint8, device=dev)
@@ -288,12 +289,12 @@ class DPMSolverPP:
                 p["used"].append(used)
                 t_hist = (t_hist + [tp])[-2:]
                 n_hist = min(n_hist + 1, 2)
+            p["t_all"], p["si_all"] = torch.cat(p["t"]), torch.cat(p["si"])
             plans[key] = p
 
         def run():
             dec.prepare_context(None, p["feats"], T, out=p["kv"], ws=p["ws_ctx"])
-            for i in range(n):
-                dec.prepare_cond(p["t"][i], p["si"][i], T, S, out=p["mods"][i])
+            dec.prepare_cond(p["t_all"], p["si_all"], T, S, out=p["mod_all"])   # all steps in one launch
             nb = len(p["x0"])
             for i in range(n):
                 a = _lib.StepArgs()
