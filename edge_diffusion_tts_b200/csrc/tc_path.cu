@@ -115,7 +115,14 @@ static int launch_tc_gemm_t(const TcGemmArgs& g, int ny, cudaStream_t st) {
   const int smem = L::total(g.amode, g.epi);
   EDTTS_REQUIRE(smem <= 232448, EDTTS_ENOTSUP, "tc_gemm<%d,%d>: %d B of shared memory", K, N_CTA, smem);
   const int64_t ntiles = (g.R + TILE_M - 1) / TILE_M;
-  int64_t nx = 148 / ny;                       // persistent: one CTA per SM
+  // persistent CTAs: as many per SM as shared memory and tensor memory allow (the small context projections are latency-
+  // bound per tile; two or three resident CTAs overlap one tile's load / prologue with another's MMA / epilogue)
+  int per_sm = 232448 / (smem + 1024);
+  const int tmem_fit = 512 / (int)L::TMEM_COLS;
+  if (per_sm > tmem_fit) per_sm = tmem_fit;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 3) per_sm = 3;
+  int64_t nx = (int64_t)148 * per_sm / ny;
   if (nx > ntiles) nx = ntiles;
   if (nx < 1) nx = 1;
   LaunchScope ls(KC_TC_GEMM, st);
@@ -337,12 +344,16 @@ int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw,
   EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "context_prepare(bf16): weights.packed_bf16 is null");
   const PackedOff po = packed_offsets();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
+  // the context rows once as a bf16 chunk-major operand image (read by the four down projections through the TMA engine,
+  // no fp32 staging / conversion prologue per layer); it lives in the third region of the context workspace
+  __nv_bfloat16* ctx_chunk = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(craw) + align_up(rows * RANK * 4, 256));
+  if (int rc0 = pack_activation(ctx, H, ctx_chunk, rows, H, 1 << 30, st)) return rc0;
   for (int l = 0; l < NL; ++l) {
     const LayerOff& lo = po.layer[l];
     int rc;
     {  // c = kv_down_proj(ctx)   (mla.py:146)
       TcGemmArgs g;
-      g.amode = A_F32; g.A_f32 = ctx; g.R = rows; g.T = (int)rows; g.W_img = reinterpret_cast<const __nv_bfloat16*>(pk + lo.kv_down);
+      g.amode = A_CHUNK; g.A_chunk = ctx_chunk; g.R = rows; g.T = (int)rows; g.W_img = reinterpret_cast<const __nv_bfloat16*>(pk + lo.kv_down);
       g.epi = TE_F32; g.out_f32 = craw; g.ldo = RANK;
       if ((rc = launch_tc_gemm(g, H, RANK, 1, st))) return rc;
     }
