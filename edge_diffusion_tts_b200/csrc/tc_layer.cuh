@@ -609,11 +609,6 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
     if (lq == 0) LY_TR(wg, 11)
     LY_FC(2)
     // ---- p -> P (f16x2 per 32-bit column, tensor memory): the A operand of P V, no shared-memory round trip ----
-#ifdef LY_PINGPONG
-    // The two warps of a sub-partition (same lane quarter, warpgroups 0 / 1) take turns on the MUFU-bound section: while
-    // one exponentiates, the other runs its barrier / TMEM-load / maximum work.  Token barrier 4 + 2 lq + wg.
-    named_bar_sync(4 + 2 * lq + wg, 64);
-#endif
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       if (ch >= nch) continue;
@@ -640,9 +635,6 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
       }
       tmem_st16u(tP + 16 * ch, pk);
     }
-#ifdef LY_PINGPONG
-    named_bar_arrive(4 + 2 * lq + (wg ^ 1), 64);          // pass the token to the partner warp
-#endif
     LY_FC(3)
     if (lq == 0) LY_TR(wg, 4)
     if (__any_sync(0xffffffffu, grow) && i > 0) {         // rescale this warp's O rows (and the row sum in column 40)
@@ -821,9 +813,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     }
   };
 
-#ifdef LY_PINGPONG
-  if (wg == 1) named_bar_arrive(4 + 2 * lq, 64);          // the token starts with warpgroup 0
-#endif
   long long pc[PROF ? 16 : 1] = {0}, fcw[PROF ? 8 : 1] = {0}, fcx[PROF ? 8 : 1] = {0};
   long long pc_last = PROF ? clock64() : 0;
 #define LY_PHASE(i)                                   \
