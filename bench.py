@@ -160,9 +160,13 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     import torch.distributed as dist
+    stdout_fd = None
     if world > 1:
-        # NCCL writes its version banner / debug log to stdout by default: keep stdout to the ONE JSON line of the contract
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # NCCL prints its version banner (and, with NCCL_DEBUG, its log) on file descriptor 1 when the communicator is
+        # created: point fd 1 at stderr until the ONE JSON line of the contract is printed
+        sys.stdout.flush()
+        stdout_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     import __graft_entry__ as ge
@@ -350,6 +354,10 @@ def main():
                          f"{N_STEPS} steps, {n} repetitions ({ms_cpu:.0f} ms each), torch {torch.__version__}",
                "host_cpus": os.cpu_count()}
 
+    if stdout_fd is not None:
+        sys.stdout.flush()
+        os.dup2(stdout_fd, 1)
+        os.close(stdout_fd)
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
