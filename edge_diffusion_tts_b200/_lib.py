@@ -73,6 +73,8 @@ SIGNATURES = {
     "edtts_ddim_step": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_float, _p, _p, _i32, _i64, _p]),
     "edtts_ddpm_step": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i32, _i64, _p]),
     "edtts_dpm_step": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i32, _i64, _p]),
+    "edtts_vddim_step": (C.c_int, [_p, _p, _p, C.c_float, _p, _p, _p, _i32, _i64, _p]),
+    "edtts_inpaint_inject": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _i32, _p]),
     "edtts_fsq_forward": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i64, _p]),
     "edtts_fsq_decode": (C.c_int, [_p, _p, _i32, _p, _i64, _p]),
     "edtts_dsconv_forward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

@@ -105,6 +105,33 @@ __global__ void __launch_bounds__(256) dpm_kernel(const float* __restrict__ x, c
   }
 }
 
+// v-prediction DDIM step with optional classifier-free guidance (inference_pipeline.py:176-192), torch operation order
+__global__ void __launch_bounds__(256) vddim_kernel(const float* __restrict__ x, const float* __restrict__ vc,
+                                                    const float* __restrict__ vu, float s, const float* __restrict__ coef,
+                                                    float* __restrict__ xn, float* __restrict__ x0_out, int64_t total, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float* c = coef + (i / n) * 4;
+    const float xv = x[i];
+    float v = vc[i];
+    if (vu) v = __fadd_rn(vu[i], __fmul_rn(s, __fsub_rn(v, vu[i])));
+    float x0 = __fsub_rn(__fmul_rn(c[0], xv), __fmul_rn(c[1], v));
+    x0 = fminf(fmaxf(x0, -3.0f), 3.0f);
+    const float eps = __fadd_rn(__fmul_rn(c[1], xv), __fmul_rn(c[0], v));
+    if (x0_out) x0_out[i] = x0;
+    xn[i] = __fadd_rn(__fmul_rn(c[2], x0), __fmul_rn(c[3], eps));
+  }
+}
+// x[b, :L, :] = sa known + sb noise
+__global__ void __launch_bounds__(256) inpaint_inject_kernel(float* __restrict__ x, const float* __restrict__ known,
+                                                             const float* __restrict__ noise, const float* __restrict__ coef,
+                                                             int64_t total, int64_t per_b, int64_t x_per_b) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / per_b, r = i % per_b;
+    const float* c = coef + b * 4;
+    x[b * x_per_b + r] = __fadd_rn(__fmul_rn(c[0], known[i]), __fmul_rn(c[1], noise[i]));
+  }
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned stream_grid(int64_t work_items) {
   const int64_t blocks = (work_items + 255) / 256;
@@ -172,4 +199,25 @@ extern "C" int edtts_dpm_step(const float* x_t, const float* model_out, const fl
     dpm_kernel<1><<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, model_out, hist1, hist2, coef, order_used,
                                                                      predict_x0, x_prev_out, x0_out, total, n);
   return check_launch("dpm_step");
+}
+
+extern "C" int edtts_vddim_step(const float* x_t, const float* v_cond, const float* v_uncond, float cfg_scale,
+                                const float* coef, float* x_next_out, float* x0_out, int32_t B, int64_t n, void* stream) {
+  EDTTS_REQUIRE(x_t && v_cond && coef && x_next_out && B > 0 && n > 0, EDTTS_EINVAL, "vddim_step: null argument");
+  const int64_t total = (int64_t)B * n;
+  LaunchScope ls(KC_SCHEDULE, as_stream(stream));
+  vddim_kernel<<<stream_grid(total), 256, 0, as_stream(stream)>>>(x_t, v_cond, v_uncond, cfg_scale, coef, x_next_out, x0_out,
+                                                                  total, n);
+  return check_launch("vddim_step");
+}
+
+extern "C" int edtts_inpaint_inject(float* x, const float* known, const float* noise, const float* coef, int32_t B, int32_t T,
+                                    int32_t L, int32_t D, void* stream) {
+  EDTTS_REQUIRE(x && known && noise && coef && B > 0 && T > 0 && D > 0 && L >= 0 && L <= T, EDTTS_EINVAL,
+                "inpaint_inject: B=%d T=%d L=%d D=%d", B, T, L, D);
+  if (L == 0) return EDTTS_OK;
+  const int64_t per_b = (int64_t)L * D, total = per_b * B;
+  LaunchScope ls(KC_SCHEDULE, as_stream(stream));
+  inpaint_inject_kernel<<<stream_grid(total), 256, 0, as_stream(stream)>>>(x, known, noise, coef, total, per_b, (int64_t)T * D);
+  return check_launch("inpaint_inject");
 }

@@ -145,6 +145,83 @@ class EdgeInference:
         _, sem_idx, _, _, _ = self.encoder(wav)
         return self.generate_mel(sem_idx, num_steps)
 
+    # ------------------------------------------------------------------ long-form pipeline: in-painting refine
+    @torch.no_grad()
+    def inpaint_refine(self, x_coarse: torch.Tensor, sem_features: torch.Tensor, known_mel: Optional[torch.Tensor] = None,
+                       overlap_len: int = 0, strength: float = 0.2, steps: int = 10, cfg_scale: float = 1.0,
+                       noise: Optional[torch.Tensor] = None,
+                       known_noises: Optional[Sequence[torch.Tensor]] = None) -> torch.Tensor:
+        """``inpaint_teacher_refine`` of the reference's long-form script (inference_pipeline.py:145-196): diffuse
+        ``x_coarse`` to t_start = int(T * strength), then ``steps`` v-prediction DDIM steps on a linear time grid with the
+        decoder's ``sem_features`` conditioning (step_idx 0); before every step the first ``overlap_len`` frames are replaced
+        by a freshly noised copy of ``known_mel`` (the previous chunk's tail) and after the loop by ``known_mel`` itself;
+        ``cfg_scale != 1`` adds classifier-free guidance against zero conditioning.  ``noise`` / ``known_noises[i]``
+        optionally inject the N(0,1) draws (the reference calls randn_like).  Context K/V (conditional and null) are
+        prepared once; the injection and the update are one streaming kernel each (edtts_inpaint_inject, edtts_vddim_step)."""
+        dec, sch, cfg = self.decoder, self.schedule, self.cfg
+        dec.eval()
+        lib = _lib.load()
+        x_coarse = _lib.f32(x_coarse)
+        dev = x_coarse.device
+        B, T, D = x_coarse.shape
+        S = sem_features.shape[1]
+        t_start = int(cfg.diff_steps * strength)
+        if not 0 <= t_start < cfg.diff_steps:
+            raise IndexError(f"t_start={t_start} is outside the {cfg.diff_steps}-entry schedule tables")   # as tensor indexing would
+        tab = {k: getattr(sch, k).detach().cpu() for k in ("alpha_bar", "sqrt_alpha_bar", "sqrt_one_minus_alpha_bar")}
+        times = torch.linspace(t_start, 0, steps + 1).long()[:-1]                     # inference_pipeline.py:164-165
+        coefs, t_dev = [], []
+        for i in range(len(times)):
+            t_next = times[i + 1] if i < len(times) - 1 else torch.tensor(0)
+            tt = torch.full((B,), int(times[i]), dtype=torch.long)
+            a_next = tab["alpha_bar"][t_next]
+            co = torch.empty(B, 4, dtype=torch.float32)
+            co[:, 0] = tab["sqrt_alpha_bar"][tt]
+            co[:, 1] = tab["sqrt_one_minus_alpha_bar"][tt]
+            co[:, 2] = torch.sqrt(a_next)
+            co[:, 3] = torch.sqrt(1 - a_next)
+            coefs.append(co.to(dev))
+            t_dev.append(tt.to(dev))
+        st = _lib.stream_ptr(dev)
+        # q_sample of the coarse input at t_start (inference_pipeline.py:160-162): the injection kernel over all T frames
+        if noise is None:
+            noise = torch.randn_like(x_coarse)
+        ts = torch.full((B,), t_start, dtype=torch.long)
+        co0 = torch.zeros(B, 4, dtype=torch.float32)
+        co0[:, 0], co0[:, 1] = tab["sqrt_alpha_bar"][ts], tab["sqrt_one_minus_alpha_bar"][ts]
+        co0 = co0.to(dev)
+        x = torch.empty_like(x_coarse)
+        _lib.check(lib.edtts_inpaint_inject(_lib.ptr(x), _lib.ptr(x_coarse), _lib.ptr(_lib.f32(noise)), _lib.ptr(co0), B, T, T, D,
+                                            st), "inpaint_inject")
+        sem_features = _lib.f32(sem_features)
+        kv = dec.prepare_context(None, sem_features, T)
+        kv0 = dec.prepare_context(None, torch.zeros_like(sem_features), T) if cfg_scale != 1.0 else None
+        s_idx = torch.zeros(B, dtype=torch.long, device=dev)
+        if known_mel is not None:
+            known_mel = _lib.f32(known_mel)
+            if tuple(known_mel.shape) != (B, overlap_len, D):
+                raise ValueError(f"known_mel must be [B, overlap_len, n_mels] = {(B, overlap_len, D)}, got {tuple(known_mel.shape)}")
+        v_c = torch.empty_like(x)
+        v_u = torch.empty_like(x) if kv0 is not None else None
+        for i in range(len(times)):
+            if known_mel is not None and overlap_len > 0:
+                nk = known_noises[i] if known_noises is not None else torch.randn_like(known_mel)
+                _lib.check(lib.edtts_inpaint_inject(_lib.ptr(x), _lib.ptr(known_mel), _lib.ptr(_lib.f32(nk)), _lib.ptr(coefs[i]), B,
+                                                    T, overlap_len, D, st), "inpaint_inject")
+            mod = dec.prepare_cond(t_dev[i], s_idx, T, S)
+            for kvx, out in ((kv, v_c), (kv0, v_u)):
+                if kvx is None:
+                    continue
+                a = _lib.StepArgs()
+                a.mode = _lib.STEP_EPS
+                a.eps_out = out.data_ptr()
+                dec.step(x, mod, kvx, S, a)
+            _lib.check(lib.edtts_vddim_step(_lib.ptr(x), _lib.ptr(v_c), _lib.ptr(v_u) if v_u is not None else None,
+                                            float(cfg_scale), _lib.ptr(coefs[i]), _lib.ptr(x), None, B, T * D, st), "vddim_step")
+        if known_mel is not None and overlap_len > 0:
+            x[:, :overlap_len, :] = known_mel                                          # inference_pipeline.py:193-194
+        return x
+
     # ------------------------------------------------------------------ DDPM, long loop
     @torch.no_grad()
     def sample_ddpm(self, sem_idx: torch.Tensor, x_T: torch.Tensor, noises: Optional[Sequence[torch.Tensor]] = None,

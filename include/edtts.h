@@ -220,6 +220,18 @@ int edtts_dpm_step(const float* x_t, const float* model_out, const float* hist1,
                    int32_t order_used, int32_t predict_x0, float* x_prev_out, float* x0_out, int32_t B, int64_t n,
                    void* stream);
 
+/* --- in-painting refine loop of the long-form pipeline (inference_pipeline.py:145-196) --------------------------------- */
+/* One v-prediction DDIM step (inference_pipeline.py:181-192): v = v_uncond ? v_uncond + cfg_scale (v_cond - v_uncond) :
+ * v_cond; x0 = clamp(sa x - sb v, +-3); eps = sb x + sa v; x_next = an x0 + bn eps.  coef is [B][4] fp32 per batch row:
+ * {sa = sqrt_alpha_bar[t], sb = sqrt_one_minus_alpha_bar[t], an = sqrt(alpha_bar[t_next]), bn = sqrt(1 - alpha_bar[t_next])},
+ * built by the caller with the reference's tensor expressions.  x_next_out may alias x_t; n = elements per batch row. */
+int edtts_vddim_step(const float* x_t, const float* v_cond, const float* v_uncond, float cfg_scale, const float* coef,
+                     float* x_next_out, float* x0_out, int32_t B, int64_t n, void* stream);
+/* In-painting injection (inference_pipeline.py:170-174): x[b, :L, :] = sa known[b] + sb noise[b] for the first L of the T
+ * frames (q_sample of the known frames at the current timestep); coef as above (sa, sb are read). */
+int edtts_inpaint_inject(float* x, const float* known, const float* noise, const float* coef, int32_t B, int32_t T,
+                         int32_t L, int32_t D, void* stream);
+
 /* --- FSQ (models/fsq.py:18-132), the reference's alternative quantiser ------- */
 /* forward (fsq.py:84-108): z [rows, dim] -> z_q = tanh(z) + (quantise(tanh(z)) - tanh(z)) and the flat index per row
  * (basis = cumprod([1] + levels[:-1]), first dimension fastest).  levels is a HOST array of dim (<= 8) ints.

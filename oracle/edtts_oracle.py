@@ -491,5 +491,53 @@ def fsq_indices_to_codes(levels, indices: Tensor) -> Tensor:
     return codes.float() / ((lv.float() - 1) / 2) - 1
 
 
+# ----------------------------------------------------------------------------
+# inference_pipeline.py:145-196  in-painting refine loop of the long-form pipeline
+# ----------------------------------------------------------------------------
+def inpaint_refine(sd: State, tab: State, x_coarse: Tensor, sem_features: Tensor, known_mel: Optional[Tensor] = None,
+                   overlap_len: int = 0, strength: float = 0.2, steps: int = 10, cfg_scale: float = 1.0,
+                   noise: Optional[Tensor] = None, known_noises=None, trace: Optional[list] = None) -> Tensor:
+    """inpaint_teacher_refine (inference_pipeline.py:145-196): diffuse x_coarse to t_start = int(T * strength), then
+    ``steps`` v-prediction DDIM steps on a linear time grid; before every step the first ``overlap_len`` frames are
+    replaced by a freshly noised copy of ``known_mel`` (the previous chunk's tail); optional classifier-free guidance
+    against zero conditioning.  ``noise`` / ``known_noises[i]`` inject the reference's randn_like draws."""
+    B = x_coarse.shape[0]
+    T = tab["alpha_bar"].shape[0]
+    t_start = int(T * strength)
+    z_null = torch.zeros_like(sem_features)
+    if noise is None:
+        noise = torch.randn_like(x_coarse)
+    ts = torch.full((B,), t_start, dtype=torch.long)
+    x = tab["sqrt_alpha_bar"][ts][:, None, None] * x_coarse + tab["sqrt_one_minus_alpha_bar"][ts][:, None, None] * noise
+    times = torch.linspace(t_start, 0, steps + 1).long()[:-1]
+    s_idx = torch.full((B,), 0, dtype=torch.long)
+    with torch.no_grad():
+        for i in range(len(times)):
+            t_curr = times[i]
+            t_next = times[i + 1] if i < len(times) - 1 else torch.tensor(0)
+            tt = torch.full((B,), int(t_curr), dtype=torch.long)
+            sa = tab["sqrt_alpha_bar"][tt][:, None, None]
+            sb = tab["sqrt_one_minus_alpha_bar"][tt][:, None, None]
+            if known_mel is not None:
+                nk = known_noises[i] if known_noises is not None else torch.randn_like(known_mel)
+                x[:, :overlap_len, :] = sa * known_mel + sb * nk
+            v_cond = decoder_forward(sd, x, tt, None, s_idx, sem_features=sem_features)
+            if cfg_scale != 1.0:
+                v_unc = decoder_forward(sd, x, tt, None, s_idx, sem_features=z_null)
+                v = v_unc + cfg_scale * (v_cond - v_unc)
+            else:
+                v = v_cond
+            x0 = torch.clamp(sa * x - sb * v, -3, 3)
+            eps = sb * x + sa * v
+            a_next = tab["alpha_bar"][t_next]
+            x_in = x
+            x = torch.sqrt(a_next) * x0 + torch.sqrt(1 - a_next) * eps
+            if trace is not None:
+                trace.append((x_in.clone(), v_cond, x0, x.clone()))
+    if known_mel is not None:
+        x[:, :overlap_len, :] = known_mel
+    return x
+
+
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -60,6 +60,33 @@ def make_fsq(ref, meta):
     torch.save(dict(meta=meta, cases=cases), os.path.join(OUT, "fsq.pt"))
 
 
+def inpaint_cases():
+    """(name, cfg_scale, with known frames) and the seeded inputs shared by the fixture generator and the tests."""
+    feats = synth.synth_features(61, 2, 16, 128)
+    xc = synth.synth_noise(61, 2, 32)
+    known = synth.synth_noise(62, 2, 8)
+    noises = [synth.synth_noise(70 + i, 2, 32 if i == 0 else 8, tag=f"n{i}") for i in range(6)]
+    return feats, xc, known, noises, (("plain", 1.0, False), ("inpaint", 1.0, True), ("inpaint_cfg", 1.7, True))
+
+
+def make_inpaint(ref, meta):
+    """inpaint_teacher_refine (inference_pipeline.py:145-196), cut out of the unmodified script (ref_harness)."""
+    fn = R.reference_inpaint_refine(ref)
+    feats, xc, known, noises, cases = inpaint_cases()
+    out = {}
+    for name, scale, with_known in cases:
+        it = iter(noises)
+        real = torch.randn_like
+        torch.randn_like = lambda a: next(it).clone()
+        try:
+            with torch.no_grad():
+                out[name] = fn(xc, feats, known_mel=known if with_known else None, overlap_len=8 if with_known else 0,
+                               strength=0.5, steps=5, cfg_scale=scale)
+        finally:
+            torch.randn_like = real
+    torch.save(dict(meta=meta, strength=0.5, steps=5, overlap=8, x=out), os.path.join(OUT, "inpaint.pt"))
+
+
 def main(only=None):
     torch.manual_seed(0)
     torch.set_num_threads(1)          # fixed summation order for the recorded outputs
@@ -73,6 +100,9 @@ def main(only=None):
         return
     if only == "fsq":
         make_fsq(ref, meta)
+        return
+    if only == "inpaint":
+        make_inpaint(ref, meta)
         return
 
     # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
@@ -176,6 +206,7 @@ def main(only=None):
 
     make_dpm(ref, meta)
     make_fsq(ref, meta)
+    make_inpaint(ref, meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -97,3 +97,19 @@ def reference_generate_mel(ref, sem_idx, num_steps, x_T):
         torch.randn = real
     assert len(calls) == 1
     return out
+
+
+def reference_inpaint_refine(ref):
+    """The reference's ``inpaint_teacher_refine`` is a closure nested inside ``main()`` of the top-level script
+    inference_pipeline.py (lines 145-196) and cannot be imported.  Its source is cut out of the UNMODIFIED file with ``ast``
+    and compiled with the closure variables it reads (cfg, schedule, device, teacher_decoder) supplied as globals -- the
+    statements that run are the reference's own."""
+    import ast
+    import textwrap
+    path = os.path.join(REFERENCE_ROOT, "inference_pipeline.py")
+    src = open(path).read()
+    fn = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "inpaint_teacher_refine")
+    code = textwrap.dedent(ast.get_source_segment(src, fn))
+    env = dict(torch=torch, cfg=ref["cfg"], schedule=ref["schedule"], device="cpu", teacher_decoder=ref["decoder"])
+    exec(compile(code, path, "exec"), env)
+    return env["inpaint_teacher_refine"]

@@ -74,3 +74,25 @@ def test_dpm_solver(ref):
         assert torch.equal(solver.get_time_steps(steps, 950), O.dpm_time_steps(tab, steps, 950))
         got = O.dpm_sample(sd, tab, xT, feats, steps, order)
         assert (got - want).abs().max().item() < 2e-5, (order, steps)
+
+
+def test_inpaint_refine(ref):
+    """inpaint_teacher_refine, cut out of the reference script (ref_harness.reference_inpaint_refine), == the oracle."""
+    from oracle.make_golden import inpaint_cases
+    fn = R.reference_inpaint_refine(ref)
+    sd = synth.synth_decoder_state(0)
+    tab = O.cosine_schedule(1000)
+    feats, xc, known, noises, cases = inpaint_cases()
+    for name, scale, with_known in cases:
+        it = iter(noises)
+        real = torch.randn_like
+        torch.randn_like = lambda a: next(it).clone()
+        try:
+            with torch.no_grad():
+                want = fn(xc, feats, known_mel=known if with_known else None, overlap_len=8 if with_known else 0,
+                          strength=0.5, steps=5, cfg_scale=scale)
+        finally:
+            torch.randn_like = real
+        got = O.inpaint_refine(sd, tab, xc, feats, known if with_known else None, 8 if with_known else 0, 0.5, 5, scale,
+                               noise=noises[0], known_noises=noises[1:])
+        assert (got - want).abs().max().item() < 2e-5, name
