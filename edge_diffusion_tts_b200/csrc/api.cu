@@ -67,7 +67,7 @@ extern "C" int edtts_kernel_classes(void) { return KC_COUNT; }
 extern "C" const char* edtts_kernel_class_name(int cls) {
   static const char* names[KC_COUNT] = {"gemm_simt_fp32", "attn_window_simt_fp32", "attn_cross_simt_fp32", "cond",
                                         "embed_ctx", "vq", "schedule", "dsconv", "tc_gemm_bf16",
-                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc", "tc_layer_bf16"};
+                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc", "tc_layer_bf16", "mel_longform"};
   return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
 }
 

@@ -1287,7 +1287,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
             ddim_update(x.y, e[4 * q + 1], 0.f, ab_t, ab_p, 0.f, xp.y, x0.y);
             ddim_update(x.z, e[4 * q + 2], 0.f, ab_t, ab_p, 0.f, xp.z, x0.z);
             ddim_update(x.w, e[4 * q + 3], 0.f, ab_t, ab_p, 0.f, xp.w, x0.w);
-            if (sa.x0_out) reinterpret_cast<float4*>(sa.x0_out + o)[q] = x0;
+            if (sa.x0_out) __stcs(reinterpret_cast<float4*>(sa.x0_out + o) + q, x0);      // streaming: read back by the host / next history step only
             if (sa.write_x_prev && sa.x_prev_out) reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
           }
         } else if (sa.mode == EDTTS_STEP_DDPM) {

@@ -232,6 +232,30 @@ int edtts_vddim_step(const float* x_t, const float* v_cond, const float* v_uncon
 int edtts_inpaint_inject(float* x, const float* known, const float* noise, const float* coef, int32_t B, int32_t T,
                          int32_t L, int32_t D, void* stream);
 
+/* --- mel statistics and the cross-fade stitch of the long-form pipeline --------------------------- */
+/* normalize_mel (edge_diffusion_tts/utils/audio.py:10-14): mel [B,T,n_mels] -> mean / std over the frames per (utterance,
+ * mel bin) ([B,n_mels], i.e. the reference's [B,1,n_mels]; std unbiased, clamped to >= 1e-5) and, if mel_n_out is
+ * non-NULL, (mel - mean) / std.  The statistics are accumulated in fp64 (parity with torch: <= 1e-6 relative); the
+ * element-wise part is bit-exact given the statistics. */
+int edtts_normalize_mel(const float* mel, float* mel_n_out, float* mean_out, float* std_out, int32_t B, int32_t T,
+                        int32_t n_mels, void* stream);
+/* denormalize_mel (utils/audio.py:17-19): mel_n * std + mean (two roundings, as torch) -- bit-exact. */
+int edtts_denormalize_mel(const float* mel_n, const float* mean, const float* std_, float* mel_out, int32_t B, int32_t T,
+                          int32_t n_mels, void* stream);
+/* One chunk of the overlap-add (inference_pipeline.py:359-375), fused: final_mel[b, m, start + t] +=
+ * exp(x_chunk[b, t, m] * std[b, m] + mean[b, m]) * window[t]; final_weights[start + t] += window[t].
+ * final_mel [B, n_mels, total_frames], final_weights [total_frames], x_chunk [B, T, n_mels] (the refined, normalised
+ * chunk), mean / std [B, n_mels] (per-chunk statistics), window [T].  start + T must fit the buffer. */
+int edtts_stitch_add(float* final_mel, float* final_weights, const float* x_chunk, const float* mean, const float* std_,
+                     const float* window, int32_t B, int32_t T, int32_t n_mels, int64_t total_frames, int64_t start_frame,
+                     void* stream);
+/* inference_pipeline.py:377-393: mel_out [B, n_mels, total_frames] = final_mel[..., :total_frames] /
+ * clamp(final_weights, 1e-5); smooth_out = avg_pool2d(mel_out, (kernel_h, kernel_w), stride 1, padding k/2) (zero
+ * padded, always divided by kernel_h * kernel_w).  Either output may be NULL; buffer_frames = row stride of final_mel. */
+int edtts_stitch_finalize(const float* final_mel, const float* final_weights, float* mel_out, float* smooth_out, int32_t B,
+                          int32_t n_mels, int64_t buffer_frames, int64_t total_frames, int32_t kernel_h, int32_t kernel_w,
+                          void* stream);
+
 /* --- FSQ (models/fsq.py:18-132), the reference's alternative quantiser ------- */
 /* forward (fsq.py:84-108): z [rows, dim] -> z_q = tanh(z) + (quantise(tanh(z)) - tanh(z)) and the flat index per row
  * (basis = cumprod([1] + levels[:-1]), first dimension fastest).  levels is a HOST array of dim (<= 8) ints.

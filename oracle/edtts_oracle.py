@@ -539,5 +539,75 @@ def inpaint_refine(sd: State, tab: State, x_coarse: Tensor, sem_features: Tensor
     return x
 
 
+# ----------------------------------------------------------------------------
+# utils/audio.py:10-19 and inference_pipeline.py:217-393  mel statistics, chunk plan, cross-fade stitch
+# ----------------------------------------------------------------------------
+def normalize_mel(mel: Tensor):
+    """utils/audio.py:10-14: statistics over dim 1, unbiased std clamped to >= 1e-5."""
+    mean = mel.mean(dim=1, keepdim=True)
+    std = mel.std(dim=1, keepdim=True).clamp_min(1e-5)
+    return (mel - mean) / std, mean, std
+
+
+def denormalize_mel(mel_n: Tensor, mean: Tensor, std: Tensor) -> Tensor:
+    """utils/audio.py:17-19."""
+    return mel_n * std + mean
+
+
+def chunk_plan(total_samples: int, sample_rate: int, chunk_seconds: float = 2.0, overlap_seconds: float = 0.5):
+    """inference_pipeline.py:218-225, 295-319: (start_sample, end_sample, start_lat, end_lat) per chunk."""
+    chunk_samples = int(chunk_seconds * sample_rate)
+    overlap_samples = int(overlap_seconds * sample_rate)
+    hop = chunk_samples - overlap_samples
+    n = int(math.ceil((total_samples - overlap_samples) / hop))
+    out = []
+    for i in range(n):
+        a = i * hop
+        b = a + chunk_samples
+        out.append((a, b, int(a / sample_rate * 16000) // 320, int(b / sample_rate * 16000) // 320))
+    return out
+
+
+def crossfade_window(chunk_frames: int, overlap_frames: int) -> Tensor:
+    """inference_pipeline.py:255-262: ones with a linear fade-in / fade-out of overlap_frames at the two ends."""
+    w = torch.ones(1, chunk_frames)
+    w[0, :overlap_frames] = torch.linspace(0, 1, overlap_frames)
+    w[0, -overlap_frames:] = torch.linspace(1, 0, overlap_frames)
+    return w
+
+
+def stitch(chunks, stats, chunk_frames: int, overlap_frames: int, total_frames: int, kernel=(5, 3)):
+    """inference_pipeline.py:228-230, 359-393: overlap-add exp(denormalised chunk) under the window at i * hop frames,
+    divide by the clamped accumulated weights, trim, average-pool.  chunks[i] [1,T,n_mels]; stats[i] = (mean, std).
+    Returns (final_mel [n_mels,total], smoothed [1,n_mels,total])."""
+    n_mels = chunks[0].shape[2]
+    final_mel = torch.zeros(n_mels, total_frames + 1000)
+    final_w = torch.zeros(1, total_frames + 1000)
+    win = crossfade_window(chunk_frames, overlap_frames)
+    hop = chunk_frames - overlap_frames
+    for i, (x, (mean, std)) in enumerate(zip(chunks, stats)):
+        out = torch.exp(denormalize_mel(x, mean, std)).transpose(1, 2).squeeze(0)[:, :chunk_frames]
+        final_mel[:, i * hop:i * hop + chunk_frames] += out * win
+        final_w[:, i * hop:i * hop + chunk_frames] += win
+    final_mel = (final_mel / torch.clamp(final_w, min=1e-5))[:, :total_frames]
+    kh, kw = kernel
+    smooth = torch.nn.functional.avg_pool2d(final_mel[None, None], kernel_size=(kh, kw), stride=1,
+                                            padding=(kh // 2, kw // 2)).squeeze(0)
+    return final_mel, smooth
+
+
+def longform_generate(sd: State, tab: State, z_q_global: Tensor, plan, chunk_stats, chunk_frames: int, overlap_frames: int,
+                      total_frames: int, refine_strength: float, refine_steps: int, cfg_scale: float, noises):
+    """The chunk loop of inference_pipeline.py:293-393 with injected draws: noises[i] = (x_coarse, noise, known_noises)."""
+    prev_tail, chunks = None, []
+    for i, (_, _, a, b) in enumerate(plan):
+        xc, nz, kn = noises[i]
+        x = inpaint_refine(sd, tab, xc, z_q_global[:, a:b, :], prev_tail, overlap_frames, refine_strength, refine_steps,
+                           cfg_scale, noise=nz, known_noises=kn)
+        prev_tail = x[:, -overlap_frames:, :].clone()
+        chunks.append(x)
+    return stitch(chunks, chunk_stats, chunk_frames, overlap_frames, total_frames) + (chunks,)
+
+
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -87,6 +87,33 @@ def make_inpaint(ref, meta):
     torch.save(dict(meta=meta, strength=0.5, steps=5, overlap=8, x=out), os.path.join(OUT, "inpaint.pt"))
 
 
+def longform_cases():
+    """Seeded inputs shared by the fixture generator and the tests: 4 chunks of 24 frames with an overlap of 6, a mel with
+    realistic (log-domain) statistics, and the per-chunk noise draws of a short refine loop."""
+    chunk_frames, overlap, n_chunks = 24, 6, 4
+    hop = chunk_frames - overlap
+    total = hop * (n_chunks - 1) + chunk_frames - 5                       # trimmed inside the last chunk
+    g = torch.Generator().manual_seed(81)
+    mel = torch.randn(3, 57, 80, generator=g) * torch.linspace(0.5, 2.5, 80) - 4.0 + torch.randn(3, 1, 80, generator=g)
+    mel[2, :, 7] = mel[2, 0, 7]                                           # a constant bin: std clamps to 1e-5
+    chunks = [synth.synth_noise(90 + i, 1, chunk_frames + (2 if i == 1 else 0), tag=f"c{i}") for i in range(n_chunks)]   # one over-long chunk
+    stats = [(torch.randn(1, 1, 80, generator=g) - 5.0, torch.rand(1, 1, 80, generator=g) + 0.5) for _ in range(n_chunks)]
+    return dict(chunk_frames=chunk_frames, overlap=overlap, total=total, mel=mel, chunks=chunks, stats=stats)
+
+
+def make_longform(ref, meta):
+    """normalize_mel / denormalize_mel (utils/audio.py, imported) and the chunk plan / window / overlap-add statements of
+    inference_pipeline.py:217-393 (cut out of the unmodified script, ref_harness._main_statements)."""
+    from edge_diffusion_tts.utils.audio import normalize_mel, denormalize_mel
+    c = longform_cases()
+    mel_n, mean, std = normalize_mel(c["mel"])
+    back = denormalize_mel(mel_n, mean, std)
+    plans = {f"{n}@{sr}": R.reference_chunk_plan(n, sr) for n, sr in ((22050 * 7, 22050), (16000 * 5 + 123, 16000), (24000 * 3, 24000))}
+    win, final_mel, smooth = R.reference_stitch(ref, c["chunks"], c["stats"], c["chunk_frames"], c["overlap"], c["total"])
+    torch.save(dict(meta=meta, mel_n=mel_n, mean=mean, std=std, back=back, plans=plans, window=win, final_mel=final_mel,
+                    smooth=smooth), os.path.join(OUT, "longform.pt"))
+
+
 def main(only=None):
     torch.manual_seed(0)
     torch.set_num_threads(1)          # fixed summation order for the recorded outputs
@@ -103,6 +130,9 @@ def main(only=None):
         return
     if only == "inpaint":
         make_inpaint(ref, meta)
+        return
+    if only == "longform":
+        make_longform(ref, meta)
         return
 
     # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
@@ -207,6 +237,7 @@ def main(only=None):
     make_dpm(ref, meta)
     make_fsq(ref, meta)
     make_inpaint(ref, meta)
+    make_longform(ref, meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -113,3 +113,86 @@ def reference_inpaint_refine(ref):
     env = dict(torch=torch, cfg=ref["cfg"], schedule=ref["schedule"], device="cpu", teacher_decoder=ref["decoder"])
     exec(compile(code, path, "exec"), env)
     return env["inpaint_teacher_refine"]
+
+
+def _main_statements(names, region, if_tests=()):
+    """Source of the statements of ``main()`` in the UNMODIFIED inference_pipeline.py that lie ``region`` = "before" /
+    "inside" / "after" its chunk loop (``for i in tqdm.tqdm(range(num_chunks))``), at any nesting depth and in source
+    order, and assign to one of ``names`` (plain, subscript or augmented assignment) or are an ``if`` whose test
+    mentions one of ``if_tests`` (taken whole).  The chunk loop is inline script code; this runs the reference's own
+    statements on supplied inputs without the audio / HuBERT / torchaudio context around them."""
+    import ast
+    import textwrap
+    path = os.path.join(REFERENCE_ROOT, "inference_pipeline.py")
+    src = open(path).read()
+    main = next(n for n in ast.walk(ast.parse(src)) if isinstance(n, ast.FunctionDef) and n.name == "main")
+    loop = next(n for n in main.body if isinstance(n, ast.For) and "num_chunks" in ast.get_source_segment(src, n.iter))
+    lo, hi = {"before": (main.lineno, loop.lineno - 1), "inside": (loop.lineno + 1, loop.end_lineno),
+              "after": (loop.end_lineno + 1, main.end_lineno)}[region]
+
+    def base(t):
+        while isinstance(t, ast.Subscript):
+            t = t.value
+        return t.id if isinstance(t, ast.Name) else None
+
+    picked = []
+
+    def visit(body):
+        for s in body:
+            if isinstance(s, ast.FunctionDef) or s.end_lineno < lo or s.lineno > hi:
+                continue
+            if isinstance(s, ast.Assign) and base(s.targets[0]) in names:
+                picked.append(s)
+            elif isinstance(s, ast.AugAssign) and base(s.target) in names:
+                picked.append(s)
+            elif isinstance(s, ast.If) and any(isinstance(n, ast.Name) and n.id in if_tests for n in ast.walk(s.test)):
+                picked.append(s)
+            elif isinstance(s, (ast.For, ast.With, ast.If)):
+                visit(s.body)
+
+    visit(main.body)
+    picked.sort(key=lambda s: s.lineno)
+    return "\n".join(textwrap.dedent(" " * s.col_offset + ast.get_source_segment(src, s)) for s in picked), path
+
+
+def reference_chunk_plan(total_samples, sample_rate):
+    """inference_pipeline.py:218-225 and :295-319 (chunk / latent ranges), the reference's own statements."""
+    import numpy as np
+    head, path = _main_statements({"chunk_seconds", "overlap_seconds", "chunk_samples", "overlap_samples", "hop_samples",
+                                   "num_chunks"}, "before")
+    body, _ = _main_statements({"start_sample", "end_sample", "start_sec", "end_sec", "start_idx_16k", "end_idx_16k", "start_lat",
+                                "end_lat"}, "inside")
+
+    class _C:
+        pass
+    cfg = _C()
+    cfg.sample_rate = sample_rate
+    env = dict(np=np, cfg=cfg, total_samples=total_samples)
+    exec(compile(head, path, "exec"), env)
+    plan = []
+    for i in range(env["num_chunks"]):
+        env["i"] = i
+        exec(compile(body, path, "exec"), env)
+        plan.append((env["start_sample"], env["end_sample"], env["start_lat"], env["end_lat"]))
+    return plan
+
+
+def reference_stitch(ref, chunks, stats, chunk_frames, overlap_frames, total_frames):
+    """The overlap-add of inference_pipeline.py:228-230, 239, 255-262, 359-393 run on given refined chunks ([1,T,n_mels]
+    each) and per-chunk (mean, std): returns (window_mask, final_mel [n_mels,total], lin_mel_smoothed [1,n_mels,total])."""
+    import torch.nn.functional as F
+    from edge_diffusion_tts.utils.audio import denormalize_mel
+    init, path = _main_statements({"estimated_frames", "final_mel", "final_weights", "hop_frames", "window_mask", "fade_len",
+                                   "fade_in", "fade_out"}, "before")
+    loop, _ = _main_statements({"mel_denorm", "lin_mel", "output_chunk", "start_frame", "end_frame", "final_mel", "final_weights"},
+                               "inside", if_tests={"output_chunk"})
+    post, _ = _main_statements({"final_weights", "final_mel", "lin_mel", "lin_mel_2d", "kernel_h", "kernel_w", "lin_mel_smoothed"},
+                               "after")
+    env = dict(torch=torch, F=F, cfg=ref["cfg"], device="cpu", denormalize_mel=denormalize_mel, total_frames=total_frames,
+               chunk_frames=chunk_frames, overlap_frames=overlap_frames)
+    exec(compile(init, path, "exec"), env)
+    for i, (x, (m, s)) in enumerate(zip(chunks, stats)):
+        env.update(i=i, x_refined=x, real_mean=m, real_std=s)
+        exec(compile(loop, path, "exec"), env)
+    exec(compile(post, path, "exec"), env)
+    return env["window_mask"], env["final_mel"], env["lin_mel_smoothed"]
