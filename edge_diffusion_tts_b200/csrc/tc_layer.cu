@@ -76,22 +76,14 @@ int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st) {
   return rc;
 }
 
-// One launch of the fused kernel.  layer = -1: head (in_proj + pe); otherwise transformer block `layer`.
+// Arguments of one "layer launch" of the fused kernel.  layer = -1: head (in_proj + pe); otherwise transformer block `layer`.
 // tail: LT_NONE / LT_QKV (norm1 + QKV of block layer+1, written to qkv_out) / LT_FINAL (final_norm + out_proj + step).
-int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, int layer, int tail, float* hc,
-                    const void* qkv_in, void* qkv_out, const void* kvx, const float* mod, const float* x_t,
-                    const edtts_step_args* step, int B, int T, int S, int stop_phase, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
-      return check_launch("tc_layer smem attribute");
-    configured = true;
-  }
+static int fill_layer_args(LayerArgs& a, const edtts_decoder_weights* w, const void* layer_img_base, int layer, int tail,
+                           float* hc, const void* qkv_in, void* qkv_out, const void* kvx, const float* mod, const float* x_t,
+                           const edtts_step_args* step, int B, int T, int S, int stop_phase) {
   const uint8_t* base = reinterpret_cast<const uint8_t*>(layer_img_base);
   const uint8_t* ex = base + LY_EXTRA_OFF;
   const int mod_stride = 2 * NL * 2 * H;                  // mod[b][2 l + {0: norm1, 1: norm3}][scale 160 | shift 160]
-  LayerArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = layer < 0 ? LM_HEAD : LM_BLOCK;
   a.tail = tail;
@@ -128,30 +120,81 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
     a.fn_w = w->final_norm_w;
     a.fn_b = w->final_norm_b;
     a.out_b = w->out_proj_b;
-    a.step = *step;
   }
   a.stop_phase = stop_phase;
   a.phase_clocks = nullptr;
+  return EDTTS_OK;
+}
+
+int64_t tc_layer_flag_bytes(int B, int T) { return align_up((int64_t)LY_MAXL * B * ((T + 127) / 128) * 4, 256); }
+
+// The head and `n_layers` transformer blocks of one decoder evaluation.  merged: one persistent launch over all of them
+// (items ordered layer-major, per-item dependency flags in `flags`, tc_layer_flag_bytes, zeroed here on the stream);
+// otherwise one launch per layer.  qb[0] receives the head's q | k | v; block l reads qb[l & 1] and writes qb[(l + 1) & 1].
+int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base, int n_layers, float* hc, void* const qb[2],
+                     const void* kv, const float* mod, const float* x_t, const edtts_step_args* step, int B, int T, int S,
+                     int stop_phase, bool merged, void* flags, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
+      return check_launch("tc_layer smem attribute");
+    configured = true;
+  }
+  EDTTS_REQUIRE(n_layers >= 0 && n_layers + 1 <= LY_MAXL, EDTTS_EINVAL, "tc_layer: %d layers", n_layers);
+  MegaArgs all;
+  memset(&all, 0, sizeof(all));
+  int rc = fill_layer_args(all.a[0], w, layer_img_base, -1, n_layers > 0 ? LT_QKV : LT_NONE, hc, nullptr, qb[0], nullptr, mod, x_t,
+                           nullptr, B, T, S, 0);
+  if (rc) return rc;
+  for (int l = 0; l < n_layers; ++l) {
+    const bool last = l == n_layers - 1;
+    const int tail = !last ? LT_QKV : (step && stop_phase == 0 ? LT_FINAL : LT_NONE);
+    const __nv_bfloat16* kvl = reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H;
+    if ((rc = fill_layer_args(all.a[l + 1], w, layer_img_base, l, tail, hc, qb[l & 1], qb[(l + 1) & 1], kvl, mod, x_t, step, B, T, S,
+                              last ? stop_phase : 0)))
+      return rc;
+  }
+  const int n_launch = n_layers + 1;
+  if (step) all.step = *step;
   static long long* clk_buf = nullptr;
   static const bool want_clocks = getenv("EDTTS_LAYER_CLOCKS") != nullptr;
   if (want_clocks) {
     if (!clk_buf) cudaMalloc(&clk_buf, 148 * 32 * sizeof(long long));
-    a.phase_clocks = clk_buf;
+    for (int l = 0; l < n_launch; ++l) all.a[l].phase_clocks = clk_buf;
   }
-  const int ntiles = B * a.tiles_per_utt;
+  const int ntiles = B * ((T + 127) / 128);
 #ifdef LY_TRACE
   static long long* tr_buf = nullptr;
   static int tr_done = 0;
-  const bool tr_now = layer == 1 && tr_done < 1 && B >= 64;
+  const bool tr_now = tr_done < 1 && B >= 64;
   if (tr_now) {
     if (!tr_buf) cudaMalloc(&tr_buf, 4 * 1024 * sizeof(long long));
     cudaMemsetAsync(tr_buf, 0, 4 * 1024 * sizeof(long long), st);
-    a.phase_clocks = tr_buf;
+    for (int l = 0; l < n_launch; ++l) all.a[l].phase_clocks = tr_buf;
   }
 #endif
-  LaunchScope ls(KC_TC_LAYER, st);
-  if (want_clocks) tc_layer_kernel<true><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
-  else tc_layer_kernel<false><<<ntiles < 148 ? ntiles : 148, LY_THREADS, LY_SMEM, st>>>(a);
+  auto launch = [&](const MegaArgs& m, int items) {
+    LaunchScope ls(KC_TC_LAYER, st);
+    if (want_clocks) tc_layer_kernel<true><<<items < 148 ? items : 148, LY_THREADS, LY_SMEM, st>>>(m);
+    else tc_layer_kernel<false><<<items < 148 ? items : 148, LY_THREADS, LY_SMEM, st>>>(m);
+  };
+  if (merged && n_launch > 1) {
+    EDTTS_REQUIRE(flags, EDTTS_EINVAL, "tc_layer: merged launch needs the flag buffer");
+    if (cudaMemsetAsync(flags, 0, (size_t)n_launch * ntiles * 4, st) != cudaSuccess) return check_launch("tc_layer flags memset");
+    all.n_launch = n_launch;
+    all.done = reinterpret_cast<int*>(flags);
+    launch(all, n_launch * ntiles);
+  } else {
+    for (int l = 0; l < n_launch; ++l) {
+      MegaArgs one;
+      memset(&one, 0, sizeof(one));
+      one.a[0] = all.a[l];
+      one.step = all.step;
+      one.n_launch = 1;
+      launch(one, ntiles);
+    }
+  }
 #ifdef LY_TRACE
   if (tr_now) {
     static long long hb[4 * 1024];
@@ -167,11 +210,11 @@ int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, 
         fprintf(stderr, "TRACE %d %lld %lld\n", s_, hb[s_ * 1024 + 2 + 2 * e], hb[s_ * 1024 + 3 + 2 * e] - t0);
   }
 #endif
-  if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0
+  if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0 (summed over its items)
     long long hc_[32];
     cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[tc_layer clocks L%d] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3 %lld\n",
-            layer, hc_[0], hc_[1], hc_[2], hc_[3], hc_[4], hc_[5], hc_[6], hc_[7]);
+    fprintf(stderr, "[tc_layer clocks] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3 %lld\n",
+            hc_[0], hc_[1], hc_[2], hc_[3], hc_[4], hc_[5], hc_[6], hc_[7]);
     fprintf(stderr, "[tc_layer tail] norm+store_h %lld mma01 %lld issue2 %lld cvt_qk %lld wait2 %lld cvt_v+sync %lld\n", hc_[24], hc_[25],
             hc_[26], hc_[27], hc_[28], hc_[29]);
     for (int k = 1; k < 3; ++k)

@@ -76,12 +76,12 @@ static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay r
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
 constexpr int LO_BAR = LO_RED + 4 * 128 * 4;
-constexpr int LY_NBAR = 8 + 2 * 16;
+constexpr int LY_NBAR = 9 + 2 * 16;
 constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
 static_assert(LY_SMEM <= 232448, "shared memory budget");
 
 // mbarrier indices
-enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_WG0 = 8 };
+enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_DEP = 6 /* two */, LB_FIN = 8, LB_WG0 = 9 };
 // One commit per MMA group: WB_SK[n % 4] = "S op n retired" tells the softmax warps that S block n % 2 is full AND the TMA
 // producer that K stage n % 4 is free; WB_PV[n % 2] = "P V op n retired" frees V stage / P block n % 2 (lazy rescale).
 enum LyWgBar : int { WB_KFULL = 0, WB_SK = 4, WB_VFULL = 8, WB_PV = 10, WB_PFULL = 12, WB_OFULL = 14, WB_OFREE = 15, WB_COUNT = 16 };
@@ -124,9 +124,25 @@ struct LayerArgs {
   const float* fn_w;                 // final_norm.weight / bias [160]
   const float* fn_b;
   const float* out_b;                // [80]
-  edtts_step_args step;
   int stop_phase;                    // debug: 1 = stop after attention + proj, 2 = after cross, 0 = whole block
   long long* phase_clocks;           // debug: [gridDim.x][24] cycles per phase / attention section (thread 0), or null
+};
+
+// One launch runs up to LY_MAXL consecutive "layer launches" of a decoder step (head, blocks 0..3) as ONE persistent
+// grid: work item g = l * ntiles + tile, handed out round-robin in that order, so the CTAs that would idle in the last
+// wave of layer l start on layer l + 1 instead (1792 tiles on 148 SMs: 13 rounds per layer separately, 12.1 merged).
+// Item (l, n) reads what items (l-1, n-1), (l-1, n), (l-1, n+1) wrote (its h rows, q | k | v rows and their +-64 frame
+// halo); `done` holds one flag per item, set (release, gpu scope) when the item's stores are out and polled (acquire)
+// before the item starts.  Both are the job of one otherwise idle lane (the "agent": warp 8, lane 1), which hands the
+// result to the compute threads / TMA producers through mbarriers, so no compute warp ever waits on a gpu-scope fence.
+// The flags also order the write-after-read hazards of the double-buffered q | k | v (the readers of the rows an item
+// overwrites are exactly its three predecessors) and the in-place h (row-local).
+constexpr int LY_MAXL = 5;
+struct MegaArgs {
+  LayerArgs a[LY_MAXL];
+  edtts_step_args step;              // update rule of the LT_FINAL tail (last layer only)
+  int n_launch;
+  int* done;                         // [n_launch][ntiles], zeroed before the launch; null: no dependencies (n_launch == 1)
 };
 
 // Development trace (-DLY_TRACE): CTA 0 records (event id, clock) pairs of four threads -- compute warp 0 / warp 4 lane 0,
@@ -166,6 +182,26 @@ __device__ __forceinline__ void ly_issue_gemm_ex(uint32_t d_tmem, uint32_t a_add
   for (int ks = 0; ks < ksteps; ++ks)
     umma_bf16(d_tmem, make_desc(a_addr + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(w_addr + ks * 2 * n * 16, n * 16, 128), idesc,
               accumulate || ks > 0);
+}
+
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.b32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(int* p, int v) { asm volatile("st.relaxed.gpu.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// all three predecessors of item g (previous layer, tiles n-1 .. n+1) have published their results
+__device__ __forceinline__ bool ly_deps_ready(const int* done, int g, int ntiles) {
+  const int l = g / ntiles;
+  if (l == 0) return true;
+  const int n = g - l * ntiles;
+  const int* f = done + (l - 1) * ntiles;
+  int ok = ld_relaxed_gpu(f + n);
+  if (n > 0) ok &= ld_relaxed_gpu(f + n - 1);
+  if (n + 1 < ntiles) ok &= ld_relaxed_gpu(f + n + 1);
+  return ok != 0;
 }
 
 struct LyTile {
@@ -208,8 +244,8 @@ __device__ __forceinline__ int ly_nkeys(const LayerArgs& a, int i) {
 
 // ---- TMA producer of one warpgroup, one attention phase (one thread) ------------------------------------------
 template <bool WINDOW>
-__device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& tl, uint8_t* smem, uint64_t* wb, int wg,
-                                             uint32_t& nk, uint32_t& nv) {
+__device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const __nv_bfloat16* qkv, const __nv_bfloat16* kvx,
+                                             const LyTile& tl, uint8_t* smem, uint64_t* wb, int wg, uint32_t& nk, uint32_t& nv) {
   const LyPlan pl = ly_plan<WINDOW>(a, tl);
   uint8_t* kv = smem + LO_KV + wg * ((LY_KST + LY_VST) * LY_KBUF);
   auto load = [&](int head, int i, bool is_v, uint32_t& cnt) {
@@ -227,7 +263,7 @@ __device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& t
 #else
       mbar_expect_tx(full, 5 * LY_KSLAB);
 #pragma unroll
-      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.qkv + ((int64_t)(c0 + g) * a.R + g0) * 8, LY_KSLAB, full);
+      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, qkv + ((int64_t)(c0 + g) * a.R + g0) * 8, LY_KSLAB, full);
 #endif
     } else {
       const int nvalid = min(LY_KB, a.S - i * LY_KB);
@@ -244,7 +280,7 @@ __device__ __forceinline__ void ly_tma_phase(const LayerArgs& a, const LyTile& t
 #else
       mbar_expect_tx(full, 5 * nvalid * 16);
 #pragma unroll
-      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, a.kvx + ((int64_t)(c0 + g) * a.RS + g0) * 8, nvalid * 16, full);
+      for (int g = 0; g < 5; ++g) bulk_g2s(dst + g * LY_KSLAB, kvx + ((int64_t)(c0 + g) * a.RS + g0) * 8, nvalid * 16, full);
 #endif
     }
     ++cnt;
@@ -694,7 +730,7 @@ __device__ __forceinline__ void ly_softmax_phase(const LayerArgs& a, const LyTil
 
 // PROF = true: per-phase cycle counters (debug builds of the launch only; they cost ~50 registers)
 template <bool PROF>
-__global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs a) {
+__global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_constant__ MegaArgs p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sA = smem + LO_A;
   uint8_t* sW0 = smem + LO_W0;
@@ -709,6 +745,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   uint64_t* bar_g = bars + LB_G;
   uint64_t* bar_kvgo = bars + LB_KVGO;
   uint64_t* bar_attgo = bars + LB_ATTGO;
+  uint64_t* bar_dep = bars + LB_DEP;                      // [2]: item it's predecessors are visible (agent -> compute, TMA)
+  uint64_t* bar_fin = bars + LB_FIN;                      // item finished, its stores are issued (compute -> agent)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LY_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -716,8 +754,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   // finite shared memory everywhere (stale rows enter MMAs as 0 * x), zero pad slabs
   for (int i = tid * 16; i < LO_BAR; i += LY_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
-  if (a.mode == LM_BLOCK)
-    for (int i = tid; i < LC_COUNT; i += LY_THREADS) sC[i] = a.consts[i];
   if (tid == 0) {
     for (int i = 0; i < LB_WG0; ++i) mbar_init(bars + i, 1);
     for (int w = 0; w < 2; ++w) {
@@ -735,7 +771,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int ntiles = a.B * a.tiles_per_utt;
+  // d: the fields every layer of the launch shares (sizes, scale, h / x_t pointers) -- read through a compile-time
+  // index they stay direct constant-bank operands; only the per-layer pointers and modes go through p.a[l]
+  const LayerArgs& d = p.a[0];
+  const int ntiles = d.B * d.tiles_per_utt;
+  const int nitems = ntiles * p.n_launch;
 
   // =========================== control warps: TMA producers and MMA issuers ===========================
   if (warp >= 8) {
@@ -753,22 +793,58 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     if (is_mma || lane == 0) {
       uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
       uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;       // TMA: c0 = K loads, c1 = V loads; MMA: S ops, PV ops, heads
-      for (int tile = blockIdx.x; tile < ntiles && a.mode == LM_BLOCK; tile += gridDim.x) {
-        const LyTile tl = ly_tile(a, tile);
+      uint32_t it = 0;                                    // the CTA's item counter (head items included)
+      for (int g = blockIdx.x; g < nitems; g += gridDim.x, ++it) {
+        const int l = g / ntiles;
+        const LayerArgs& a = p.a[l];
+        if (a.mode != LM_BLOCK) continue;
+        const LyTile tl = ly_tile(d, g - l * ntiles);
         for (int ph = 0; ph < 2; ++ph) {
           if (ph == 1 && a.stop_phase == 1) break;
           if (!is_mma) {
             mbar_wait(bar_kvgo, n_phase & 1);
-            if (ph == 0) ly_tma_phase<true>(a, tl, smem, cwb, cwg, c0, c1);
-            else ly_tma_phase<false>(a, tl, smem, cwb, cwg, c0, c1);
+            if (ph == 0 && p.done) {                      // the window K/V (and halo) rows come from the previous layer's items
+              mbar_wait(bar_dep + (it & 1), (it >> 1) & 1);
+              fence_proxy_async_all();                    // they were written through the generic proxy, the copies read them through the async proxy
+            }
+            if (ph == 0) ly_tma_phase<true>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
+            else ly_tma_phase<false>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
           } else {
             mbar_wait(bar_attgo, n_phase & 1);
             tc_fence_after();
-            if (ph == 0) ly_mma_phase<true>(a, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
-            else ly_mma_phase<false>(a, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
+            if (ph == 0) ly_mma_phase<true>(d, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
+            else ly_mma_phase<false>(d, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
           }
           ++n_phase;
         }
+      }
+    } else if (cw == 0 && lane == 1 && p.done) {
+      // ---- the agent: gpu-scope acquire of every item's predecessors, gpu-scope release of every finished item ----
+      auto acquire = [&](int g, uint32_t slot) {          // blocking
+        for (uint32_t spin = 0; !ly_deps_ready(p.done, g, ntiles); ++spin) {
+          if (spin > (1u << 22)) __trap();
+          __nanosleep(64);
+        }
+        fence_acq_rel_gpu();
+        mbar_arrive(bar_dep + slot);
+      };
+      uint32_t it = 0;
+      if ((int)blockIdx.x < nitems) acquire(blockIdx.x, 0);
+      for (int g = blockIdx.x; g < nitems; g += gridDim.x, ++it) {
+        const int gn = g + (int)gridDim.x;
+        bool acq_done = gn >= nitems;
+        // while the item runs: pick up the next item's predecessors as soon as they are there (normally at once)
+        for (uint32_t spin = 0; !mbar_try_wait(bar_fin, it & 1); ++spin) {
+          if (!acq_done && ly_deps_ready(p.done, gn, ntiles)) {
+            fence_acq_rel_gpu();
+            mbar_arrive(bar_dep + ((it + 1) & 1));
+            acq_done = true;
+          }
+          if (spin > (1u << 24)) __trap();
+        }
+        fence_acq_rel_gpu();                              // the CTA's stores of item g (ordered before the arrive on bar_fin) ...
+        st_relaxed_gpu(p.done + g, 1);                    // ... are visible to whoever sees this flag
+        if (!acq_done) acquire(gn, (it + 1) & 1);         // release first: the next item may depend on items that wait for this one
       }
     }
     return;
@@ -787,19 +863,18 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     mbar_expect_tx(bar, bytes);
     bulk_g2s(slot, src, bytes, bar);
   };
-  auto load_wc = [&](int chunk, uint8_t* slot, uint64_t* bar) { load_w(a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, slot, bar); };
   auto gemm_wait = [&]() {
     mbar_wait(bar_g, ph_g);
     ph_g ^= 1;
     tc_fence_after();
   };
-  // first weight chunk of a tile (slot 0)
-  auto load_first = [&]() {
-    if (a.mode == LM_HEAD) load_w(a.w_in, LY_WCHUNK / 2, sW0, bar_w0);
-    else load_wc(WC_PROJ, sW0, bar_w0);
+  // first weight chunk of an item (slot 0); x = the item's layer arguments
+  auto load_first = [&](const LayerArgs& x) {
+    if (x.mode == LM_HEAD) load_w(x.w_in, LY_WCHUNK / 2, sW0, bar_w0);
+    else load_w(x.wimg + (int64_t)WC_PROJ * (LY_WCHUNK / 2), LY_WCHUNK, sW0, bar_w0);
   };
   // h (TMEM) of the valid rows -> HBM, chunk-major (debug stops only; the tail stores from registers)
-  auto store_h = [&](const LyTile& tl) {
+  auto store_h = [&](const LayerArgs& a, const LyTile& tl) {
 #pragma unroll 1
     for (int i = 0; i < 5; ++i) {
       float v[16];
@@ -807,7 +882,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       if (row < tl.nq) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + 4 * i + q) * a.R + tl.row0 + row) * 4) =
+          *reinterpret_cast<float4*>(d.hc + ((int64_t)(cb / 4 + 4 * i + q) * d.R + tl.row0 + row) * 4) =
               make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
@@ -821,32 +896,50 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     pc[i] += now_ - pc_last;                          \
     pc_last = now_;                                   \
   }
-  // tail constants that do not depend on the tile
-  if (tid < H) {
-    sC[LS_TB + tid] = a.mode == LM_HEAD ? a.in_b[tid] : sC[LC_F3B + tid];
-    if (a.tail == LT_FINAL) {
-      sC[LS_TG + tid] = a.fn_w[tid];
-      sC[LS_TS + tid] = a.fn_b[tid];
-      if (tid < M) sC[LS_OB + tid] = a.out_b[tid];
-    }
-  }
-  if (tid == 0 && blockIdx.x < ntiles) {
-    load_first();
-    if (a.mode == LM_BLOCK) mbar_arrive(bar_kvgo);        // K/V buffers are free: first window phase may load
+  if (tid == 0 && (int)blockIdx.x < nitems) {
+    const LayerArgs& a0 = p.a[blockIdx.x / ntiles];
+    load_first(a0);
+    if (a0.mode == LM_BLOCK) mbar_arrive(bar_kvgo);       // K/V buffers are free: first window phase may load
   }
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const LyTile tl = ly_tile(a, tile);
-    const bool more = tile + (int)gridDim.x < ntiles;
+  int cur_l = -1;
+  uint32_t it = 0;
+  for (int g = blockIdx.x; g < nitems; g += gridDim.x, ++it) {
+    const int l = g / ntiles;
+    const LayerArgs& a = p.a[l];
+    const LyTile tl = ly_tile(d, g - l * ntiles);
+    const bool more = g + (int)gridDim.x < nitems;
+    const LayerArgs& an = p.a[more ? (g + (int)gridDim.x) / ntiles : l];      // the next item's layer
+    auto load_wc = [&](int chunk, uint8_t* slot, uint64_t* bar) { load_w(a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, slot, bar); };
+    // end of an item: every compute thread has issued its stores (csync before); the agent publishes them
+    auto item_fin = [&]() {
+      if (p.done && tid == 0) mbar_arrive(bar_fin);
+    };
+
+    if (l != cur_l) {                                     // first item of a layer on this CTA: its constants
+      cur_l = l;
+      if (a.mode == LM_BLOCK)
+        for (int i = tid; i < LC_COUNT; i += LY_CTHREADS) sC[i] = a.consts[i];
+      csync();
+      if (tid < H) {                                      // tail constants that do not depend on the tile
+        sC[LS_TB + tid] = a.mode == LM_HEAD ? a.in_b[tid] : sC[LC_F3B + tid];
+        if (a.tail == LT_FINAL) {
+          sC[LS_TG + tid] = a.fn_w[tid];
+          sC[LS_TS + tid] = a.fn_b[tid];
+          if (tid < M) sC[LS_OB + tid] = a.out_b[tid];
+        }
+      }
+    }
+    if (p.done) mbar_wait(bar_dep + (it & 1), (it >> 1) & 1);   // the predecessors' h / q | k | v rows are visible
 
     if (tid < H) {                                        // per-utterance AdaLN vectors: gain = w * (1 + scale), shift
       if (a.mode == LM_BLOCK) {
-        const float* m = a.mod3 + (int64_t)tl.b * a.mod_stride;
+        const float* m = a.mod3 + (int64_t)tl.b * d.mod_stride;
         sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
         sC[LS_SH3 + tid] = m[H + tid];
       }
       if (a.tail == LT_QKV) {
-        const float* m = a.mod1 + (int64_t)tl.b * a.mod_stride;
+        const float* m = a.mod1 + (int64_t)tl.b * d.mod_stride;
         sC[LS_TG + tid] = a.n1w[tid] * (1.0f + m[tid]);
         sC[LS_TS + tid] = m[H + tid];
       }
@@ -855,7 +948,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     if (a.mode == LM_HEAD) {
       // ---- h = in_proj(x_t): x tile -> bf16 A operand (K = 80), one MMA chain into the h columns -----------------------
       {
-        const float4* src = reinterpret_cast<const float4*>(a.x_t + (tl.row0 + row) * M + 40 * wg);
+        const float4* src = reinterpret_cast<const float4*>(d.x_t + (tl.row0 + row) * M + 40 * wg);
         float4 x[10];
 #pragma unroll
         for (int q = 0; q < 10; ++q) x[q] = row < tl.nq ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -882,18 +975,19 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     if (lq == 0) LY_TR(wg, 40)
     if (warp_u == 1) {                                    // converged warp + elected lane: uniform-register addressing
       if (elect_one()) {
+        if (p.done) fence_proxy_async_all();              // q rows: written by another SM through the generic proxy
         mbar_expect_tx(bar_q, 20 * tl.nq * 16);
 #pragma unroll
-        for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * a.R + tl.row0) * 8, tl.nq * 16, bar_q);
+        for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * d.R + tl.row0) * 8, tl.nq * 16, bar_q);
       }
       __syncwarp();
     }
     {
-      const float* src = a.hc + ((int64_t)(cb / 4) * a.R + tl.row0 + row) * 4;
+      const float* src = d.hc + ((int64_t)(cb / 4) * d.R + tl.row0 + row) * 4;
       float4 x[20];
 #pragma unroll
       for (int q = 0; q < 20; ++q)
-        x[q] = row < tl.nq ? __ldcs(reinterpret_cast<const float4*>(src + (int64_t)q * a.R * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[q] = row < tl.nq ? __ldcs(reinterpret_cast<const float4*>(src + (int64_t)q * d.R * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 5; ++i) {
         float v[16];
@@ -920,7 +1014,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     LY_PHASE(0)
 
     // ---- banded self-attention -------------------------------------------------------------------------------
-    ly_softmax_phase<true, PROF>(a, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
+    ly_softmax_phase<true, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
     csync();
     LY_PHASE(1)
 
@@ -971,16 +1065,17 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     csync();
     if (a.stop_phase == 1) {
       tc_fence_after();
-      store_h(tl);
+      store_h(a, tl);
       // drain the prefetches so that the barrier phases stay consistent
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
       ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
       if (tid == 0 && more) {
-        load_first();
+        load_first(an);
         mbar_arrive(bar_kvgo);
       }
+      item_fin();
       continue;
     }
     LY_PHASE(2)
@@ -1007,7 +1102,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     LY_PHASE(3)
 
     // ---- cross attention over the context tokens ---------------------------------------------------------------------
-    ly_softmax_phase<false, PROF>(a, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
+    ly_softmax_phase<false, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
     csync();
     LY_PHASE(4)
 
@@ -1049,15 +1144,16 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
     csync();
     if (a.stop_phase == 2) {
       tc_fence_after();
-      store_h(tl);
+      store_h(a, tl);
       if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
       ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
       if (tid == 0 && more) {
-        load_first();
+        load_first(an);
         mbar_arrive(bar_kvgo);
       }
+      item_fin();
       continue;
     }
     LY_PHASE(5)
@@ -1132,7 +1228,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
 #pragma unroll
       for (int j = 0; j < 80; j += 2) f2_add_to(v + j, sC + LS_TB + cb + j);
       if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
-        const float4* pp = reinterpret_cast<const float4*>(a.pe + (int64_t)(tl.t0 + row) * H + cb);
+        const float4* pp = reinterpret_cast<const float4*>(d.pe + (int64_t)(tl.t0 + row) * H + cb);
 #pragma unroll
         for (int q = 0; q < 20; ++q) {
           const float4 pv = pp[q];
@@ -1145,7 +1241,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       if (a.tail != LT_FINAL && row < tl.nq) {
 #pragma unroll
         for (int q = 0; q < 20; ++q)
-          __stcs(reinterpret_cast<float4*>(a.hc + ((int64_t)(cb / 4 + q) * a.R + tl.row0 + row) * 4),
+          __stcs(reinterpret_cast<float4*>(d.hc + ((int64_t)(cb / 4 + q) * d.R + tl.row0 + row) * 4),
                  make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));    // streaming: read next by another SM's launch
       }
       if (lq == 0) LY_TR(wg, 52)
@@ -1217,7 +1313,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         tc_fence_after();
         ly_issue_gemm(tmem_base + 320, smem_u32(sA), smem_u32(sW1), false);
         umma_commit(bar_g);
-        if (more) load_first();                           // slot 0: first chunk of the next tile
+        if (more) load_first(an);                         // slot 0: first chunk of the next item
       }
       ph_w1 ^= 1;
       LY_PHASE(10)
@@ -1232,10 +1328,10 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           float v[80];
           tmem_ld80(trow + 160 * part + cb, v);
           if (row < tl.nq) {
-            __nv_bfloat16* o = a.qkv_out + ((int64_t)(20 * part + cb / 8) * a.R + tl.row0 + row) * 8;
+            __nv_bfloat16* o = a.qkv_out + ((int64_t)(20 * part + cb / 8) * d.R + tl.row0 + row) * 8;
 #pragma unroll
             for (int g = 0; g < 10; ++g)
-              *reinterpret_cast<uint4*>(o + (int64_t)g * a.R * 8) = part == 2 ? pack_f16x8(v + 8 * g) : pack_bf16x8(v + 8 * g);
+              *reinterpret_cast<uint4*>(o + (int64_t)g * d.R * 8) = part == 2 ? pack_f16x8(v + 8 * g) : pack_bf16x8(v + 8 * g);
           }
         }
       }
@@ -1249,8 +1345,8 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
       }
       ph_w1 ^= 1;
       gemm_wait();
-      if (tid == 0 && more) load_first();
-      const edtts_step_args& sa = a.step;
+      if (tid == 0 && more) load_first(an);
+      const edtts_step_args& sa = p.step;
       float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
       if ((sa.mode == EDTTS_STEP_DDIM || sa.mode == EDTTS_STEP_DDPM) && row < tl.nq) {
         const int64_t tt = sa.t[tl.b];
@@ -1281,7 +1377,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         if (sa.mode == EDTTS_STEP_DDIM) {
 #pragma unroll
           for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
             float4 xp, x0;
             ddim_update(x.x, e[4 * q], 0.f, ab_t, ab_p, 0.f, xp.x, x0.x);
             ddim_update(x.y, e[4 * q + 1], 0.f, ab_t, ab_p, 0.f, xp.y, x0.y);
@@ -1293,7 +1389,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         } else if (sa.mode == EDTTS_STEP_DDPM) {
 #pragma unroll
           for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
             const float4 nz = reinterpret_cast<const float4*>(sa.noise + o)[q];
             float4 xp;
             xp.x = ddpm_update(x.x, e[4 * q], nz.x, al, ab_t, be, pv, nzm);
@@ -1307,7 +1403,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
           const int ord = sa.dpm_order, pm = sa.dpm_predict_x0 ? 1 : 0;
 #pragma unroll
           for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(a.x_t + o)[q];
+            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
             const float4 ha = ord >= 2 ? reinterpret_cast<const float4*>(sa.dpm_hist1 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 hb = ord >= 3 ? reinterpret_cast<const float4*>(sa.dpm_hist2 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
             float4 xp, x0;
@@ -1321,18 +1417,21 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const LayerArgs
         }
       }
     } else {
-      if (tid == 0 && more) load_first();
+      if (tid == 0 && more) load_first(an);
     }
+    // a head item is followed by a block item: its K/V buffers are free
+    if (tid == 0 && a.mode == LM_HEAD && more && an.mode == LM_BLOCK) mbar_arrive(bar_kvgo);
     tc_fence_before();
     csync();
+    item_fin();
     LY_PHASE(13)
   }
-  if (PROF && a.phase_clocks && tid == 0)
+  if (PROF && p.a[0].phase_clocks && tid == 0)
     for (int i = 0; i < 8; ++i) {
-      a.phase_clocks[blockIdx.x * 32 + i] = pc[i];
-      a.phase_clocks[blockIdx.x * 32 + 8 + i] = fcw[i];
-      a.phase_clocks[blockIdx.x * 32 + 16 + i] = fcx[i];
-      a.phase_clocks[blockIdx.x * 32 + 24 + i] = pc[8 + i];
+      p.a[0].phase_clocks[blockIdx.x * 32 + i] = pc[i];
+      p.a[0].phase_clocks[blockIdx.x * 32 + 8 + i] = fcw[i];
+      p.a[0].phase_clocks[blockIdx.x * 32 + 16 + i] = fcx[i];
+      p.a[0].phase_clocks[blockIdx.x * 32 + 24 + i] = pc[8 + i];
     }
 
   csync();

@@ -187,9 +187,9 @@ using namespace tc;
 
 // ---- workspace ------------------------------------------------------------------------------
 struct TcWs {
-  int64_t h, qkv, qkv2, q, o, u, total;
+  int64_t h, qkv, qkv2, q, o, u, flags, total;
 };
-static TcWs tc_ws_layout(int64_t R) {
+static TcWs tc_ws_layout(int64_t R, int64_t flag_bytes = 0) {
   TcWs w;
   int64_t o = 0;
   auto take = [&](int64_t bytes) {
@@ -206,13 +206,14 @@ static TcWs tc_ws_layout(int64_t R) {
   w.q = take(R * H * 2);
   w.o = take(R * H * 2);
   w.u = take(R * FFN * 2);
+  w.flags = take(flag_bytes);          // fused path: per-item completion flags of the merged launch (last: offsets above are fixed)
   w.total = o;
   return w;
 }
 
 int64_t tc_decoder_workspace_bytes(int32_t B, int32_t T, int32_t S) {
   (void)S;
-  return tc_ws_layout((int64_t)B * T).total;
+  return tc_ws_layout((int64_t)B * T, tc::tc_layer_flag_bytes(B, T)).total;
 }
 
 static bool env_flag(const char* name, bool dflt) {
@@ -232,7 +233,7 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
   auto img = [&](int64_t off) { return reinterpret_cast<const __nv_bfloat16*>(pk + off); };
   const int64_t R = (int64_t)B * T;
-  const TcWs wl = tc_ws_layout(R);
+  const TcWs wl = tc_ws_layout(R, tc::tc_layer_flag_bytes(B, T));
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
   float* h = reinterpret_cast<float*>(ws + wl.h);
   __nv_bfloat16* qkv = reinterpret_cast<__nv_bfloat16*>(ws + wl.qkv);
@@ -246,21 +247,12 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
       cudaMemsetAsync(ws + wl.qkv2 + R * 3 * H * 2, 0, ATT_PAD_BYTES, st) != cudaSuccess)
     return check_launch("tc workspace memset");
   if (fused) {
-    // head: h = in_proj(x_t) + pe, q|k|v of block 0; then one launch per block, each also producing the next
-    // block's q|k|v (or, after the last block, final_norm + out_proj + the update rule when `step` is given)
+    // head (h = in_proj(x_t) + pe, q|k|v of block 0) and the blocks, each also producing the next block's q|k|v (or,
+    // after the last block, final_norm + out_proj + the update rule when `step` is given): ONE persistent launch with
+    // per-tile dependencies between the layers (EDTTS_MERGED_LAYERS=0: one launch per layer)
+    static const bool merged = env_flag("EDTTS_MERGED_LAYERS", true);
     void* qb[2] = {qkv, ws + wl.qkv2};
-    if ((rc = launch_tc_layer(w, pk + po.total, -1, n_layers > 0 ? tc::LT_QKV : tc::LT_NONE, h, nullptr, qb[0], nullptr, mod,
-                              x_t, nullptr, B, T, S, 0, st)))
-      return rc;
-    for (int l = 0; l < n_layers; ++l) {
-      const bool last = l == n_layers - 1;
-      const int tail = !last ? tc::LT_QKV : (step && stop_phase == 0 ? tc::LT_FINAL : tc::LT_NONE);
-      const __nv_bfloat16* kvl = reinterpret_cast<const __nv_bfloat16*>(kv) + (int64_t)l * B * S * 2 * H;
-      if ((rc = launch_tc_layer(w, pk + po.total, l, tail, h, qb[l & 1], qb[(l + 1) & 1], kvl, mod, x_t, step, B, T, S,
-                                last ? stop_phase : 0, st)))
-        return rc;
-    }
-    return EDTTS_OK;
+    return launch_tc_layers(w, pk + po.total, n_layers, h, qb, kv, mod, x_t, step, B, T, S, stop_phase, merged, ws + wl.flags, st);
   }
   {  // h = in_proj(x_t) + pe[:T]
     TcGemmArgs g;

@@ -23,10 +23,12 @@ enum LyMode : int { LM_BLOCK = 0, LM_HEAD = 1 };
 enum LyTail : int { LT_NONE = 0, LT_QKV = 1, LT_FINAL = 2 };
 int64_t tc_layer_packed_bytes();
 int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st);
-// one launch of the fused kernel (tc_layer.cuh): head (layer -1) or transformer block, with an optional tail
-int launch_tc_layer(const edtts_decoder_weights* w, const void* layer_img_base, int layer, int tail, float* hc,
-                    const void* qkv_in, void* qkv_out, const void* kvx, const float* mod, const float* x_t,
-                    const edtts_step_args* step, int B, int T, int S, int stop_phase, cudaStream_t st);
+// the head + `n_layers` blocks of a decoder evaluation on the fused kernel (tc_layer.cuh): one merged persistent launch
+// (flags: tc_layer_flag_bytes, zeroed inside) or one launch per layer
+int64_t tc_layer_flag_bytes(int B, int T);
+int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base, int n_layers, float* hc, void* const qb[2],
+                     const void* kv, const float* mod, const float* x_t, const edtts_step_args* step, int B, int T, int S,
+                     int stop_phase, bool merged, void* flags, cudaStream_t st);
 int unpack_hc(const float* hc, float* h, int64_t R, cudaStream_t st);
 // fp32 row-major [R][lda] (first K columns) -> 16-bit chunk-major [K/8][R][8]: bf16, columns >= f16_from_col as f16
 int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K, int f16_from_col, cudaStream_t st);
