@@ -803,9 +803,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
           if (ph == 1 && a.stop_phase == 1) break;
           if (!is_mma) {
             mbar_wait(bar_kvgo, n_phase & 1);
-            if (ph == 0 && p.done) {                      // the window K/V (and halo) rows come from the previous layer's items
+            if (ph == 0 && p.done) {                      // the window K/V (and halo) rows come from the previous layer's items;
+                                                          // the agent's acquire + proxy fence precede the arrive on bar_dep
               mbar_wait(bar_dep + (it & 1), (it >> 1) & 1);
-              fence_proxy_async_all();                    // they were written through the generic proxy, the copies read them through the async proxy
             }
             if (ph == 0) ly_tma_phase<true>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
             else ly_tma_phase<false>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
@@ -826,6 +826,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
           __nanosleep(64);
         }
         fence_acq_rel_gpu();
+        fence_proxy_async_all();                          // the rows were written through the generic proxy; q / k / v are read by bulk copies (async proxy)
         mbar_arrive(bar_dep + slot);
       };
       uint32_t it = 0;
@@ -837,6 +838,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
         for (uint32_t spin = 0; !mbar_try_wait(bar_fin, it & 1); ++spin) {
           if (!acq_done && ly_deps_ready(p.done, gn, ntiles)) {
             fence_acq_rel_gpu();
+            fence_proxy_async_all();
             mbar_arrive(bar_dep + ((it + 1) & 1));
             acq_done = true;
           }
@@ -975,7 +977,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     if (lq == 0) LY_TR(wg, 40)
     if (warp_u == 1) {                                    // converged warp + elected lane: uniform-register addressing
       if (elect_one()) {
-        if (p.done) fence_proxy_async_all();              // q rows: written by another SM through the generic proxy
         mbar_expect_tx(bar_q, 20 * tl.nq * 16);
 #pragma unroll
         for (int c = 0; c < 20; ++c) bulk_g2s(sA + c * LY_SLAB, a.qkv + ((int64_t)c * d.R + tl.row0) * 8, tl.nq * 16, bar_q);

@@ -250,7 +250,7 @@ static int tc_run_layers(const edtts_decoder_weights* w, const float* x_t, const
     // head (h = in_proj(x_t) + pe, q|k|v of block 0) and the blocks, each also producing the next block's q|k|v (or,
     // after the last block, final_norm + out_proj + the update rule when `step` is given): ONE persistent launch with
     // per-tile dependencies between the layers (EDTTS_MERGED_LAYERS=0: one launch per layer)
-    static const bool merged = env_flag("EDTTS_MERGED_LAYERS", true);
+    const bool merged = env_flag("EDTTS_MERGED_LAYERS", true);     // read per call: tests compare both routes in one process
     void* qb[2] = {qkv, ws + wl.qkv2};
     return launch_tc_layers(w, pk + po.total, n_layers, h, qb, kv, mod, x_t, step, B, T, S, stop_phase, merged, ws + wl.flags, st);
   }

@@ -135,6 +135,23 @@ def test_decoder_bf16_vs_oracle(tc, B, S):
     assert rel_l2(eps, ref) <= 1e-2
 
 
+@pytest.mark.parametrize("B,S", [(1, 30), (5, 100), (40, 400), (3, 1500)])
+def test_merged_equals_per_layer_launches(tc, B, S, monkeypatch):
+    """The decoder step as one persistent launch (head + 4 blocks, per-tile dependency flags between the layers; more
+    work items than CTAs at the larger sizes, single-tile utterances at the smallest) gives the bits of one launch per
+    layer: the schedule changes, the arithmetic of a tile does not."""
+    idx = synth.synth_sem_idx(S + 3, B, S).to(DEV)
+    x = synth.synth_noise(S + 3, B, 2 * S).to(DEV)
+    t = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(S)).to(DEV)
+    si = torch.randint(0, 16, (B,), generator=torch.Generator().manual_seed(S + 1)).to(DEV)
+    monkeypatch.setenv("EDTTS_MERGED_LAYERS", "0")
+    ref = tc["dec"](x, t, idx, si).clone()
+    monkeypatch.setenv("EDTTS_MERGED_LAYERS", "1")
+    for _ in range(3):                                     # repeated: the flags are re-armed by every call
+        out = tc["dec"](x, t, idx, si)
+        assert torch.equal(out, ref)
+
+
 def test_decoder_bf16_long_sequence(tc):
     """BASELINE config 5 shape class: T = 3000 frames, 1500 context tokens (24 key blocks per head)."""
     B, S = 1, 1500

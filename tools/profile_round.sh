@@ -12,5 +12,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 echo "launch list rc=$?"
 CMD2="python bench.py --steps 1 --warmup 3 --timed-only --no-graph"
 timeout 300 $CMD2 > $OUT/plain2_${TAG}.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_layer -s 26 -c 1 -o $OUT/prof_${TAG} $CMD2 > $OUT/ncu_full_${TAG}.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc_layer -s 13 -c 1 -o $OUT/prof_${TAG} $CMD2 > $OUT/ncu_full_${TAG}.log 2>&1
 echo "full capture rc=$?"
