@@ -79,6 +79,7 @@ SIGNATURES = {
     "edtts_denormalize_mel": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i32, _p]),
     "edtts_stitch_add": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _i32, _i32, _i64, _i64, _p]),
     "edtts_stitch_finalize": (C.c_int, [_p, _p, _p, _p, _i32, _i32, _i64, _i64, _i32, _i32, _p]),
+    "edtts_inverse_mel": (C.c_int, [_p, _p, _p, _i32, _i32, _i32, _i64, _p]),
     "edtts_fsq_forward": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i64, _p]),
     "edtts_fsq_decode": (C.c_int, [_p, _p, _i32, _p, _i64, _p]),
     "edtts_dsconv_forward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),

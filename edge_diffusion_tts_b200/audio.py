@@ -52,3 +52,40 @@ def denormalize_mel(mel_n: torch.Tensor, mean: torch.Tensor, std: torch.Tensor) 
     _lib.check(_lib.load().edtts_denormalize_mel(_lib.ptr(mel_n), _lib.ptr(mean_b), _lib.ptr(std_b), _lib.ptr(out), B, T, M,
                                                  _lib.stream_ptr(mel_n.device)), "denormalize_mel")
     return out
+
+
+class InverseMelScale(torch.nn.Module):
+    """torchaudio.transforms.InverseMelScale as the reference uses it (generate_sample.py:125-141,
+    inference_pipeline.py:88,395): mel [..., n_mels, time] -> relu(least-squares solution of fb^T X = mel) [..., n_stft, time].
+    Same constructor arguments and ``fb`` buffer; the filter bank comes from torchaudio (library table, built once on the
+    host), its fp64 pseudo-inverse is applied to every frame by one kernel (edtts_inverse_mel).  Parity with torchaudio's
+    ``gels`` solve: rel-L2 <= 1e-5 (the bank has full column rank for the reference's settings; a rank-deficient bank
+    raises, as the solve would be ill-defined)."""
+
+    def __init__(self, n_stft: int, n_mels: int = 128, sample_rate: int = 16000, f_min: float = 0.0, f_max=None,
+                 norm=None, mel_scale: str = "htk", driver: str = "gels"):
+        super().__init__()
+        import torchaudio.functional as AF
+        self.n_mels, self.sample_rate, self.f_min, self.driver = n_mels, sample_rate, f_min, driver
+        self.f_max = f_max or float(sample_rate // 2)
+        if f_min > self.f_max:
+            raise ValueError("Require f_min: {} <= f_max: {}".format(f_min, self.f_max))
+        if driver not in ["gels", "gelsy", "gelsd", "gelss"]:
+            raise ValueError(f'driver must be one of ["gels", "gelsy", "gelsd", "gelss"]. Found {driver}.')
+        fb = AF.melscale_fbanks(n_stft, self.f_min, self.f_max, self.n_mels, self.sample_rate, norm, mel_scale)
+        if int(torch.linalg.matrix_rank(fb.double())) < min(fb.shape):
+            raise ValueError("the mel filter bank is rank deficient: InverseMelScale is ill-defined for these settings")
+        self.register_buffer("fb", fb)                                               # [n_stft, n_mels], as torchaudio
+        self.register_buffer("pinv_fb", torch.linalg.pinv(fb.double().T).float().contiguous())   # [n_stft, n_mels]
+
+    def forward(self, melspec: torch.Tensor) -> torch.Tensor:
+        shape = melspec.size()
+        n_mels, time = shape[-2], shape[-1]
+        if self.n_mels != n_mels:
+            raise ValueError("Expected an input with {} mel bins. Found: {}".format(self.n_mels, n_mels))
+        mel = _lib.f32(melspec).reshape(-1, n_mels, time).contiguous()
+        freq = self.fb.shape[0]
+        out = torch.empty(mel.shape[0], freq, time, dtype=torch.float32, device=mel.device)
+        _lib.check(_lib.load().edtts_inverse_mel(_lib.ptr(self.pinv_fb), _lib.ptr(mel), _lib.ptr(out), mel.shape[0], freq, n_mels,
+                                                 time, _lib.stream_ptr(mel.device)), "inverse_mel")
+        return out.view(shape[:-2] + (freq, time))

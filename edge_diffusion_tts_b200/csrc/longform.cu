@@ -134,6 +134,57 @@ __global__ void __launch_bounds__(256) stitch_finalize_kernel(const float* __res
   }
 }
 
+// ---- InverseMelScale: spec[b, f, t] = relu(sum_m P[f, m] * mel[b, m, t]),  P = pinv(fb^T)  [n_stft, n_mels] ----
+// (torchaudio solves min ||fb^T X - mel|| per frame with lstsq and clamps at 0; for the full-rank filter bank that is the
+// pseudo-inverse applied to every frame: one skinny GEMM, K = n_mels.)  64 x 64 output tile per block, 4 x 4 per thread,
+// both operands staged in shared memory with coalesced row reads; HBM-bound on the [n_stft, T] write.
+constexpr int IM_TF = 64, IM_TT = 64, IM_KC = 16;
+__global__ void __launch_bounds__(256) inverse_mel_kernel(const float* __restrict__ P, const float* __restrict__ mel,
+                                                          float* __restrict__ out, int n_stft, int n_mels, int64_t T) {
+  __shared__ float sP[IM_KC][IM_TF + 1];     // [m][f]
+  __shared__ __align__(16) float sM[IM_KC][IM_TT];         // [m][t]
+  const int b = blockIdx.z, f0 = blockIdx.y * IM_TF;
+  const int64_t t0 = (int64_t)blockIdx.x * IM_TT;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // thread: frames t0 + 4 tx .. +3, bins f0 + 4 ty .. +3
+  const float* melb = mel + (int64_t)b * n_mels * T;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < n_mels; k0 += IM_KC) {
+    for (int i = threadIdx.x; i < IM_KC * IM_TF; i += 256) {   // P[f0 + f][k0 + m]: m fastest in memory
+      const int f = i / IM_KC, m = i % IM_KC;
+      sP[m][f] = (f0 + f < n_stft && k0 + m < n_mels) ? __ldg(P + (int64_t)(f0 + f) * n_mels + k0 + m) : 0.f;
+    }
+    for (int i = threadIdx.x; i < IM_KC * IM_TT; i += 256) {
+      const int m = i / IM_TT, t = i % IM_TT;
+      sM[m][t] = (k0 + m < n_mels && t0 + t < T) ? __ldcs(melb + (int64_t)(k0 + m) * T + t0 + t) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int m = 0; m < IM_KC; ++m) {
+      float pf[4], mt[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pf[i] = sP[m][4 * ty + i];
+      const float4 mv = *reinterpret_cast<const float4*>(&sM[m][4 * tx]);
+      mt[0] = mv.x; mt[1] = mv.y; mt[2] = mv.z; mt[3] = mv.w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(pf[i], mt[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* ob = out + (int64_t)b * n_stft * T;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int f = f0 + 4 * ty + i;
+    if (f >= n_stft) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t t = t0 + 4 * tx + j;
+      if (t < T) __stcs(ob + (int64_t)f * T + t, fmaxf(acc[i][j], 0.f));
+    }
+  }
+}
+
 static inline unsigned stream_grid(int64_t work_items) {
   const int64_t blocks = (work_items + 255) / 256;
   const int64_t cap = 148 * 8;   // 8 resident 256-thread CTAs per SM
@@ -200,4 +251,14 @@ extern "C" int edtts_stitch_finalize(const float* final_mel, const float* final_
   stitch_finalize_kernel<<<stream_grid(n), 256, 0, as_stream(stream)>>>(final_mel, final_weights, mel_out, smooth_out, n_mels,
                                                                         buffer_frames, total_frames, kernel_h, kernel_w, n);
   return check_launch("stitch_finalize");
+}
+
+extern "C" int edtts_inverse_mel(const float* pinv_fb, const float* mel, float* spec_out, int32_t B, int32_t n_stft, int32_t n_mels,
+                                 int64_t T, void* stream) {
+  EDTTS_REQUIRE(pinv_fb && mel && spec_out && B > 0 && B <= 65535 && n_stft > 0 && n_mels > 0 && T > 0, EDTTS_EINVAL,
+                "inverse_mel: B=%d n_stft=%d n_mels=%d T=%lld", B, n_stft, n_mels, (long long)T);
+  LaunchScope ls(KC_MEL, as_stream(stream));
+  inverse_mel_kernel<<<dim3((unsigned)((T + IM_TT - 1) / IM_TT), (n_stft + IM_TF - 1) / IM_TF, B), 256, 0, as_stream(stream)>>>(
+      pinv_fb, mel, spec_out, n_stft, n_mels, T);
+  return check_launch("inverse_mel");
 }

@@ -256,6 +256,13 @@ int edtts_stitch_finalize(const float* final_mel, const float* final_weights, fl
                           int32_t n_mels, int64_t buffer_frames, int64_t total_frames, int32_t kernel_h, int32_t kernel_w,
                           void* stream);
 
+/* InverseMelScale as the reference applies it (generate_sample.py:125-141, inference_pipeline.py:88,395; torchaudio
+ * transforms.InverseMelScale = relu(lstsq(fb^T, mel)), i.e. the pseudo-inverse of the mel filter bank applied to every
+ * frame): spec_out [B, n_stft, T] = relu(pinv_fb [n_stft, n_mels] @ mel [B, n_mels, T]).  pinv_fb is built once by the
+ * caller (host, fp64 pinv of the filter bank). */
+int edtts_inverse_mel(const float* pinv_fb, const float* mel, float* spec_out, int32_t B, int32_t n_stft, int32_t n_mels,
+                      int64_t T, void* stream);
+
 /* --- FSQ (models/fsq.py:18-132), the reference's alternative quantiser ------- */
 /* forward (fsq.py:84-108): z [rows, dim] -> z_q = tanh(z) + (quantise(tanh(z)) - tanh(z)) and the flat index per row
  * (basis = cumprod([1] + levels[:-1]), first dimension fastest).  levels is a HOST array of dim (<= 8) ints.

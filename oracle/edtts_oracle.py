@@ -609,5 +609,15 @@ def longform_generate(sd: State, tab: State, z_q_global: Tensor, plan, chunk_sta
     return stitch(chunks, chunk_stats, chunk_frames, overlap_frames, total_frames) + (chunks,)
 
 
+def inverse_mel_scale(fb: Tensor, melspec: Tensor, driver: str = "gels") -> Tensor:
+    """torchaudio.transforms.InverseMelScale.forward (torchaudio 2.x, the reference's dependency; call sites
+    generate_sample.py:125-141, inference_pipeline.py:88,395): per frame the least-squares solution of fb^T X = mel, clamped at 0.
+    fb [n_stft, n_mels] (torchaudio.functional.melscale_fbanks), melspec [..., n_mels, time] -> [..., n_stft, time]."""
+    shape = melspec.size()
+    mel = melspec.reshape(-1, shape[-2], shape[-1])
+    spec = torch.relu(torch.linalg.lstsq(fb.transpose(-1, -2)[None], mel, driver=driver).solution)
+    return spec.view(shape[:-2] + (fb.shape[0], shape[-1]))
+
+
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}

@@ -114,6 +114,26 @@ def make_longform(ref, meta):
                     smooth=smooth), os.path.join(OUT, "longform.pt"))
 
 
+def invmel_cases():
+    """A linear-mel input (exp of a normalised-mel-like signal) and the filter-bank settings of generate_sample.py:125-132
+    (inference_pipeline.py:88 leaves f_min / f_max at their defaults, 0 and sample_rate // 2 = 8000: the same bank)."""
+    g = torch.Generator().manual_seed(91)
+    mel = torch.exp(torch.randn(1, 80, 21, generator=g) * 1.5 - 4.0)
+    return mel, dict(generate_sample=dict(n_stft=513, n_mels=80, sample_rate=16000, f_min=0.0, f_max=8000.0, norm=None))
+
+
+def make_invmel(ref, meta):
+    """torchaudio.transforms.InverseMelScale exactly as generate_sample.py:125-132 / inference_pipeline.py:88 construct it."""
+    import torchaudio
+    import torchaudio.transforms as T
+    mel, settings = invmel_cases()
+    out = {}
+    for name, kw in settings.items():
+        m = T.InverseMelScale(**kw)
+        out[name] = dict(fb=m.fb.clone(), spec=m(mel))
+    torch.save(dict(meta=dict(meta, torchaudio=torchaudio.__version__), cases=out), os.path.join(OUT, "invmel.pt"))
+
+
 def main(only=None):
     torch.manual_seed(0)
     torch.set_num_threads(1)          # fixed summation order for the recorded outputs
@@ -133,6 +153,9 @@ def main(only=None):
         return
     if only == "longform":
         make_longform(ref, meta)
+        return
+    if only == "invmel":
+        make_invmel(ref, meta)
         return
 
     # --- decoder.forward, one step, mixed t / step_idx, with per-layer hidden rows
@@ -238,6 +261,7 @@ def main(only=None):
     make_fsq(ref, meta)
     make_inpaint(ref, meta)
     make_longform(ref, meta)
+    make_invmel(ref, meta)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -9,7 +9,7 @@ import torch
 
 from oracle import edtts_oracle as O
 from oracle import synth
-from oracle.make_golden import longform_cases
+from oracle.make_golden import invmel_cases, longform_cases
 
 DEV = "cuda:0"
 
@@ -159,3 +159,38 @@ def test_generate_longform_vs_oracle(lib, precision, tol):
                                       noises=[(d(a), d(b), [d(k) for k in c]) for a, b, c in noises])
     assert mel.shape == (80, total) and smooth.shape == (1, 80, total)
     assert rel_l2(mel, ref_mel) <= tol and rel_l2(smooth, ref_smooth) <= tol
+
+
+def test_inverse_mel_oracle_vs_torchaudio_fixture(golden):
+    g = golden("invmel")
+    mel, settings = invmel_cases()
+    for name in settings:
+        c = g["cases"][name]
+        assert rel_l2(O.inverse_mel_scale(c["fb"], mel), c["spec"]) <= 1e-6, name     # LAPACK blocking may differ with the thread count
+
+
+@pytest.mark.gpu
+def test_inverse_mel_scale(golden, lib):
+    """relu(pinv(fb^T) mel) against torchaudio's per-frame least-squares solve (fixture recorded with torchaudio itself):
+    rel-L2 <= 1e-5, same support of the clamp up to values below 1e-5 of the peak."""
+    import edge_diffusion_tts_b200 as E
+    g = golden("invmel")
+    mel, settings = invmel_cases()
+    for name, kw in settings.items():
+        c = g["cases"][name]
+        m = E.InverseMelScale(**kw).to(DEV)
+        assert torch.equal(m.fb.cpu(), c["fb"])
+        out = m(mel.to(DEV))
+        assert out.shape == c["spec"].shape and (out >= 0).all()
+        assert rel_l2(out, c["spec"]) <= 1e-5, name
+        assert (out.cpu() - c["spec"]).abs().max().item() <= 1e-5 * c["spec"].abs().max().item(), name
+    # ragged: one frame, frames not a multiple of the tile, leading batch dimensions as torchaudio accepts them
+    m = E.InverseMelScale(n_stft=513, n_mels=80, sample_rate=16000).to(DEV)
+    fb = g["cases"]["generate_sample"]["fb"]                # inference_pipeline.py:88: same bank (f_max defaults to 8000)
+    for shape in ((80, 1), (3, 2, 80, 131)):
+        x = torch.rand(*shape, generator=torch.Generator().manual_seed(5)) + 0.01
+        out = m(x.to(DEV))
+        assert out.shape == shape[:-2] + (513, shape[-1])
+        assert rel_l2(out, O.inverse_mel_scale(fb, x)) <= 1e-5
+    with pytest.raises(ValueError):
+        m(torch.rand(1, 64, 10, device=DEV))
