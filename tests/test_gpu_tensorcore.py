@@ -135,7 +135,9 @@ def test_decoder_bf16_vs_oracle(tc, B, S):
     assert rel_l2(eps, ref) <= 1e-2
 
 
-@pytest.mark.parametrize("B,S", [(1, 30), (5, 100), (40, 400), (3, 1500)])
+# (21, 400) / (37, 256) / (149, 64): 147 / 148 / 149 tiles per layer on 148 CTAs -- the sizes at which an item, its successor on
+# the same CTA and their predecessors on the neighbouring CTAs form the tightest dependency pattern
+@pytest.mark.parametrize("B,S", [(1, 30), (5, 100), (40, 400), (3, 1500), (21, 400), (37, 256), (149, 64)])
 def test_merged_equals_per_layer_launches(tc, B, S, monkeypatch):
     """The decoder step as one persistent launch (head + 4 blocks, per-tile dependency flags between the layers; more
     work items than CTAs at the larger sizes, single-tile utterances at the smallest) gives the bits of one launch per
