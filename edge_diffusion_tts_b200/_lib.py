@@ -36,7 +36,7 @@ class DecoderWeights(C.Structure):
         "in_proj_w", "in_proj_b", "pos_pe", "ctx_pe", "time_freqs", "final_norm_w", "final_norm_b", "out_proj_w",
         "out_proj_b")] + [("layers", LayerWeights * N_LAYERS), ("codebook_size", C.c_int32),
                           ("pos_rows", C.c_int32), ("ctx_rows", C.c_int32), ("reserved", C.c_int32),
-                          ("packed_bf16", _f)]
+                          ("packed_bf16", _f), ("pos_pe_cm", _f)]
 
 
 class StepArgs(C.Structure):

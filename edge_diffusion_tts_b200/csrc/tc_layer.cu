@@ -106,6 +106,8 @@ static int fill_layer_args(LayerArgs& a, const edtts_decoder_weights* w, const v
     a.w_in = reinterpret_cast<const __nv_bfloat16*>(ex + LY_EX_IN);
     a.in_b = w->in_proj_b;
     a.pe = w->pos_pe;
+    a.pe_cm = w->pos_pe_cm;
+    a.pe_rows = w->pos_rows;
   }
   if (tail == LT_QKV) {
     const int nl = layer + 1;

@@ -114,6 +114,8 @@ struct LayerArgs {
   const __nv_bfloat16* w_in;         // in_proj.weight as [10][160][8]
   const float* in_b;                 // [160]
   const float* pe;                   // pos_emb.pe [>= T][160]
+  const float* pe_cm;                // the same table chunk-major [40][pe_rows][4] (coalesced thread-per-row reads), or null
+  int pe_rows;
   // LT_QKV
   const __nv_bfloat16* w_qkv;        // 3 chunks (q, k, v) of the next block's attn.qkv.weight
   const float* n1w;                  // next block's norm1.norm.weight [160]
@@ -950,14 +952,20 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     if (a.mode == LM_HEAD) {
       // ---- h = in_proj(x_t): x tile -> bf16 A operand (K = 80), one MMA chain into the h columns -----------------------
       {
-        const float4* src = reinterpret_cast<const float4*>(d.x_t + (tl.row0 + row) * M + 40 * wg);
+        // 128 rows x 10 groups of 8 columns, consecutive threads on consecutive 32-byte pieces of the (contiguous) tile
         float4 x[10];
 #pragma unroll
-        for (int q = 0; q < 10; ++q) x[q] = row < tl.nq ? src[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 5; ++i) {
+          const int e = i * LY_CTHREADS + tid, r = e / 10, g = e - r * 10;
+          const float4* src = reinterpret_cast<const float4*>(d.x_t + (tl.row0 + r) * M + 8 * g);
+          x[2 * i] = r < tl.nq ? src[0] : make_float4(0.f, 0.f, 0.f, 0.f);      // plain loads: x_prev of the same launch may alias x_t
+          x[2 * i + 1] = r < tl.nq ? src[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 #pragma unroll
-        for (int g = 0; g < 5; ++g) {
-          const float o[8] = {x[2 * g].x, x[2 * g].y, x[2 * g].z, x[2 * g].w, x[2 * g + 1].x, x[2 * g + 1].y, x[2 * g + 1].z, x[2 * g + 1].w};
-          *reinterpret_cast<uint4*>(sA + (5 * wg + g) * LY_SLAB + row * 16) = pack_bf16x8(o);
+        for (int i = 0; i < 5; ++i) {
+          const int e = i * LY_CTHREADS + tid, r = e / 10, g = e - r * 10;
+          const float o[8] = {x[2 * i].x, x[2 * i].y, x[2 * i].z, x[2 * i].w, x[2 * i + 1].x, x[2 * i + 1].y, x[2 * i + 1].z, x[2 * i + 1].w};
+          *reinterpret_cast<uint4*>(sA + g * LY_SLAB + r * 16) = pack_bf16x8(o);
         }
       }
       fence_proxy_async();
@@ -1229,12 +1237,22 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
 #pragma unroll
       for (int j = 0; j < 80; j += 2) f2_add_to(v + j, sC + LS_TB + cb + j);
       if (a.mode == LM_HEAD && row < tl.nq) {             // + pos_emb.pe[t]
-        const float4* pp = reinterpret_cast<const float4*>(d.pe + (int64_t)(tl.t0 + row) * H + cb);
+        if (d.pe_cm) {                                    // chunk-major table: consecutive rows are 16 bytes apart
+          const float* pp = d.pe_cm + ((int64_t)(cb / 4) * d.pe_rows + tl.t0 + row) * 4;
 #pragma unroll
-        for (int q = 0; q < 20; ++q) {
-          const float4 pv = pp[q];
-          f2_add_to(v + 4 * q, &pv.x);
-          f2_add_to(v + 4 * q + 2, &pv.z);
+          for (int q = 0; q < 20; ++q) {
+            const float4 pv = __ldg(reinterpret_cast<const float4*>(pp + (int64_t)q * d.pe_rows * 4));
+            f2_add_to(v + 4 * q, &pv.x);
+            f2_add_to(v + 4 * q + 2, &pv.z);
+          }
+        } else {
+          const float4* pp = reinterpret_cast<const float4*>(d.pe + (int64_t)(tl.t0 + row) * H + cb);
+#pragma unroll
+          for (int q = 0; q < 20; ++q) {
+            const float4 pv = pp[q];
+            f2_add_to(v + 4 * q, &pv.x);
+            f2_add_to(v + 4 * q + 2, &pv.z);
+          }
         }
       }
       // h -> HBM: 20 x 16 bytes per thread (the LSU queue makes this ~3 k cycles per tile; interleaving the stores with the
@@ -1348,8 +1366,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
       gemm_wait();
       if (tid == 0 && more) load_first(an);
       const edtts_step_args& sa = p.step;
+      // Per-utterance coefficients: the same for every row of the tile (all threads load them, the loads broadcast).
       float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
-      if ((sa.mode == EDTTS_STEP_DDIM || sa.mode == EDTTS_STEP_DDPM) && row < tl.nq) {
+      if (sa.mode == EDTTS_STEP_DDIM || sa.mode == EDTTS_STEP_DDPM) {
         const int64_t tt = sa.t[tl.b];
         ab_t = sa.alpha_bar[tt];
         if (sa.mode == EDTTS_STEP_DDIM) {
@@ -1362,61 +1381,69 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
           nzm = tt > 0 ? 1.0f : 0.0f;
         }
       }
-      const int c0 = 40 * wg;                             // this thread's 40 of the 80 mel columns
-      float e[40];
-      tmem_ld32(trow + c0, e);
-      tmem_ld8(trow + c0 + 32, e + 32);
-      if (row < tl.nq) {
-        const int64_t o = (tl.row0 + row) * M + c0;
+      // eps (+ bias) of this thread's row goes through shared memory (sA: the out_proj A operand is dead once the MMA
+      // retired), so that the update below walks x_t / x_prev / x0 -- row-major [R][80] fp32 -- with consecutive threads on
+      // consecutive 16-byte pieces: 4 LSU wavefronts per warp request instead of the 32 of a thread-per-row walk (each
+      // lane in its own 320-byte row), which made this phase the slowest per byte of the whole item.
+      // The tile takes slabs 0..19 of sA exactly (128 x 80 x 4 B): slab 20 is head 3's zero padding of the S = Q K^T
+      // operand and must stay zero.  The 16-byte pieces of a row are rotated by row / 2 so that the thread-per-row
+      // stores of a warp spread over all banks (row stride 80 words = 16 mod 32).
+      constexpr int FE_LD = 80;
+      static_assert(128 * FE_LD * 4 <= 20 * LY_SLAB, "staged eps tile must not reach the padding slab of sA");
+      float* sE = reinterpret_cast<float*>(sA);
+      {
+        const int c0 = 40 * wg;                           // this thread's 40 of the 80 mel columns
+        float e[40];
+        tmem_ld32(trow + c0, e);
+        tmem_ld8(trow + c0 + 32, e + 32);
 #pragma unroll
-        for (int j = 0; j < 40; ++j) e[j] += sC[LS_OB + c0 + j];
-        if (sa.eps_out) {
-#pragma unroll
-          for (int q = 0; q < 10; ++q)
-            reinterpret_cast<float4*>(sa.eps_out + o)[q] = make_float4(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3]);
-        }
+        for (int q = 0; q < 10; ++q)
+          *reinterpret_cast<float4*>(sE + row * FE_LD + 4 * ((10 * wg + q + (row >> 1)) % 20)) =
+              make_float4(e[4 * q] + sC[LS_OB + c0 + 4 * q], e[4 * q + 1] + sC[LS_OB + c0 + 4 * q + 1],
+                          e[4 * q + 2] + sC[LS_OB + c0 + 4 * q + 2], e[4 * q + 3] + sC[LS_OB + c0 + 4 * q + 3]);
+      }
+      csync();
+      const float* dc = sa.mode == EDTTS_STEP_DPM ? sa.dpm_coef + tl.b * 8 : nullptr;
+      const int ord = sa.dpm_order, pm = sa.dpm_predict_x0 ? 1 : 0;
+#pragma unroll 2
+      for (int i = 0; i < 10; ++i) {                      // 128 rows x 20 float4 = 10 per thread
+        const int idx = i * LY_CTHREADS + tid, r = idx / 20, q = idx - r * 20;
+        if (r >= tl.nq) break;                            // idx grows with i: no later piece of this thread is valid either
+        const float4 e4 = *reinterpret_cast<const float4*>(sE + r * FE_LD + 4 * ((q + (r >> 1)) % 20));
+        const int64_t o = (tl.row0 + r) * M + 4 * q;
+        if (sa.eps_out) *reinterpret_cast<float4*>(sa.eps_out + o) = e4;
         if (sa.mode == EDTTS_STEP_DDIM) {
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
-            float4 xp, x0;
-            ddim_update(x.x, e[4 * q], 0.f, ab_t, ab_p, 0.f, xp.x, x0.x);
-            ddim_update(x.y, e[4 * q + 1], 0.f, ab_t, ab_p, 0.f, xp.y, x0.y);
-            ddim_update(x.z, e[4 * q + 2], 0.f, ab_t, ab_p, 0.f, xp.z, x0.z);
-            ddim_update(x.w, e[4 * q + 3], 0.f, ab_t, ab_p, 0.f, xp.w, x0.w);
-            if (sa.x0_out) __stcs(reinterpret_cast<float4*>(sa.x0_out + o) + q, x0);      // streaming: read back by the host / next history step only
-            if (sa.write_x_prev && sa.x_prev_out) reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
-          }
+          const float4 x = *reinterpret_cast<const float4*>(d.x_t + o);
+          float4 xp, x0;
+          ddim_update(x.x, e4.x, 0.f, ab_t, ab_p, 0.f, xp.x, x0.x);
+          ddim_update(x.y, e4.y, 0.f, ab_t, ab_p, 0.f, xp.y, x0.y);
+          ddim_update(x.z, e4.z, 0.f, ab_t, ab_p, 0.f, xp.z, x0.z);
+          ddim_update(x.w, e4.w, 0.f, ab_t, ab_p, 0.f, xp.w, x0.w);
+          if (sa.x0_out) __stcs(reinterpret_cast<float4*>(sa.x0_out + o), x0);      // streaming: read back by the host / next history step only
+          if (sa.write_x_prev && sa.x_prev_out) *reinterpret_cast<float4*>(sa.x_prev_out + o) = xp;
         } else if (sa.mode == EDTTS_STEP_DDPM) {
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
-            const float4 nz = reinterpret_cast<const float4*>(sa.noise + o)[q];
-            float4 xp;
-            xp.x = ddpm_update(x.x, e[4 * q], nz.x, al, ab_t, be, pv, nzm);
-            xp.y = ddpm_update(x.y, e[4 * q + 1], nz.y, al, ab_t, be, pv, nzm);
-            xp.z = ddpm_update(x.z, e[4 * q + 2], nz.z, al, ab_t, be, pv, nzm);
-            xp.w = ddpm_update(x.w, e[4 * q + 3], nz.w, al, ab_t, be, pv, nzm);
-            reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
-          }
+          const float4 x = *reinterpret_cast<const float4*>(d.x_t + o);
+          const float4 nz = *reinterpret_cast<const float4*>(sa.noise + o);
+          float4 xp;
+          xp.x = ddpm_update(x.x, e4.x, nz.x, al, ab_t, be, pv, nzm);
+          xp.y = ddpm_update(x.y, e4.y, nz.y, al, ab_t, be, pv, nzm);
+          xp.z = ddpm_update(x.z, e4.z, nz.z, al, ab_t, be, pv, nzm);
+          xp.w = ddpm_update(x.w, e4.w, nz.w, al, ab_t, be, pv, nzm);
+          *reinterpret_cast<float4*>(sa.x_prev_out + o) = xp;
         } else if (sa.mode == EDTTS_STEP_DPM) {
-          const float* dc = sa.dpm_coef + tl.b * 8;
-          const int ord = sa.dpm_order, pm = sa.dpm_predict_x0 ? 1 : 0;
-#pragma unroll
-          for (int q = 0; q < 10; ++q) {
-            const float4 x = reinterpret_cast<const float4*>(d.x_t + o)[q];
-            const float4 ha = ord >= 2 ? reinterpret_cast<const float4*>(sa.dpm_hist1 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 hb = ord >= 3 ? reinterpret_cast<const float4*>(sa.dpm_hist2 + o)[q] : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4 xp, x0;
-            dpm_update(x.x, e[4 * q], ha.x, hb.x, dc, ord, pm, xp.x, x0.x);
-            dpm_update(x.y, e[4 * q + 1], ha.y, hb.y, dc, ord, pm, xp.y, x0.y);
-            dpm_update(x.z, e[4 * q + 2], ha.z, hb.z, dc, ord, pm, xp.z, x0.z);
-            dpm_update(x.w, e[4 * q + 3], ha.w, hb.w, dc, ord, pm, xp.w, x0.w);
-            if (sa.x0_out) reinterpret_cast<float4*>(sa.x0_out + o)[q] = x0;
-            reinterpret_cast<float4*>(sa.x_prev_out + o)[q] = xp;
-          }
+          const float4 x = *reinterpret_cast<const float4*>(d.x_t + o);
+          const float4 ha = ord >= 2 ? *reinterpret_cast<const float4*>(sa.dpm_hist1 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 hb = ord >= 3 ? *reinterpret_cast<const float4*>(sa.dpm_hist2 + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 xp, x0;
+          dpm_update(x.x, e4.x, ha.x, hb.x, dc, ord, pm, xp.x, x0.x);
+          dpm_update(x.y, e4.y, ha.y, hb.y, dc, ord, pm, xp.y, x0.y);
+          dpm_update(x.z, e4.z, ha.z, hb.z, dc, ord, pm, xp.z, x0.z);
+          dpm_update(x.w, e4.w, ha.w, hb.w, dc, ord, pm, xp.w, x0.w);
+          if (sa.x0_out) *reinterpret_cast<float4*>(sa.x0_out + o) = x0;
+          *reinterpret_cast<float4*>(sa.x_prev_out + o) = xp;
         }
       }
+      fence_proxy_async();                                // sA is written next by the following item's bulk copies
     } else {
       if (tid == 0 && more) load_first(an);
     }

@@ -170,7 +170,10 @@ class EdgeDiffusionDecoder(nn.Module):
         w.codebook_size = self.token_emb.weight.shape[0]
         w.pos_rows, w.ctx_rows = pos.shape[0], ctx.shape[0]
         w.packed_bf16 = None
+        w.pos_pe_cm = None
         if self.precision == "bf16":
+            # the positional table once more, chunk-major [40][rows][4]: a row-per-thread walk of it is then coalesced
+            w.pos_pe_cm = P(pos.detach().view(pos.shape[0], pos.shape[1] // 4, 4).permute(1, 0, 2))
             lib = _lib.load()
             packed = torch.empty(max(int(lib.edtts_packed_bf16_bytes()), 16), dtype=torch.uint8, device=dev)
             _lib.check(lib.edtts_pack_weights_bf16(w, _lib.ptr(packed), _lib.stream_ptr(dev)), "pack_weights_bf16")

@@ -110,6 +110,8 @@ typedef struct edtts_decoder_weights {
   int32_t ctx_rows;
   int32_t reserved;
   const void* packed_bf16;     /* image written by edtts_pack_weights_bf16 (or NULL)  */
+  const float* pos_pe_cm;      /* optional: pos_emb.pe chunk-major [40][pos_rows][4] (pe_cm[c][t][j] = pe[t][4c+j]); the fused bf16
+                                * kernel then reads the table with coalesced loads.  NULL: it reads pos_pe row-major.         */
 } edtts_decoder_weights;
 
 /* --- library ------------------------------------------------------------- */

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layout_matches_header():
     from edge_diffusion_tts_b200 import _lib
     assert ctypes.sizeof(_lib.LayerWeights) == 19 * 8
-    assert ctypes.sizeof(_lib.DecoderWeights) == 17 * 8 + 4 * 19 * 8 + 16 + 8
+    assert ctypes.sizeof(_lib.DecoderWeights) == 17 * 8 + 4 * 19 * 8 + 16 + 8 + 8      # ... packed_bf16, pos_pe_cm
     assert ctypes.sizeof(_lib.StepArgs) == 8 + 10 * 8 + 3 * 8 + 8
 
 
