@@ -156,11 +156,13 @@ class EdgeInference:
         decoder's ``sem_features`` conditioning (step_idx 0); before every step the first ``overlap_len`` frames are replaced
         by a freshly noised copy of ``known_mel`` (the previous chunk's tail) and after the loop by ``known_mel`` itself;
         ``cfg_scale != 1`` adds classifier-free guidance against zero conditioning.  ``noise`` / ``known_noises[i]``
-        optionally inject the N(0,1) draws (the reference calls randn_like).  Context K/V (conditional and null) are
-        prepared once; the injection and the update are one streaming kernel each (edtts_inpaint_inject, edtts_vddim_step)."""
-        dec, sch, cfg = self.decoder, self.schedule, self.cfg
+        optionally inject the N(0,1) draws (the reference calls randn_like).  Context K/V (conditional and null) and the
+        conditioning of all steps are prepared once; the injection and the update are one streaming kernel each
+        (edtts_inpaint_inject, edtts_vddim_step); the whole loop runs on static buffers and is replayed from a CUDA graph per
+        shape (``use_cuda_graph``): the long-form pipeline calls it once per chunk with the same shapes, batch 1, where the
+        launches -- not the arithmetic -- are the cost."""
+        dec, cfg = self.decoder, self.cfg
         dec.eval()
-        lib = _lib.load()
         x_coarse = _lib.f32(x_coarse)
         dev = x_coarse.device
         B, T, D = x_coarse.shape
@@ -168,9 +170,62 @@ class EdgeInference:
         t_start = int(cfg.diff_steps * strength)
         if not 0 <= t_start < cfg.diff_steps:
             raise IndexError(f"t_start={t_start} is outside the {cfg.diff_steps}-entry schedule tables")   # as tensor indexing would
+        L = overlap_len if known_mel is not None else 0
+        if known_mel is not None:
+            known_mel = _lib.f32(known_mel)
+            if tuple(known_mel.shape) != (B, overlap_len, D):
+                raise ValueError(f"known_mel must be [B, overlap_len, n_mels] = {(B, overlap_len, D)}, got {tuple(known_mel.shape)}")
+        p = self._plan_inpaint(B, T, S, sem_features.shape[2], L, steps, t_start, cfg_scale != 1.0, dev)
+        n = len(p.t)
+        # the reference's draws, in its order: randn_like(x_coarse) before the loop, randn_like(known_mel) in every iteration
+        p.x_in.copy_(x_coarse)
+        p.noise.copy_(noise if noise is not None else torch.randn_like(x_coarse))
+        p.sem.copy_(_lib.f32(sem_features))
+        if L > 0:
+            p.known.copy_(known_mel)
+            for i in range(n):
+                p.known_noise[i].copy_(known_noises[i] if known_noises is not None else torch.randn_like(known_mel))
+        p.cfg_scale = float(cfg_scale)
+        if not self.use_cuda_graph:
+            self._run_inpaint(p)
+        else:
+            key = (dec.weights_epoch, p.cfg_scale)                       # the guidance scale is baked into the captured launch
+            if p.graph is None or p.epoch != key:
+                self._run_inpaint(p)                                     # warm-up: builds weight views
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._run_inpaint(p)
+                p.graph, p.epoch = g, key
+            p.graph.replay()
+        return p.x.clone()
+
+    def _plan_inpaint(self, B: int, T: int, S: int, Dsem: int, L: int, steps: int, t_start: int, guided: bool, device) -> _Plan:
+        """Static buffers of one refine-loop shape (so the loop can be replayed from a CUDA graph): inputs, the per-step
+        coefficient rows built with the reference's tensor expressions, conditioning of all steps, plan-private scratch."""
+        key = ("inpaint", B, T, S, Dsem, L, steps, t_start, guided, self.decoder.precision, str(device))
+        p = self._plans.get(key)
+        if p is not None:
+            return p
+        cfg, sch = self.cfg, self.schedule
+        p = _Plan()
+        f = dict(dtype=torch.float32, device=device)
+        p.x_in, p.noise, p.x = (torch.empty(B, T, cfg.n_mels, **f) for _ in range(3))
+        p.v_c = torch.empty_like(p.x)
+        p.v_u = torch.empty_like(p.x) if guided else None
+        p.sem = torch.empty(B, S, Dsem, **f)
+        p.sem0 = torch.zeros_like(p.sem) if guided else None
+        p.known = torch.empty(B, max(L, 1), cfg.n_mels, **f)
+        p.known_noise = torch.empty(max(steps, 1), B, max(L, 1), cfg.n_mels, **f)
+        p.L = L
+        p.kv = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, **f)
+        p.kv0 = torch.empty_like(p.kv) if guided else None
+        nb_ctx, nb_step = self.decoder.workspace_bytes(B, T, S)
+        p.ws_ctx = torch.empty(max(nb_ctx, 256), dtype=torch.uint8, device=device)
+        p.ws_step = torch.empty(max(nb_step, 256), dtype=torch.uint8, device=device)
         tab = {k: getattr(sch, k).detach().cpu() for k in ("alpha_bar", "sqrt_alpha_bar", "sqrt_one_minus_alpha_bar")}
         times = torch.linspace(t_start, 0, steps + 1).long()[:-1]                     # inference_pipeline.py:164-165
-        coefs, t_dev = [], []
+        p.coefs = []
         for i in range(len(times)):
             t_next = times[i + 1] if i < len(times) - 1 else torch.tensor(0)
             tt = torch.full((B,), int(times[i]), dtype=torch.long)
@@ -180,47 +235,50 @@ class EdgeInference:
             co[:, 1] = tab["sqrt_one_minus_alpha_bar"][tt]
             co[:, 2] = torch.sqrt(a_next)
             co[:, 3] = torch.sqrt(1 - a_next)
-            coefs.append(co.to(dev))
-            t_dev.append(tt.to(dev))
-        st = _lib.stream_ptr(dev)
-        # q_sample of the coarse input at t_start (inference_pipeline.py:160-162): the injection kernel over all T frames
-        if noise is None:
-            noise = torch.randn_like(x_coarse)
-        ts = torch.full((B,), t_start, dtype=torch.long)
+            p.coefs.append(co.to(device))
+            p.t.append(tt.to(device))
+        ts = torch.full((B,), t_start, dtype=torch.long)                              # q_sample at t_start, :160-162
         co0 = torch.zeros(B, 4, dtype=torch.float32)
         co0[:, 0], co0[:, 1] = tab["sqrt_alpha_bar"][ts], tab["sqrt_one_minus_alpha_bar"][ts]
-        co0 = co0.to(dev)
-        x = torch.empty_like(x_coarse)
-        _lib.check(lib.edtts_inpaint_inject(_lib.ptr(x), _lib.ptr(x_coarse), _lib.ptr(_lib.f32(noise)), _lib.ptr(co0), B, T, T, D,
-                                            st), "inpaint_inject")
-        sem_features = _lib.f32(sem_features)
-        kv = dec.prepare_context(None, sem_features, T)
-        kv0 = dec.prepare_context(None, torch.zeros_like(sem_features), T) if cfg_scale != 1.0 else None
-        s_idx = torch.zeros(B, dtype=torch.long, device=dev)
-        if known_mel is not None:
-            known_mel = _lib.f32(known_mel)
-            if tuple(known_mel.shape) != (B, overlap_len, D):
-                raise ValueError(f"known_mel must be [B, overlap_len, n_mels] = {(B, overlap_len, D)}, got {tuple(known_mel.shape)}")
-        v_c = torch.empty_like(x)
-        v_u = torch.empty_like(x) if kv0 is not None else None
-        for i in range(len(times)):
-            if known_mel is not None and overlap_len > 0:
-                nk = known_noises[i] if known_noises is not None else torch.randn_like(known_mel)
-                _lib.check(lib.edtts_inpaint_inject(_lib.ptr(x), _lib.ptr(known_mel), _lib.ptr(_lib.f32(nk)), _lib.ptr(coefs[i]), B,
-                                                    T, overlap_len, D, st), "inpaint_inject")
-            mod = dec.prepare_cond(t_dev[i], s_idx, T, S)
-            for kvx, out in ((kv, v_c), (kv0, v_u)):
+        p.co0 = co0.to(device)
+        n = len(p.t)
+        p.t_all = torch.cat(p.t) if n else torch.zeros(0, dtype=torch.long, device=device)
+        p.step_all = torch.zeros(n * B, dtype=torch.long, device=device)             # s_idx = 0 in every step (:167)
+        p.mod_all = torch.empty(max(n, 1) * B, 2 * cfg.layers, 2 * cfg.hidden, **f)
+        p.mods = [p.mod_all[i * B:(i + 1) * B] for i in range(n)]
+        self._plans[key] = p
+        return p
+
+    def _run_inpaint(self, p: _Plan):
+        """Every launch of the refine loop on the plan's buffers (eager or under graph capture)."""
+        dec = self.decoder
+        lib = _lib.load()
+        B, T, D = p.x.shape
+        S, L, n = p.sem.shape[1], p.L, len(p.t)
+        st = _lib.stream_ptr(p.x.device)
+        # q_sample of the coarse input at t_start: the injection kernel over all T frames
+        _lib.check(lib.edtts_inpaint_inject(_lib.ptr(p.x), _lib.ptr(p.x_in), _lib.ptr(p.noise), _lib.ptr(p.co0), B, T, T, D, st),
+                   "inpaint_inject")
+        dec.prepare_context(None, p.sem, T, out=p.kv, ws=p.ws_ctx)
+        if p.kv0 is not None:
+            dec.prepare_context(None, p.sem0, T, out=p.kv0, ws=p.ws_ctx)
+        if n:
+            dec.prepare_cond(p.t_all, p.step_all, T, S, out=p.mod_all)               # conditioning of all steps in one launch
+        for i in range(n):
+            if L > 0:
+                _lib.check(lib.edtts_inpaint_inject(_lib.ptr(p.x), _lib.ptr(p.known), _lib.ptr(p.known_noise[i]),
+                                                    _lib.ptr(p.coefs[i]), B, T, L, D, st), "inpaint_inject")
+            for kvx, out in ((p.kv, p.v_c), (p.kv0, p.v_u)):
                 if kvx is None:
                     continue
                 a = _lib.StepArgs()
                 a.mode = _lib.STEP_EPS
                 a.eps_out = out.data_ptr()
-                dec.step(x, mod, kvx, S, a)
-            _lib.check(lib.edtts_vddim_step(_lib.ptr(x), _lib.ptr(v_c), _lib.ptr(v_u) if v_u is not None else None,
-                                            float(cfg_scale), _lib.ptr(coefs[i]), _lib.ptr(x), None, B, T * D, st), "vddim_step")
-        if known_mel is not None and overlap_len > 0:
-            x[:, :overlap_len, :] = known_mel                                          # inference_pipeline.py:193-194
-        return x
+                dec.step(p.x, p.mods[i], kvx, S, a, ws=p.ws_step)
+            _lib.check(lib.edtts_vddim_step(_lib.ptr(p.x), _lib.ptr(p.v_c), _lib.ptr(p.v_u) if p.v_u is not None else None,
+                                            p.cfg_scale, _lib.ptr(p.coefs[i]), _lib.ptr(p.x), None, B, T * D, st), "vddim_step")
+        if L > 0:
+            p.x[:, :L, :].copy_(p.known)                                              # inference_pipeline.py:193-194
 
     # ------------------------------------------------------------------ DDPM, long loop
     @torch.no_grad()

@@ -109,3 +109,24 @@ def test_inpaint_refine_errors_and_rng(gpu):
     torch.manual_seed(0)
     b = inf.inpaint_refine(x, f, strength=0.3, steps=3)
     assert torch.equal(a, b) and a.shape == x.shape and torch.isfinite(a).all()
+
+
+@pytest.mark.gpu
+def test_inpaint_refine_graph_equals_eager(gpu):
+    """The refine loop replayed from a CUDA graph (static buffers per shape, re-used across the chunks of a long utterance)
+    gives the bits of the eager launches, also when the same plan is replayed with new inputs and a new guidance scale."""
+    inf = gpu["inf"]
+    feats, xc, known, noises, _ = inpaint_cases()
+    d = lambda t: t.to(DEV)
+    for scale in (1.0, 1.7, 1.3):
+        for shift in (0.0, 0.25):
+            args = (d(xc) + shift, d(feats), d(known), 8, 0.5, 5, scale)
+            kw = dict(noise=d(noises[0]), known_noises=[d(n) for n in noises[1:]])
+            inf.use_cuda_graph = True
+            a = inf.inpaint_refine(*args, **kw)
+            inf.use_cuda_graph = False
+            try:
+                b = inf.inpaint_refine(*args, **kw)
+            finally:
+                inf.use_cuda_graph = True
+            assert torch.equal(a, b), (scale, shift)
