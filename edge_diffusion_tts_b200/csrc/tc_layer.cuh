@@ -809,8 +809,13 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
                                                           // the agent's acquire + proxy fence precede the arrive on bar_dep
               mbar_wait(bar_dep + (it & 1), (it >> 1) & 1);
             }
-            if (ph == 0) ly_tma_phase<true>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
-            else ly_tma_phase<false>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
+            if (ph == 0) {
+              ly_tma_phase<true>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
+              // (prefetching the utterance's context K / V into L2 here was measured: 10.47 against 10.02 ms -- the seven CTAs of
+              // an utterance ask for the same 256 KB and the producers fall behind; the 4 K / 2 V stages already cover it)
+            } else {
+              ly_tma_phase<false>(d, a.qkv, a.kvx, tl, smem, cwb, cwg, c0, c1);
+            }
           } else {
             mbar_wait(bar_attgo, n_phase & 1);
             tc_fence_after();
@@ -819,6 +824,27 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
           }
           ++n_phase;
         }
+#ifndef LY_NO_L2_PREFETCH
+        // The producers idle from here to the next item's window phase: pull that item's h tile and q | k | v rows (+ halo)
+        // into L2 -- they were written a dozen rounds ago by other SMs and have left it -- so that its prologue and first
+        // K/V stages see L2 latency instead of HBM latency.  wg 0: h and q; wg 1: k and v.
+        if (!is_mma) {
+          const int gn = g + (int)gridDim.x;
+          if (gn < nitems) {
+            const int ln = gn / ntiles;
+            const LayerArgs& an = p.a[ln];
+            if (an.mode == LM_BLOCK) {
+              const LyTile tn = ly_tile(d, gn - ln * ntiles);
+              if (cwg == 0) {
+                for (int c = 0; c < 40; ++c) bulk_prefetch_l2(d.hc + ((int64_t)c * d.R + tn.row0) * 4, tn.nq * 16);
+                for (int c = 0; c < 20; ++c) bulk_prefetch_l2(an.qkv + ((int64_t)c * d.R + tn.row0) * 8, tn.nq * 16);
+              } else {
+                for (int c = 20; c < 60; ++c) bulk_prefetch_l2(an.qkv + ((int64_t)c * d.R + tn.row0 - WIN) * 8, 4 * LY_KB * 16);
+              }
+            }
+          }
+        }
+#endif
       }
     } else if (cw == 0 && lane == 1 && p.done) {
       // ---- the agent: gpu-scope acquire of every item's predecessors, gpu-scope release of every finished item ----
@@ -935,6 +961,23 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
       }
     }
     if (p.done) mbar_wait(bar_dep + (it & 1), (it >> 1) & 1);   // the predecessors' h / q | k | v rows are visible
+#ifndef LY_NO_L2_PREFETCH
+    if (tid == 0) {                                       // contiguous row-major tiles this CTA reads later: one L2 prefetch each
+      if (a.tail == LT_FINAL) {                           // the update rule's operands, read at the very end of this item
+        const edtts_step_args& sp = p.step;
+        const int64_t o = tl.row0 * M;
+        const uint32_t nb = (uint32_t)tl.nq * M * 4;
+        if (sp.mode != EDTTS_STEP_EPS) bulk_prefetch_l2(d.x_t + o, nb);
+        if (sp.mode == EDTTS_STEP_DDPM && sp.noise) bulk_prefetch_l2(sp.noise + o, nb);
+        if (sp.mode == EDTTS_STEP_DPM && sp.dpm_order >= 2 && sp.dpm_hist1) bulk_prefetch_l2(sp.dpm_hist1 + o, nb);
+        if (sp.mode == EDTTS_STEP_DPM && sp.dpm_order >= 3 && sp.dpm_hist2) bulk_prefetch_l2(sp.dpm_hist2 + o, nb);
+      }
+      if (more && an.mode == LM_HEAD) {                   // the next head item's x_t tile
+        const LyTile tn = ly_tile(d, g + (int)gridDim.x - ((g + (int)gridDim.x) / ntiles) * ntiles);
+        bulk_prefetch_l2(d.x_t + tn.row0 * M, (uint32_t)tn.nq * M * 4);
+      }
+    }
+#endif
 
     if (tid < H) {                                        // per-utterance AdaLN vectors: gain = w * (1 + scale), shift
       if (a.mode == LM_BLOCK) {
