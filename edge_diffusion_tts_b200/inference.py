@@ -61,8 +61,11 @@ class EdgeInference:
         B, T, _ = p.x.shape
         dec.prepare_context(p.sem_idx, None, T, out=p.kv, ws=p.ws_ctx)
         n = len(p.t)
-        # conditioning of ALL steps in one launch (rows are independent: [n * B] timesteps -> [n * B, 8, 320])
-        dec.prepare_cond(p.t_all, p.step_all, T, S, out=p.mod_all)
+        # conditioning of ALL steps in one launch.  Within a step every utterance has the same (t, step_idx) -- the reference
+        # builds them with torch.full (inference.py:38-40) -- and a row of the conditioning depends on nothing else, so it is
+        # computed once per step ([n] rows) and broadcast over the batch (bit-identical to n * B separate rows)
+        dec.prepare_cond(p.t_uni, p.step_uni, T, S, out=p.mod_uni)
+        p.mod_all.view(n, B, *p.mod_uni.shape[1:]).copy_(p.mod_uni[:, None].expand(n, B, *p.mod_uni.shape[1:]))
         for i in range(n):
             a = _lib.StepArgs()
             a.mode = _lib.STEP_DDIM
@@ -93,8 +96,9 @@ class EdgeInference:
             p.t.append(torch.full((B,), t, dtype=torch.int64, device=device))
             p.t_prev.append(torch.full((B,), tp, dtype=torch.int64, device=device))
             p.step_idx.append(torch.full((B,), i, dtype=torch.int64, device=device))
-        p.t_all = torch.cat(p.t)
-        p.step_all = torch.cat(p.step_idx)
+        p.t_uni = torch.stack([t[0] for t in p.t])                        # one (t, step_idx) per step
+        p.step_uni = torch.stack([s[0] for s in p.step_idx])
+        p.mod_uni = torch.empty(num_steps, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
         p.mod_all = torch.empty(num_steps * B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
         p.mods = [p.mod_all[i * B:(i + 1) * B] for i in range(num_steps)]
         self._plans[key] = p
