@@ -289,12 +289,17 @@ class DPMSolverPP:
                 p["used"].append(used)
                 t_hist = (t_hist + [tp])[-2:]
                 n_hist = min(n_hist + 1, 2)
-            p["t_all"], p["si_all"] = torch.cat(p["t"]), torch.cat(p["si"])
+            # one (t, step index) per step: they are torch.full over the batch (reference schedule.py:476-477), and a
+            # conditioning row depends on nothing else -> computed once per step, broadcast over the batch (bit-identical)
+            p["t_uni"] = torch.stack([t[0] for t in p["t"]])
+            p["si_uni"] = torch.stack([s_[0] for s_ in p["si"]])
+            p["mod_uni"] = torch.empty(n, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=dev)
             plans[key] = p
 
         def run():
             dec.prepare_context(None, p["feats"], T, out=p["kv"], ws=p["ws_ctx"])
-            dec.prepare_cond(p["t_all"], p["si_all"], T, S, out=p["mod_all"])   # all steps in one launch
+            dec.prepare_cond(p["t_uni"], p["si_uni"], T, S, out=p["mod_uni"])   # all steps in one launch, one row per step
+            p["mod_all"].view(n, B, *p["mod_uni"].shape[1:]).copy_(p["mod_uni"][:, None].expand(n, B, *p["mod_uni"].shape[1:]))
             nb = len(p["x0"])
             for i in range(n):
                 a = _lib.StepArgs()
