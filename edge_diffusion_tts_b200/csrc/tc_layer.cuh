@@ -1,6 +1,8 @@
 // Fused DiffusionTransformerBlock for the bf16 tensor-core path (layers/transformer.py:141-160).
 //
-// One persistent CTA per SM; a work item is one (utterance, 128-frame tile).  For its tile the
+// One persistent CTA per SM; a work item is one (layer, utterance, 128-frame tile), and ONE launch runs a whole decoder
+// evaluation: the head (in_proj + positional embedding + QKV of block 0) and the four blocks, items numbered layer-major
+// and dealt round-robin, per-item completion flags between the layers (MegaArgs below).  For its tile the
 // CTA runs the whole block on chip -- the only HBM traffic of a layer is: q/k/v of the tile
 // (+ the +-64 frame halo of k, v) in, the fp32 residual stream h in and out, and the layer's
 // weights / the utterance's context K, V streamed from L2:
@@ -23,7 +25,9 @@
 //                     phases warpgroup g owns heads g and g+2; in the row passes it handles columns
 //                     80g .. 80g+79 of every row.  Thread 0 also issues the GEMM-chain MMAs and
 //                     weight-chunk copies (they are strictly ordered with the row passes anyway).
-//   warp 8 / 10       TMA producer of warpgroup 0 / 1: K (4 stages) and V (2 stages) blocks of 64 keys
+//   warp 8 / 10       TMA producer of warpgroup 0 / 1 (lane 0): K (4 stages) and V (2 stages) blocks of 64 keys; between
+//                     two items it prefetches the next item's h / q | k | v rows into L2.  Lane 1 of warp 8 is the
+//                     "agent" of the merged launch: gpu-scope acquire / release of the per-item flags
 //   warp 9 / 11       MMA issuer of warpgroup 0 / 1 (converged warp, elected lane):  S = Q K^T into a
 //                     double-buffered TMEM block, O += P V accumulating in TMEM
 // Attention is a single streaming pass per head in which no thread waits for a tensor-core round
