@@ -306,10 +306,18 @@ class EdgeInference:
         mod = torch.empty(B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
         chunk = max(1, min(graph_steps, n_iter))
         noise_buf = torch.empty(chunk, B, T, cfg.n_mels, dtype=torch.float32, device=device)
+        # The conditioning depends on the timestep alone (step_idx is None and every utterance is at the same t): all
+        # t_start .. t_end rows in ONE launch up front, and each iteration only copies its row over the batch (row index =
+        # t - t_end, read from the device-side counter, so the captured graph stays valid for every iteration).
+        mod_table = dec.prepare_cond(torch.arange(t_end, t_start + 1, dtype=torch.int64, device=device), None, T, S)
+        row = torch.empty(1, dtype=torch.int64, device=device)
+        sel = torch.empty(1, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
 
         def body(k: int):
             for j in range(k):
-                dec.prepare_cond(t_dev, None, T, S, out=mod)
+                torch.sub(t_dev[:1], t_end, out=row)
+                torch.index_select(mod_table, 0, row, out=sel)
+                mod.copy_(sel.expand_as(mod))
                 a = _lib.StepArgs()
                 a.mode = _lib.STEP_DDPM
                 a.t = t_dev.data_ptr()
