@@ -10,7 +10,7 @@ ABI of ``include/edtts.h``.  No CPU fallback, no Triton, no torch.compile.
 from .config import CFG, get_device, set_seed
 from .schedule import DiffusionSchedule, DPMSolverPP
 from .vq import VectorQuantizer
-from .fsq import FSQ
+from .fsq import FSQ, FSQEncoder
 from .decoder import EdgeDiffusionDecoder
 from .encoder import SemanticEncoder
 from .inference import EdgeInference
@@ -20,6 +20,6 @@ from .longform import MelStitcher, chunk_plan, crossfade_window, generate_longfo
 from . import dist
 
 __version__ = "0.1.0"
-__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "FSQ", "EdgeDiffusionDecoder",
+__all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "FSQ", "FSQEncoder", "EdgeDiffusionDecoder",
            "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "normalize_mel", "denormalize_mel", "InverseMelScale", "MelStitcher",
            "chunk_plan", "crossfade_window", "generate_longform", "dist"]

@@ -2,15 +2,16 @@
 
 Field names and defaults are the reference's; an instance of the reference's
 own ``CFG`` dataclass can be passed anywhere this one is accepted (only
-attribute reads are performed).  Differences, both deliberate: constructing it
-does not create ``./data`` / ``./run_edge_diffusion`` (config.py:165-166), and
-``use_fsq`` defaults to False because the path's quantiser is VectorQuantizer
-(FSQ is out of scope).
+attribute reads are performed).  One deliberate difference: constructing it
+does not create ``./data`` / ``./run_edge_diffusion`` (config.py:165-166).
+``use_fsq`` / ``fsq_levels`` keep the reference defaults (config.py:99-100):
+``SemanticEncoder`` then builds an ``FSQEncoder``; BASELINE configs 2 and 5 name
+the VectorQuantizer and pass ``use_fsq=False``.
 """
 from __future__ import annotations
 
 import random
-from dataclasses import dataclass, fields
+from dataclasses import dataclass, field, fields
 
 import torch
 
@@ -41,7 +42,8 @@ class CFG:
     semantic_dim: int = 128
     codebook_size: int = 512
     vq_commit: float = 1.0
-    use_fsq: bool = False
+    use_fsq: bool = True
+    fsq_levels: list = field(default_factory=lambda: [4, 4, 3, 3, 2, 2, 2, 2])
     hidden: int = 160
     layers: int = 4
     heads: int = 4

@@ -31,6 +31,21 @@ int check_launch(const char* what) {
   return EDTTS_OK;
 }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
+int sm_count() {
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 1;
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
 // ---- launch counter + per-class event timing ---------------------------------
 struct ProfSlot {
   cudaEvent_t a, b;

@@ -51,6 +51,18 @@ struct LaunchScope {
   void* slot_;
 };
 
+// ---- device facts (never the literal 148): cached per device ordinal -------------------------------------
+int current_device();                        // cudaGetDevice, -1 on error
+int sm_count();                              // cudaDevAttrMultiProcessorCount of the current device
+// cudaFuncSetAttribute is per DEVICE: a function-local `static PerDeviceOnce once;` guards the attribute set-up of a kernel
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() const { const int d = current_device(); return d < 0 || d >= 64 || !done[d]; }
+  void set() { const int d = current_device(); if (d >= 0 && d < 64) done[d] = true; }
+};
+// grid cap of a grid-stride streaming kernel: `per_sm` resident CTAs on every SM of the current device
+static inline int64_t stream_grid_cap(int per_sm) { return (int64_t)sm_count() * per_sm; }
+
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 

@@ -160,7 +160,7 @@ extern "C" int edtts_dsconv_forward(const float* x, const float* dw_w, const flo
   const int64_t total = (int64_t)B * c_out * t_out;
   const int64_t blocks = (total + 255) / 256;
   LaunchScope ls(KC_DSCONV, st);
-  dsconv_norm_gelu_kernel<<<(unsigned)(blocks > 148 * 8 ? 148 * 8 : blocks), 256, 0, st>>>(y_out, stats, gn_w, gn_b,
+  dsconv_norm_gelu_kernel<<<(unsigned)(blocks > stream_grid_cap(8) ? stream_grid_cap(8) : blocks), 256, 0, st>>>(y_out, stats, gn_w, gn_b,
                                                                                           total, c_out, t_out, cpg);
   return check_launch("dsconv_norm_gelu");
 }

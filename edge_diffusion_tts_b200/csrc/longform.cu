@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) inverse_mel_kernel(const float* __restric
 
 static inline unsigned stream_grid(int64_t work_items) {
   const int64_t blocks = (work_items + 255) / 256;
-  const int64_t cap = 148 * 8;   // 8 resident 256-thread CTAs per SM
+  const int64_t cap = stream_grid_cap(8);   // 8 resident 256-thread CTAs per SM
   return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 

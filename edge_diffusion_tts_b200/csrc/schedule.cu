@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) inpaint_inject_kernel(float* __restrict__
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline unsigned stream_grid(int64_t work_items) {
   const int64_t blocks = (work_items + 255) / 256;
-  const int64_t cap = 148 * 8;   // 8 resident 256-thread CTAs per SM
+  const int64_t cap = stream_grid_cap(8);   // 8 resident 256-thread CTAs per SM
   return (unsigned)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 

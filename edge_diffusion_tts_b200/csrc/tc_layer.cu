@@ -130,18 +130,48 @@ static int fill_layer_args(LayerArgs& a, const edtts_decoder_weights* w, const v
 
 int64_t tc_layer_flag_bytes(int B, int T) { return align_up((int64_t)LY_MAXL * B * ((T + 127) / 128) * 4, 256); }
 
+// Resident CTAs of the fused kernel on the current device: SM count x occupancy (1: the kernel takes the whole shared memory
+// and all 512 tensor-memory columns of an SM).  EDTTS_MAX_CTAS (development / tests) lowers it.
+static int layer_resident_ctas() {
+  static int cached[64] = {};
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tc_layer_kernel<false>, LY_THREADS, LY_SMEM) != cudaSuccess || per_sm < 1) {
+    (void)cudaGetLastError();
+    per_sm = 1;
+  }
+  if (per_sm > 1) per_sm = 1;                                 // TMEM: one CTA allocates all 512 columns
+  int n = sm_count() * per_sm;
+  if (const char* e = getenv("EDTTS_MAX_CTAS")) {
+    const int cap = atoi(e);
+    if (cap > 0 && cap < n) n = cap;
+  }
+  if (dev >= 0 && dev < 64) cached[dev] = n;
+  return n;
+}
+
 // The head and `n_layers` transformer blocks of one decoder evaluation.  merged: one persistent launch over all of them
 // (items ordered layer-major, per-item dependency flags in `flags`, tc_layer_flag_bytes, zeroed here on the stream);
 // otherwise one launch per layer.  qb[0] receives the head's q | k | v; block l reads qb[l & 1] and writes qb[(l + 1) & 1].
+//
+// Co-residency: in the merged launch CTAs wait on flags other CTAs of the same grid publish, so every CTA of the grid must be
+// resident at once.  The launch is therefore COOPERATIVE (cudaLaunchAttributeCooperative): the driver starts it only when
+// the whole grid fits on the SMs the context may use (MPS limits, green contexts, kernels of other streams holding SMs) and
+// refuses it (cudaErrorCooperativeLaunchTooLarge) when it never can; a refusal falls back to one launch per layer, which
+// has no inter-CTA waits.  The grid is min(items, SM count x occupancy) of the CURRENT device, never a literal.
 int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base, int n_layers, float* hc, void* const qb[2],
                      const void* kv, const float* mod, const float* x_t, const edtts_step_args* step, int B, int T, int S,
                      int stop_phase, bool merged, void* flags, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
+  static PerDeviceOnce configured;                            // the attribute is per device, not per process
+  if (configured.need()) {
+    if (cudaFuncSetAttribute(tc_layer_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
       return check_launch("tc_layer smem attribute");
-    configured = true;
+#ifdef EDTTS_DEBUG_CLOCKS
+    if (cudaFuncSetAttribute(tc_layer_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LY_SMEM) != cudaSuccess)
+      return check_launch("tc_layer smem attribute");
+#endif
+    configured.set();
   }
   EDTTS_REQUIRE(n_layers >= 0 && n_layers + 1 <= LY_MAXL, EDTTS_EINVAL, "tc_layer: %d layers", n_layers);
   MegaArgs all;
@@ -159,13 +189,18 @@ int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base,
   }
   const int n_launch = n_layers + 1;
   if (step) all.step = *step;
+  const int ntiles = B * ((T + 127) / 128);
+  const int resident = layer_resident_ctas();
+#ifdef EDTTS_DEBUG_CLOCKS
+  // development build only (-DEDTTS_DEBUG_CLOCKS): per-phase cycle counters of CTA 0, read back synchronously.  Allocates and
+  // synchronises, which the ABI forbids -- never compiled into the shipped library.
   static long long* clk_buf = nullptr;
   static const bool want_clocks = getenv("EDTTS_LAYER_CLOCKS") != nullptr;
   if (want_clocks) {
-    if (!clk_buf) cudaMalloc(&clk_buf, 148 * 32 * sizeof(long long));
+    if (!clk_buf) cudaMalloc(&clk_buf, 1024 * 32 * sizeof(long long));
     for (int l = 0; l < n_launch; ++l) all.a[l].phase_clocks = clk_buf;
   }
-  const int ntiles = B * ((T + 127) / 128);
+#endif
 #ifdef LY_TRACE
   static long long* tr_buf = nullptr;
   static int tr_done = 0;
@@ -176,25 +211,43 @@ int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base,
     for (int l = 0; l < n_launch; ++l) all.a[l].phase_clocks = tr_buf;
   }
 #endif
-  auto launch = [&](const MegaArgs& m, int items) {
+  auto launch = [&](const MegaArgs& m, int items, bool cooperative) -> cudaError_t {
     LaunchScope ls(KC_TC_LAYER, st);
-    if (want_clocks) tc_layer_kernel<true><<<items < 148 ? items : 148, LY_THREADS, LY_SMEM, st>>>(m);
-    else tc_layer_kernel<false><<<items < 148 ? items : 148, LY_THREADS, LY_SMEM, st>>>(m);
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)(items < resident ? items : resident));
+    lc.blockDim = dim3(LY_THREADS);
+    lc.dynamicSmemBytes = LY_SMEM;
+    lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = 1;
+    lc.attrs = at;
+    lc.numAttrs = cooperative ? 1 : 0;
+#ifdef EDTTS_DEBUG_CLOCKS
+    if (want_clocks) return cudaLaunchKernelEx(&lc, tc_layer_kernel<true>, m);
+#endif
+    return cudaLaunchKernelEx(&lc, tc_layer_kernel<false>, m);
   };
+  bool done_merged = false;
   if (merged && n_launch > 1) {
     EDTTS_REQUIRE(flags, EDTTS_EINVAL, "tc_layer: merged launch needs the flag buffer");
     if (cudaMemsetAsync(flags, 0, (size_t)n_launch * ntiles * 4, st) != cudaSuccess) return check_launch("tc_layer flags memset");
     all.n_launch = n_launch;
     all.done = reinterpret_cast<int*>(flags);
-    launch(all, n_launch * ntiles);
-  } else {
+    const cudaError_t e = launch(all, n_launch * ntiles, true);
+    if (e == cudaSuccess) done_merged = true;
+    else if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) (void)cudaGetLastError();   // -> per layer
+    else return check_launch("tc_layer (merged)");
+  }
+  if (!done_merged) {
     for (int l = 0; l < n_launch; ++l) {
       MegaArgs one;
       memset(&one, 0, sizeof(one));
       one.a[0] = all.a[l];
       one.step = all.step;
       one.n_launch = 1;
-      launch(one, ntiles);
+      if (launch(one, ntiles, false) != cudaSuccess) return check_launch("tc_layer");
     }
   }
 #ifdef LY_TRACE
@@ -212,7 +265,8 @@ int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base,
         fprintf(stderr, "TRACE %d %lld %lld\n", s_, hb[s_ * 1024 + 2 + 2 * e], hb[s_ * 1024 + 3 + 2 * e] - t0);
   }
 #endif
-  if (want_clocks) {   // debug only: synchronous read-back of the per-phase cycle counters of CTA 0 (summed over its items)
+#ifdef EDTTS_DEBUG_CLOCKS
+  if (want_clocks) {   // synchronous read-back of the per-phase cycle counters of CTA 0 (summed over its items)
     long long hc_[32];
     cudaMemcpy(hc_, clk_buf, sizeof(hc_), cudaMemcpyDeviceToHost);
     fprintf(stderr, "[tc_layer clocks] prologue %lld window %lld proj+n2 %lld q %lld cross %lld out+n3 %lld ffn %lld f3 %lld\n",
@@ -224,6 +278,7 @@ int launch_tc_layers(const edtts_decoder_weights* w, const void* layer_img_base,
               k == 1 ? "window" : "cross ", hc_[8 * k], hc_[8 * k + 1], hc_[8 * k + 2], hc_[8 * k + 3], hc_[8 * k + 4],
               hc_[8 * k + 5], hc_[8 * k + 6], hc_[8 * k + 7]);
   }
+#endif
   return check_launch("tc_layer");
 }
 

@@ -104,13 +104,13 @@ template <int K, int N_CTA>
 static int launch_tc_gemm_t(const TcGemmArgs& g, int ny, cudaStream_t st) {
   using L = TcGemmSmem<K, N_CTA>;
   EDTTS_REQUIRE(!(g.amode == A_F32 && g.epi == TE_RESID), EDTTS_EINVAL, "tc_gemm: fp32 input with residual epilogue");
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     const int max_smem = L::OFF_IO + (L::IN_BYTES > L::OUT_BYTES ? L::IN_BYTES : L::OUT_BYTES) + 64;
     if (cudaFuncSetAttribute(tc_gemm_kernel<K, N_CTA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              max_smem > 232448 ? 232448 : max_smem) != cudaSuccess)
       return check_launch("tc_gemm smem attribute");
-    configured = true;
+    configured.set();
   }
   const int smem = L::total(g.amode, g.epi);
   EDTTS_REQUIRE(smem <= 232448, EDTTS_ENOTSUP, "tc_gemm<%d,%d>: %d B of shared memory", K, N_CTA, smem);
@@ -122,7 +122,7 @@ static int launch_tc_gemm_t(const TcGemmArgs& g, int ny, cudaStream_t st) {
   if (per_sm > tmem_fit) per_sm = tmem_fit;
   if (per_sm < 1) per_sm = 1;
   if (per_sm > 3) per_sm = 3;
-  int64_t nx = (int64_t)148 * per_sm / ny;
+  int64_t nx = (int64_t)sm_count() * per_sm / ny;
   if (nx > ntiles) nx = ntiles;
   if (nx < 1) nx = 1;
   LaunchScope ls(KC_TC_GEMM, st);
@@ -151,13 +151,13 @@ int pack_activation(const float* src, int lda, void* dst_chunk, int64_t R, int K
 
 template <bool WINDOW>
 static int launch_tc_attn(const TcAttnArgs& a, int B, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.need()) {
     if (cudaFuncSetAttribute(tc_attn_kernel<WINDOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnSmem::TOTAL) !=
         cudaSuccess)
       return check_launch("tc_attn smem attribute");
     cudaFuncSetAttribute(tc_attn_kernel<WINDOW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    configured = true;
+    configured.set();
   }
   LaunchScope ls(WINDOW ? KC_TC_ATTN_WINDOW : KC_TC_ATTN_CROSS, st);
   tc_attn_kernel<WINDOW><<<dim3((a.Tq + AT_M - 1) / AT_M, NH, B), 128, AttnSmem::TOTAL, st>>>(a);

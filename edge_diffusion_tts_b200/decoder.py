@@ -85,6 +85,9 @@ class _Block(_Params):
                                      nn.Identity())                 # keys net.0 / net.3 (transformer.py:40-46)
 
 
+_next_uid = [0]
+
+
 class EdgeDiffusionDecoder(nn.Module):
     #: arithmetic of the contractions: "fp32" (parity path) or "bf16" (tcgen05 tensor cores)
     precision: str = "fp32"
@@ -111,6 +114,8 @@ class EdgeDiffusionDecoder(nn.Module):
                                                       * (-math.log(10000.0) / (half - 1))), persistent=False)
         self._wcache = None
         self.weights_epoch = 0          # bumped whenever the C view of the weights is rebuilt
+        _next_uid[0] += 1
+        self._uid = _next_uid[0]        # process-unique: graph / plan caches of callers are keyed on (uid, epoch)
         self._ws_ctx = _lib.Workspace()
         self._ws_step = _lib.Workspace()
 
@@ -122,11 +127,12 @@ class EdgeDiffusionDecoder(nn.Module):
         dev = self.out_proj.weight.device
         if dev.type != "cuda":
             raise RuntimeError("EdgeDiffusionDecoder must be on a CUDA device (.to('cuda')); there is no CPU path")
-        key = (tuple((p.data_ptr(), p._version) for p in ps.values()), T > self.pos_emb.pe.shape[0],
-               S > self.context_pos_emb.pe.shape[0], self.precision)
+        key = (tuple((p.data_ptr(), p._version) for p in ps.values()), self.precision)
         c = self._wcache
         if c is not None and c["key"] == key and c["pos_rows"] >= T and c["ctx_rows"] >= S:
             return c["w"]
+        if c is not None:               # an extended table, once built, is kept: alternating short / long shapes
+            T, S = max(T, c["pos_rows"]), max(S, c["ctx_rows"])      # must not rebuild (and re-capture) every call
         keep = []
 
         def P(t):
@@ -182,6 +188,13 @@ class EdgeDiffusionDecoder(nn.Module):
         self._wcache = dict(key=key, w=w, keep=keep, pos_rows=pos.shape[0], ctx_rows=ctx.shape[0])
         self.weights_epoch += 1
         return w
+
+    def weights_token(self, T: int = 1, S: int = 1):
+        """Refreshes the C view of the weights if a parameter changed (load_state_dict, in-place update, .to()) and returns
+        a token that identifies decoder + weight image: callers that replay captured graphs compare it before every
+        replay -- a graph holds raw pointers into the packed image of the epoch it was captured in."""
+        self._weights(T, S)
+        return (self._uid, self.weights_epoch)
 
     def _prec(self) -> int:
         if self.precision not in ("fp32", "bf16"):

@@ -1,6 +1,7 @@
 """SemanticEncoder (models/encoder.py:14-131), thin: the trainable projection
-(Linear 768->128, GELU, LayerNorm, Linear 128->128) and the VectorQuantizer run
-as CUDA kernels; HuBERT stays the ``transformers`` module (frozen third-party
+(Linear 768->128, GELU, LayerNorm, Linear 128->128) and the quantiser -- FSQEncoder
+when ``cfg.use_fsq`` (the reference default, encoder.py:49-50), else VectorQuantizer --
+run as CUDA kernels; HuBERT stays the ``transformers`` module (frozen third-party
 feature extractor, out of scope -- BASELINE configs feed synthetic 768-d features
 through ``quantize_features`` / ``encode_features``)."""
 from __future__ import annotations
@@ -11,6 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from .fsq import FSQEncoder
 from .vq import VectorQuantizer
 
 
@@ -18,8 +20,6 @@ class SemanticEncoder(nn.Module):
     def __init__(self, cfg, hubert: Optional[nn.Module] = None, load_hubert: bool = True):
         super().__init__()
         self.cfg = cfg
-        if getattr(cfg, "use_fsq", False):
-            raise NotImplementedError("FSQ quantiser is outside the accelerated path (SURVEY.md F5); set use_fsq=False")
         if hubert is None and load_hubert:
             from transformers import HubertModel                       # encoder.py:35 (needs the checkpoint)
             hubert = HubertModel.from_pretrained(cfg.hubert_id)
@@ -30,8 +30,12 @@ class SemanticEncoder(nn.Module):
                 p.requires_grad = False
         self.proj = nn.Sequential(nn.Linear(768, cfg.semantic_dim), nn.GELU(), nn.LayerNorm(cfg.semantic_dim),
                                   nn.Linear(cfg.semantic_dim, cfg.semantic_dim))      # encoder.py:41-46
-        self.vq = VectorQuantizer(cfg.semantic_dim, cfg.codebook_size, commit=cfg.vq_commit)
-        self.codebook_size = cfg.codebook_size
+        if getattr(cfg, "use_fsq", False):                                             # encoder.py:49-57
+            self.vq = FSQEncoder(cfg.semantic_dim, cfg.fsq_levels)
+            self.codebook_size = self.vq.codebook_size
+        else:
+            self.vq = VectorQuantizer(cfg.semantic_dim, cfg.codebook_size, commit=cfg.vq_commit)
+            self.codebook_size = cfg.codebook_size
         self._ws = _lib.Workspace()
 
     @torch.no_grad()

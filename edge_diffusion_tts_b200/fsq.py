@@ -4,7 +4,11 @@ value is computed (z_b + (q - z_b)) but no autograd graph is built.
 
 Reference quirk kept as is: ``codes_to_indices`` flattens with the FIRST dimension fastest
 (basis = cumprod([1] + levels[:-1])) while ``indices_to_codes`` decodes with the LAST dimension fastest, so the two are
-inverse to each other only when all levels are equal."""
+inverse to each other only when all levels are equal.
+
+``FSQEncoder`` (models/fsq.py:135-222) is the quantiser ``SemanticEncoder`` builds with the reference's default
+``use_fsq=True``: proj_down -> FSQ -> proj_up with the VectorQuantizer 5-tuple interface, one fused kernel
+(edtts_fsq_encoder)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -81,3 +85,73 @@ class FSQ(nn.Module):
         _lib.check(lib.edtts_fsq_decode(_lib.ptr(indices), C.cast(self._lv, C.c_void_p), self.dim, _lib.ptr(codes),
                                         indices.numel(), _lib.stream_ptr(indices.device)), "fsq_decode")
         return codes
+
+
+class FSQEncoder(nn.Module):
+    """models/fsq.py:135-222: same constructor, sub-module names (``fsq``, ``proj_down``, ``proj_up``: reference encoder
+    checkpoints load strictly), ``codebook_size``, ``forward`` 5-tuple, ``encode`` / ``decode``.  Inference only."""
+
+    def __init__(self, input_dim: int, levels: List[int] = [8, 6, 5, 5, 5]):
+        super().__init__()
+        self.fsq = FSQ(list(levels))
+        self.fsq_dim = len(levels)
+        self.proj_down = nn.Linear(input_dim, self.fsq_dim)
+        self.proj_up = nn.Linear(self.fsq_dim, input_dim)
+        self.input_dim = input_dim
+
+    @property
+    def codebook_size(self) -> int:
+        return self.fsq.codebook_size
+
+    def _run(self, z, idx_in, want_zq: bool, want_idx: bool):
+        lib = _lib.load()
+        src = z if z is not None else idx_in
+        if src.device.type != "cuda":
+            raise RuntimeError("FSQEncoder runs on CUDA tensors only (no CPU fallback)")
+        lead = tuple(src.shape[:-1]) if z is not None else tuple(src.shape)
+        rows = 1
+        for n in lead:
+            rows *= n
+        D = self.input_dim
+        zq = torch.empty(*lead, D, dtype=torch.float32, device=src.device) if want_zq else None
+        idx = torch.empty(lead, dtype=torch.int64, device=src.device) if want_idx else None
+        W = [_lib.f32(t.detach()) for t in (self.proj_down.weight, self.proj_down.bias, self.proj_up.weight, self.proj_up.bias)]
+        _lib.check(lib.edtts_fsq_encoder(_lib.ptr(z), _lib.ptr(idx_in), *[_lib.ptr(t) for t in W],
+                                         C.cast(self.fsq._lv, C.c_void_p), self.fsq_dim, D, _lib.ptr(zq), _lib.ptr(idx), rows,
+                                         _lib.stream_ptr(src.device)), "fsq_encoder")
+        return zq, idx
+
+    def _check(self, z: torch.Tensor) -> torch.Tensor:
+        if z.shape[-1] != self.input_dim:
+            raise ValueError(f"last dimension must be {self.input_dim}, got {tuple(z.shape)}")
+        return _lib.f32(z)
+
+    @torch.no_grad()
+    def forward(self, z: torch.Tensor):
+        """fsq.py:161-198 -> (z_q, idx, loss = 0, perplexity, used)."""
+        z = self._check(z)
+        z_q, idx = self._run(z, None, True, True)
+        counts = self.fused_count_usage(idx)
+        probs = counts / counts.sum().clamp_min(1.0)
+        perplexity = torch.exp(-(probs * torch.log(probs.clamp_min(1e-12))).sum())
+        used = (counts > 0).sum()
+        return z_q, idx, torch.tensor(0.0, device=z.device), perplexity, used
+
+    def fused_count_usage(self, indices: torch.Tensor) -> torch.Tensor:
+        """fsq.py:200-209: float32 usage counts per code (edtts_vq_bincount: shared-memory histogram, no host sync)."""
+        lib = _lib.load()
+        flat = _lib.i64(indices).reshape(-1)
+        counts = torch.empty(self.fsq.num_codes, dtype=torch.int32, device=flat.device)
+        _lib.check(lib.edtts_vq_bincount(_lib.ptr(flat), _lib.ptr(counts), flat.numel(), self.fsq.num_codes,
+                                         _lib.stream_ptr(flat.device)), "vq_bincount")
+        return counts.float()
+
+    @torch.no_grad()
+    def encode(self, z: torch.Tensor) -> torch.Tensor:
+        """fsq.py:212-216."""
+        return self._run(self._check(z), None, False, True)[1]
+
+    @torch.no_grad()
+    def decode(self, indices: torch.Tensor) -> torch.Tensor:
+        """fsq.py:218-221: indices_to_codes (last dimension fastest, as the reference) -> proj_up."""
+        return self._run(None, _lib.i64(indices), True, False)[0]

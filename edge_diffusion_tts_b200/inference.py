@@ -77,7 +77,7 @@ class EdgeInference:
             dec.step(p.x, p.mods[i], p.kv, S, a, ws=p.ws_step)
 
     def _plan_ddim(self, B: int, S: int, num_steps: int, device) -> _Plan:
-        key = ("ddim", B, S, num_steps, self.decoder.precision, str(device))
+        key = ("ddim", B, S, num_steps, self.decoder.precision, str(device), self.decoder._uid)
         p = self._plans.get(key)
         if p is not None:
             return p
@@ -98,6 +98,7 @@ class EdgeInference:
             p.step_idx.append(torch.full((B,), i, dtype=torch.int64, device=device))
         p.t_uni = torch.stack([t[0] for t in p.t])                        # one (t, step_idx) per step
         p.step_uni = torch.stack([s[0] for s in p.step_idx])
+        num_steps = len(p.t)                                              # range() may yield fewer than asked for
         p.mod_uni = torch.empty(num_steps, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
         p.mod_all = torch.empty(num_steps * B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=device)
         p.mods = [p.mod_all[i * B:(i + 1) * B] for i in range(num_steps)]
@@ -127,7 +128,8 @@ class EdgeInference:
         if not self.use_cuda_graph:
             self._run_ddim(p, S)
         else:
-            if p.graph is None or p.epoch != self.decoder.weights_epoch:
+            token = self.decoder.weights_token(T, S)                     # repacks + bumps the epoch if a parameter changed
+            if p.graph is None or p.epoch != token:
                 self._run_ddim(p, S)                                     # warm-up: builds weight views, workspaces
                 p.x.copy_(x_T)
                 torch.cuda.synchronize(device)
@@ -135,7 +137,7 @@ class EdgeInference:
                 with torch.cuda.graph(g):
                     self._run_ddim(p, S)
                 p.graph = g
-                p.epoch = self.decoder.weights_epoch
+                p.epoch = token
                 p.x.copy_(x_T)
             p.graph.replay()
         return p.x0.clone()
@@ -193,7 +195,7 @@ class EdgeInference:
         if not self.use_cuda_graph:
             self._run_inpaint(p)
         else:
-            key = (dec.weights_epoch, p.cfg_scale)                       # the guidance scale is baked into the captured launch
+            key = (dec.weights_token(T, S), p.cfg_scale)                 # the guidance scale is baked into the captured launch
             if p.graph is None or p.epoch != key:
                 self._run_inpaint(p)                                     # warm-up: builds weight views
                 torch.cuda.synchronize(dev)
@@ -207,7 +209,7 @@ class EdgeInference:
     def _plan_inpaint(self, B: int, T: int, S: int, Dsem: int, L: int, steps: int, t_start: int, guided: bool, device) -> _Plan:
         """Static buffers of one refine-loop shape (so the loop can be replayed from a CUDA graph): inputs, the per-step
         coefficient rows built with the reference's tensor expressions, conditioning of all steps, plan-private scratch."""
-        key = ("inpaint", B, T, S, Dsem, L, steps, t_start, guided, self.decoder.precision, str(device))
+        key = ("inpaint", B, T, S, Dsem, L, steps, t_start, guided, self.decoder.precision, str(device), self.decoder._uid)
         p = self._plans.get(key)
         if p is not None:
             return p

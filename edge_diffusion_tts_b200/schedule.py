@@ -262,7 +262,9 @@ class DPMSolverPP:
         B, T, _ = x_T.shape
         S = sem_features.shape[1]
         n = len(ts)
-        key = (B, T, S, tuple(ts), self.order, self.predict_x0, bool(return_intermediates), dec.precision, str(dev))
+        # the plan holds a graph with the decoder's weight pointers baked in: keyed on the decoder as well (a teacher and a
+        # student decoder share one solver in the reference pipeline)
+        key = (dec._uid, B, T, S, tuple(ts), self.order, self.predict_x0, bool(return_intermediates), dec.precision, str(dev))
         plans = self.__dict__.setdefault("_plans", {})
         p = plans.get(key)
         if p is None:
@@ -321,14 +323,15 @@ class DPMSolverPP:
         if not self.use_cuda_graph:
             run()
         else:
-            if p["graph"] is None or p["epoch"] != dec.weights_epoch:
+            token = dec.weights_token(T, S)                           # repacks + bumps the epoch if a parameter changed
+            if p["graph"] is None or p["epoch"] != token:
                 run()                                                 # warm-up: builds weight views / packed images
                 p["x"].copy_(x_T)
                 torch.cuda.synchronize(dev)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     run()
-                p["graph"], p["epoch"] = g, dec.weights_epoch
+                p["graph"], p["epoch"] = g, token
                 p["x"].copy_(x_T)
             p["graph"].replay()
         x = p["x"].clone()

@@ -274,6 +274,13 @@ int edtts_fsq_forward(const float* z, const int32_t* levels_host, int32_t dim, i
 /* indices_to_codes (fsq.py:121-132): last dimension fastest, as the reference decodes. */
 int edtts_fsq_decode(const int64_t* idx, const int32_t* levels_host, int32_t dim, float* codes_out, int64_t rows,
                      void* stream);
+/* FSQEncoder (models/fsq.py:135-222), the quantiser SemanticEncoder builds when cfg.use_fsq (models/encoder.py:49-50), fused:
+ * forward (fsq.py:161-198, idx_in == NULL): z [rows, in_dim] -> proj_down (w_down [dim, in_dim], b_down [dim]) -> FSQ ->
+ * proj_up (w_up [in_dim, dim], b_up [in_dim]) -> zq_out [rows, in_dim] (may be NULL: encode, fsq.py:212-216) and
+ * idx_out [rows] (may be NULL); decode (fsq.py:218-221, idx_in != NULL): indices_to_codes -> proj_up -> zq_out. */
+int edtts_fsq_encoder(const float* z, const int64_t* idx_in, const float* w_down, const float* b_down, const float* w_up,
+                      const float* b_up, const int32_t* levels_host, int32_t dim, int32_t in_dim, float* zq_out,
+                      int64_t* idx_out, int64_t rows, void* stream);
 
 /* --- DepthwiseSeparableConv (layers/conv.py:10-64), operator level ---------- */
 /* x [B,C_in,T] -> y [B,C_out,T_out], T_out = (T + 2*(k/2) - k)/stride + 1:

@@ -491,6 +491,26 @@ def fsq_indices_to_codes(levels, indices: Tensor) -> Tensor:
     return codes.float() / ((lv.float() - 1) / 2) - 1
 
 
+def fsq_encoder_forward(sd: State, levels, z: Tensor):
+    """FSQEncoder.forward (fsq.py:161-198) -> (z_q, indices, loss, perplexity, used, z_scaled); sd holds proj_down.* /
+    proj_up.* (nn.Linear).  z_scaled as in fsq_forward, for boundary exclusion in the GPU tests."""
+    z_low = F.linear(z, sd["proj_down.weight"], sd["proj_down.bias"])
+    z_q_low, idx, zs = fsq_forward(levels, z_low)
+    z_q = F.linear(z_q_low, sd["proj_up.weight"], sd["proj_up.bias"])
+    n = 1
+    for l in levels:
+        n *= l
+    counts = torch.zeros(n, dtype=torch.float32).scatter_add_(0, idx.flatten(), torch.ones(idx.numel()))
+    probs = counts / counts.sum().clamp_min(1.0)
+    perplexity = torch.exp(-(probs * torch.log(probs.clamp_min(1e-12))).sum())
+    return z_q, idx, torch.tensor(0.0), perplexity, (counts > 0).sum(), zs
+
+
+def fsq_encoder_decode(sd: State, levels, indices: Tensor) -> Tensor:
+    """FSQEncoder.decode (fsq.py:218-221)."""
+    return F.linear(fsq_indices_to_codes(levels, indices), sd["proj_up.weight"], sd["proj_up.bias"])
+
+
 # ----------------------------------------------------------------------------
 # inference_pipeline.py:145-196  in-painting refine loop of the long-form pipeline (SURVEY.md section 8f-2)
 # ----------------------------------------------------------------------------

@@ -60,6 +60,23 @@ def make_fsq(ref, meta):
     torch.save(dict(meta=meta, cases=cases), os.path.join(OUT, "fsq.pt"))
 
 
+def make_fsq_encoder(ref, meta):
+    """FSQEncoder.forward / encode / decode of the reference (models/fsq.py:135-222) with synthetic projections, and the
+    reference SemanticEncoder's quantiser choice (encoder.py:49-57) recorded as state-dict keys."""
+    import importlib
+    F = importlib.import_module("edge_diffusion_tts.models.fsq")
+    cases = {}
+    for levels in ([4, 4, 3, 3, 2, 2, 2, 2], [8, 6, 5, 5, 5]):
+        m = F.FSQEncoder(128, levels).eval()
+        m.load_state_dict(synth.synth_fsq_encoder_state(23, levels), strict=True)
+        z = torch.randn(3, 37, 128, generator=torch.Generator().manual_seed(23 + len(levels)))
+        with torch.no_grad():
+            z_q, idx, loss, ppl, used = m(z)
+            cases[tuple(levels)] = dict(z_q=z_q, idx=idx, loss=loss, perplexity=ppl, used=used, encode=m.encode(z),
+                                        decode=m.decode(idx), keys=sorted(m.state_dict()), codebook_size=m.codebook_size)
+    torch.save(dict(meta=meta, seed=23, cases=cases), os.path.join(OUT, "fsq_encoder.pt"))
+
+
 def inpaint_cases():
     """(name, cfg_scale, with known frames) and the seeded inputs shared by the fixture generator and the tests."""
     feats = synth.synth_features(61, 2, 16, 128)
@@ -147,6 +164,9 @@ def main(only=None):
         return
     if only == "fsq":
         make_fsq(ref, meta)
+        return
+    if only == "fsq_encoder":
+        make_fsq_encoder(ref, meta)
         return
     if only == "inpaint":
         make_inpaint(ref, meta)
@@ -259,6 +279,7 @@ def main(only=None):
 
     make_dpm(ref, meta)
     make_fsq(ref, meta)
+    make_fsq_encoder(ref, meta)
     make_inpaint(ref, meta)
     make_longform(ref, meta)
     make_invmel(ref, meta)

@@ -112,6 +112,19 @@ def synth_proj_state(seed: int = 0, dim=O.SEMANTIC_DIM) -> Dict[str, Tensor]:
     }
 
 
+def synth_fsq_encoder_state(seed: int, levels, dim=O.SEMANTIC_DIM) -> Dict[str, Tensor]:
+    """FSQEncoder state (models/fsq.py:148-154): fsq._levels / fsq._basis buffers + the two projections."""
+    n = len(levels)
+    return {
+        "fsq._levels": torch.tensor(list(levels), dtype=torch.int32),
+        "fsq._basis": torch.cumprod(torch.tensor([1] + list(levels[:-1]), dtype=torch.int64), dim=0),
+        "proj_down.weight": _uniform(seed, "fsq.proj_down.weight", (n, dim), 3 * dim ** -0.5),
+        "proj_down.bias": _uniform(seed, "fsq.proj_down.bias", (n,), dim ** -0.5),
+        "proj_up.weight": _uniform(seed, "fsq.proj_up.weight", (dim, n), n ** -0.5),
+        "proj_up.bias": _uniform(seed, "fsq.proj_up.bias", (dim,), n ** -0.5),
+    }
+
+
 def synth_dsconv_state(seed: int, in_ch: int, out_ch: int, k: int = 3) -> Dict[str, Tensor]:
     """DepthwiseSeparableConv state (conv.py:31-49)."""
     return {

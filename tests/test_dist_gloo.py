@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from edge_diffusion_tts_b200.dist import gather_batch, generate_mel_sharded, shard_bounds
+from edge_diffusion_tts_b200.dist import RootGather, gather_batch, gather_to_root, generate_mel_sharded, shard_bounds
 
 
 def test_shard_bounds():
@@ -35,6 +35,19 @@ def _worker(rank, world, port, B, out):
         ok = torch.equal(got, full)
         lo, hi = shard_bounds(B, world)[rank]
         ok = ok and torch.equal(gather_batch(full[lo:hi], B), full)
+        # the consumer on one rank: gather to rank 0 only, synchronous and as the double-buffered asynchronous pipeline
+        r = gather_to_root(full[lo:hi], B, dst=0)
+        ok = ok and ((r is None) if rank else torch.equal(r, full))
+        r = generate_mel_sharded(_FakeInference(), idx, 4, x_T=xT, dst=1)
+        ok = ok and ((r is None) if rank != 1 else torch.equal(r, full))
+        rg = RootGather(B, dst=0)
+        for k in range(5):                                  # slots alternate; start() k+2 waits for gather k
+            rg.start(full[lo:hi] + k)
+            if k % 2:
+                r = rg.finish()
+                ok = ok and ((r is None) if rank else torch.equal(r, full + k))
+        r = rg.finish()
+        ok = ok and ((r is None) if rank else torch.equal(r, full + 4))
         out[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

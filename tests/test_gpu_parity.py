@@ -75,7 +75,7 @@ def test_ddim_ddpm_random_shapes_bit_exact(pkg, B, T, eta):
 
 # ------------------------------------------------------------------ VQ + encoder projection
 def _encoder(pkg):
-    cfg = pkg.CFG(device=DEV)
+    cfg = pkg.CFG(device=DEV, use_fsq=False)
     enc = pkg.SemanticEncoder(cfg, load_hubert=False).to(DEV).eval()
     enc.proj.load_state_dict(synth.synth_proj_state(0))
     enc.vq.load_state_dict(synth.synth_vq_state(0))

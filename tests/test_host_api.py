@@ -55,7 +55,7 @@ def test_decoder_state_dict_is_the_reference_layout():
     assert sorted(vq.state_dict()) == ["codebook.weight", "ema_cluster_size", "ema_w", "update_count"]
     conv = E.DepthwiseSeparableConv(16, 24, 5, 2)
     assert sorted(conv.state_dict()) == ["depthwise.weight", "norm.bias", "norm.weight", "pointwise.bias", "pointwise.weight"]
-    enc = E.SemanticEncoder(E.CFG(), load_hubert=False)
+    enc = E.SemanticEncoder(E.CFG(use_fsq=False), load_hubert=False)
     assert [k for k in enc.state_dict() if k.startswith("proj.")] == ["proj.0.weight", "proj.0.bias", "proj.2.weight",
                                                                       "proj.2.bias", "proj.3.weight", "proj.3.bias"]
 

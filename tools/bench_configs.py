@@ -47,7 +47,7 @@ def main():
     dec.load_state_dict(synth.synth_decoder_state(0), strict=True)
     dec.precision = "bf16"
     sched = E.DiffusionSchedule(cfg.diff_steps, device=DEV)
-    enc = E.SemanticEncoder(cfg, load_hubert=False).to(DEV).eval()
+    enc = E.SemanticEncoder(E.CFG(device=DEV, use_fsq=False), load_hubert=False).to(DEV).eval()
     enc.proj.load_state_dict(synth.synth_proj_state(0))
     enc.vq.load_state_dict(synth.synth_vq_state(0))
     inf = E.EdgeInference(cfg, sched, enc, dec)

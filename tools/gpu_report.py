@@ -135,7 +135,7 @@ def generate(prec="fp32"):
 
 
 def vq():
-    cfg = E.CFG(device=DEV)
+    cfg = E.CFG(device=DEV, use_fsq=False)
     enc = E.SemanticEncoder(cfg, load_hubert=False).to(DEV).eval()
     enc.proj.load_state_dict(synth.synth_proj_state(0))
     enc.vq.load_state_dict(synth.synth_vq_state(0))
