@@ -141,6 +141,8 @@ class FSQEncoder(nn.Module):
         """fsq.py:200-209: float32 usage counts per code (edtts_vq_bincount: shared-memory histogram, no host sync)."""
         lib = _lib.load()
         flat = _lib.i64(indices).reshape(-1)
+        if flat.numel() == 0:
+            return torch.zeros(self.fsq.num_codes, dtype=torch.float32, device=flat.device)
         counts = torch.empty(self.fsq.num_codes, dtype=torch.int32, device=flat.device)
         _lib.check(lib.edtts_vq_bincount(_lib.ptr(flat), _lib.ptr(counts), flat.numel(), self.fsq.num_codes,
                                          _lib.stream_ptr(flat.device)), "vq_bincount")

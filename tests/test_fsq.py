@@ -141,5 +141,7 @@ def test_semantic_encoder_use_fsq(lib):
     safe = ((zs - torch.floor(zs) - 0.5).abs() > 1e-3).all(dim=-1)
     assert safe.float().mean().item() > 0.95 and torch.equal(idx.cpu()[safe], o_idx[safe])
     assert torch.equal(enc.encode_features(h.to(DEV)).cpu(), idx.cpu())
-    assert (enc.decode_tokens(idx) - z_q).abs().max().item() <= 2e-6
+    # decode_tokens is NOT the inverse of the forward index for unequal levels (the reference's basis mismatch, kept)
+    want = O.fsq_encoder_decode(synth.synth_fsq_encoder_state(23, cfg.fsq_levels), cfg.fsq_levels, idx.cpu())
+    assert (enc.decode_tokens(idx).cpu() - want).abs().max().item() <= 2e-6
     assert 0 <= int(idx.min()) and int(idx.max()) < enc.codebook_size == 2304
