@@ -429,7 +429,7 @@ def main():
 
         for _ in range(n_warm):
             one()
-        if rg is not None:
+        if rg is not None and n_warm:
             rg.finish()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
