@@ -84,7 +84,7 @@ SIGNATURES = {
     "edtts_fsq_decode": (C.c_int, [_p, _p, _i32, _p, _i64, _p]),
     "edtts_fsq_encoder": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i64, _p]),
     "edtts_dsconv_forward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
-    "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "edtts_test_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "edtts_test_attention": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "edtts_test_hidden": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32,

@@ -35,7 +35,7 @@ class DepthwiseSeparableConv(nn.Module):
         y = torch.empty(B, self.out_ch, max(t_out, 0), dtype=torch.float32, device=x.device)
         if B == 0 or t_out <= 0:
             return y
-        nbytes = lib.edtts_dsconv_workspace_bytes(B, self.out_ch, t_out)
+        nbytes = lib.edtts_dsconv_workspace_bytes(B, self.in_ch, self.out_ch, t_out)
         ws = self._ws.get(nbytes, x.device)
         W = [_lib.f32(t.detach()) for t in (self.depthwise.weight, self.pointwise.weight, self.pointwise.bias,
                                             self.norm.weight, self.norm.bias)]

@@ -285,12 +285,12 @@ int edtts_fsq_encoder(const float* z, const int64_t* idx_in, const float* w_down
 /* --- DepthwiseSeparableConv (layers/conv.py:10-64), operator level ---------- */
 /* x [B,C_in,T] -> y [B,C_out,T_out], T_out = (T + 2*(k/2) - k)/stride + 1:
  * depthwise k taps (no bias) -> pointwise 1x1 (+bias) -> GroupNorm(min(8,C_out)) -> GELU.
- * workspace: edtts_dsconv_workspace_bytes(B, C_out, T_out). */
+ * workspace: edtts_dsconv_workspace_bytes(B, C_in, C_out, T_out). */
 int edtts_dsconv_forward(const float* x, const float* dw_w, const float* pw_w, const float* pw_b,
                          const float* gn_w, const float* gn_b, float* y_out, void* workspace,
                          int64_t workspace_bytes, int32_t B, int32_t c_in, int32_t c_out, int32_t T,
                          int32_t kernel_size, int32_t stride, void* stream);
-int64_t edtts_dsconv_workspace_bytes(int32_t B, int32_t c_out, int32_t t_out);
+int64_t edtts_dsconv_workspace_bytes(int32_t B, int32_t c_in, int32_t c_out, int32_t t_out);
 
 /* --- unit-test hooks for single kernels (parity tests call them through the ABI) */
 /* y[rows,N] = x[rows,K] @ w[N,K]^T (+bias) in the given precision. */

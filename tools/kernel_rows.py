@@ -67,13 +67,13 @@ def cases():
     out.append(("inpaint_inject [256,800,80]", lambda: _lib.check(lib.edtts_inpaint_inject(_lib.ptr(xo), _lib.ptr(x), _lib.ptr(nz), _lib.ptr(co), B, T, T,
                                                                                          M, _lib.stream_ptr(dev))), 3 * n, 0))
     # ---- mel statistics / stitch / inverse mel
-    mel = torch.randn(B, M, T, generator=g, **f)
-    out.append(("normalize_mel [256,80,800]", lambda: E.normalize_mel(mel), 3 * n, 0))
-    mn, sd = torch.zeros(B, M, 1, **f), torch.ones(B, M, 1, **f)
-    out.append(("denormalize_mel [256,80,800]", lambda: E.denormalize_mel(mel, mn, sd), 2 * n, 0))
+    mel = torch.randn(B, T, M, generator=g, **f)
+    out.append(("normalize_mel [256,800,80]", lambda: E.normalize_mel(mel), 3 * n, 0))
+    mn, sd = torch.zeros(B, 1, M, **f), torch.ones(B, 1, M, **f)
+    out.append(("denormalize_mel [256,800,80]", lambda: E.denormalize_mel(mel, mn, sd), 2 * n, 0))
     st = E.MelStitcher(M, 4000, 800, 200, dev, batch=16)
     xs = torch.randn(16, 800, M, generator=g, **f)
-    m16, s16 = torch.zeros(16, M, 1, **f), torch.ones(16, M, 1, **f)
+    m16, s16 = torch.zeros(16, 1, M, **f), torch.ones(16, 1, M, **f)
     out.append(("stitch_add 16 x [800,80]", lambda: st.add_chunk(0, xs, m16, s16), 16 * 800 * M * 4 * 3, 0))
     out.append(("stitch_finalize 16 x [80,4000]", lambda: st.finalize(3800), 16 * M * 4000 * 4 * 3, 0))
     inv = E.InverseMelScale(n_stft=513, n_mels=M).to(dev)
@@ -99,6 +99,9 @@ def main():
     import torch
     once = "--once" in sys.argv
     cs = cases()
+    if "--only" in sys.argv:
+        pat = sys.argv[sys.argv.index("--only") + 1]
+        cs = [c for c in cs if pat in c[0]]
     torch.cuda.synchronize()
     rows = []
     for name, fn, nbytes, flops in cs:

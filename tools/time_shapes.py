@@ -15,7 +15,7 @@ inf = E.EdgeInference(cfg, E.DiffusionSchedule(cfg.diff_steps, device=dev), torc
 for spec in sys.argv[1:]:
     parts = spec.split(",")
     B, S = int(parts[0]), int(parts[1])
-    dec.batch_invariant = not (len(parts) > 2 and parts[2] == "flat")
+    pass
     idx = synth.synth_sem_idx(1, B, S).to(dev)
     xT = torch.randn(B, 2 * S, 80, device=dev)
     for _ in range(4):
