@@ -15,11 +15,11 @@ from .decoder import EdgeDiffusionDecoder
 from .encoder import SemanticEncoder
 from .inference import EdgeInference
 from .conv import DepthwiseSeparableConv
-from .audio import normalize_mel, denormalize_mel, InverseMelScale
+from .audio import normalize_mel, denormalize_mel, InverseMelScale, GriffinLim
 from .longform import MelStitcher, chunk_plan, crossfade_window, generate_longform
 from . import dist
 
 __version__ = "0.1.0"
 __all__ = ["CFG", "get_device", "set_seed", "DiffusionSchedule", "DPMSolverPP", "VectorQuantizer", "FSQ", "FSQEncoder", "EdgeDiffusionDecoder",
-           "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "normalize_mel", "denormalize_mel", "InverseMelScale", "MelStitcher",
+           "SemanticEncoder", "EdgeInference", "DepthwiseSeparableConv", "normalize_mel", "denormalize_mel", "InverseMelScale", "GriffinLim", "MelStitcher",
            "chunk_plan", "crossfade_window", "generate_longform", "dist"]

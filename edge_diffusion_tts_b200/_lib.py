@@ -83,6 +83,8 @@ SIGNATURES = {
     "edtts_fsq_forward": (C.c_int, [_p, _p, _i32, _i32, _p, _p, _i64, _p]),
     "edtts_fsq_decode": (C.c_int, [_p, _p, _i32, _p, _i64, _p]),
     "edtts_fsq_encoder": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _i32, _i32, _p, _p, _i64, _p]),
+    "edtts_griffinlim_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "edtts_griffinlim": (C.c_int, [_p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, C.c_float, C.c_float, _i64, _p]),
     "edtts_dsconv_forward": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _p]),
     "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "edtts_test_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),

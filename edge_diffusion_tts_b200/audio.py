@@ -5,7 +5,7 @@ the element-wise parts are bit-exact given the statistics.
 """
 from __future__ import annotations
 
-from typing import Tuple
+from typing import Optional, Tuple
 
 import torch
 
@@ -89,3 +89,61 @@ class InverseMelScale(torch.nn.Module):
         _lib.check(_lib.load().edtts_inverse_mel(_lib.ptr(self.pinv_fb), _lib.ptr(mel), _lib.ptr(out), mel.shape[0], freq, n_mels,
                                                  time, _lib.stream_ptr(mel.device)), "inverse_mel")
         return out.view(shape[:-2] + (freq, time))
+
+
+class GriffinLim(torch.nn.Module):
+    """torchaudio.transforms.GriffinLim as the reference uses it after the sampling path (generate_sample.py:135-141,
+    inference_pipeline.py:89,398: n_fft 1024, n_iter 32 / 100, win_length 1024, hop_length 160, power 2): same constructor
+    arguments, ``window`` buffer and ``forward(specgram [..., n_fft // 2 + 1, frames]) -> waveform [..., hop (frames - 1)]``.
+    The iteration (istft -> stft -> momentum phase update, torchaudio.functional.griffinlim) runs as two CUDA kernels per
+    iteration with shared-memory FFTs (edtts_griffinlim); the random initial phases are drawn with the same call
+    (``torch.rand(size, complex64)``) or injected with ``angles_init`` (extension, for parity tests)."""
+
+    def __init__(self, n_fft: int = 400, n_iter: int = 32, win_length: Optional[int] = None, hop_length: Optional[int] = None,
+                 window_fn=torch.hann_window, power: float = 2.0, wkwargs: Optional[dict] = None, momentum: float = 0.99,
+                 length: Optional[int] = None, rand_init: bool = True) -> None:
+        super().__init__()
+        if not (0 <= momentum < 1):
+            raise ValueError("momentum must be in the range [0, 1). Found: {}".format(momentum))
+        self.n_fft = n_fft
+        self.n_iter = n_iter
+        self.win_length = win_length if win_length is not None else n_fft
+        self.hop_length = hop_length if hop_length is not None else self.win_length // 2
+        window = window_fn(self.win_length) if wkwargs is None else window_fn(self.win_length, **wkwargs)
+        self.register_buffer("window", window)
+        self.length = length
+        self.power = power
+        self.momentum = momentum
+        self.rand_init = rand_init
+        self._ws = _lib.Workspace()
+
+    @torch.no_grad()
+    def forward(self, specgram: torch.Tensor, angles_init: Optional[torch.Tensor] = None) -> torch.Tensor:
+        lib = _lib.load()
+        if specgram.device.type != "cuda":
+            raise RuntimeError("GriffinLim runs on CUDA (B200) only; there is no CPU fallback")
+        n_freq = self.n_fft // 2 + 1
+        if specgram.dim() < 2 or specgram.shape[-2] != n_freq:
+            raise ValueError(f"specgram must be [..., {n_freq}, frames], got {tuple(specgram.shape)}")
+        if self.win_length > self.n_fft:
+            raise RuntimeError("win_length must not exceed n_fft")                      # as torch.stft
+        shape = specgram.shape
+        spec = _lib.f32(specgram).reshape(-1, n_freq, shape[-1])
+        B, _, F = spec.shape
+        L = self.hop_length * (F - 1)
+        if self.length is not None and self.length != L:
+            raise NotImplementedError(f"length={self.length}: only the natural length hop_length * (frames - 1) = {L} is supported")
+        dev = spec.device
+        if angles_init is None:                                                         # functional.griffinlim: rand / ones
+            angles_init = (torch.rand(spec.size(), dtype=torch.complex64, device=dev) if self.rand_init
+                           else torch.full(spec.size(), 1, dtype=torch.complex64, device=dev))
+        ang = torch.view_as_real(angles_init.to(device=dev, dtype=torch.complex64).reshape(B, n_freq, F).transpose(1, 2).contiguous())
+        pad = self.n_fft - self.win_length                                              # torch.stft pads the window to n_fft, centred
+        window = torch.nn.functional.pad(_lib.f32(self.window.to(dev)), (pad // 2, pad - pad // 2)).contiguous()
+        wave = torch.empty(B, L, dtype=torch.float32, device=dev)
+        nbytes = lib.edtts_griffinlim_workspace_bytes(B, F, self.n_fft)
+        ws = self._ws.get(nbytes, dev)
+        _lib.check(lib.edtts_griffinlim(_lib.ptr(spec), _lib.ptr(ang), _lib.ptr(window), _lib.ptr(wave), _lib.ptr(ws), nbytes, B, F,
+                                        self.n_fft, self.hop_length, self.n_iter, float(self.power), float(self.momentum), L,
+                                        _lib.stream_ptr(dev)), "griffinlim")
+        return wave.reshape(shape[:-2] + (L,))

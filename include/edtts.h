@@ -265,6 +265,17 @@ int edtts_stitch_finalize(const float* final_mel, const float* final_weights, fl
 int edtts_inverse_mel(const float* pinv_fb, const float* mel, float* spec_out, int32_t B, int32_t n_stft, int32_t n_mels,
                       int64_t T, void* stream);
 
+/* Griffin-Lim (torchaudio.transforms.GriffinLim at generate_sample.py:135-141, inference_pipeline.py:89,398; the algorithm is
+ * torchaudio.functional.griffinlim: n_iter rounds of istft -> stft (centred, reflect padding) -> momentum phase update, then a
+ * last istft).  spec [B, n_fft/2+1, frames] power spectrogram; angles_init [B, frames, n_fft/2+1][2] interleaved complex
+ * initial phases (NOT normalised: torch.rand / ones, as the reference draws them); window [n_fft] (the win_length window
+ * zero-padded, centred); wave_out [B, out_len], out_len = hop (frames - 1) (0 selects it; a longer out_len is zero-filled).
+ * n_fft: a power of two in [64, 4096]. */
+int edtts_griffinlim(const float* spec, const float* angles_init, const float* window, float* wave_out, void* workspace,
+                     int64_t workspace_bytes, int32_t B, int32_t frames, int32_t n_fft, int32_t hop, int32_t n_iter, float power,
+                     float momentum, int64_t out_len, void* stream);
+int64_t edtts_griffinlim_workspace_bytes(int32_t B, int32_t frames, int32_t n_fft);
+
 /* --- FSQ (models/fsq.py:18-132), the reference's alternative quantiser ------- */
 /* forward (fsq.py:84-108): z [rows, dim] -> z_q = tanh(z) + (quantise(tanh(z)) - tanh(z)) and the flat index per row
  * (basis = cumprod([1] + levels[:-1]), first dimension fastest).  levels is a HOST array of dim (<= 8) ints.

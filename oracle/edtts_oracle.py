@@ -641,3 +641,29 @@ def inverse_mel_scale(fb: Tensor, melspec: Tensor, driver: str = "gels") -> Tens
 
 def to_dtype(sd: State, dtype) -> State:
     return {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ----------------------------------------------------------------------------
+# torchaudio.functional.griffinlim (third-party: torchaudio, in-image 2.11; the reference calls it through
+# T.GriffinLim at generate_sample.py:135-141 and inference_pipeline.py:89,398)  -- SURVEY.md section 8f-3
+# ----------------------------------------------------------------------------
+def griffinlim(spec: Tensor, window: Tensor, n_fft: int, hop_length: int, win_length: int, power: float, n_iter: int,
+               momentum: float, angles_init: Tensor) -> Tensor:
+    """The published algorithm with the initial phases injected (the library draws torch.rand(size, complex64)):
+    spec [..., n_fft // 2 + 1, frames] -> waveform [..., hop_length * (frames - 1)]."""
+    mom = momentum / (1 + momentum)
+    shape = spec.shape
+    mag = spec.reshape(-1, shape[-2], shape[-1]).pow(1 / power)
+    angles = angles_init.reshape(mag.shape).to(torch.complex64)
+    tprev = torch.tensor(0.0, dtype=mag.dtype)
+    for _ in range(n_iter):
+        inverse = torch.istft(mag * angles, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window)
+        rebuilt = torch.stft(inverse, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window, center=True,
+                             pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
+        angles = rebuilt
+        if mom:
+            angles = angles - tprev * mom
+        angles = angles / (angles.abs() + 1e-16)
+        tprev = rebuilt
+    wave = torch.istft(mag * angles, n_fft=n_fft, hop_length=hop_length, win_length=win_length, window=window)
+    return wave.reshape(shape[:-2] + wave.shape[-1:])

@@ -60,6 +60,29 @@ def make_fsq(ref, meta):
     torch.save(dict(meta=meta, cases=cases), os.path.join(OUT, "fsq.pt"))
 
 
+def make_griffinlim(ref, meta):
+    """torchaudio.transforms.GriffinLim as the reference configures it (generate_sample.py:135-141: n_fft 1024, n_iter 32,
+    win_length 1024, hop_length 160, power 2), the library's torch.rand initial phases captured by patching torch.rand for the
+    call; plus a short-window / odd-size case."""
+    import torchaudio.transforms as T
+    cases = {}
+    for name, (n_fft, win, hop, n_iter, frames, B) in dict(reference=(1024, 1024, 160, 32, 60, 2), small=(256, 200, 64, 8, 33, 3),
+                                                           one_iter=(1024, 1024, 160, 1, 40, 1), no_iter=(512, 512, 128, 0, 20, 1)).items():
+        g = torch.Generator().manual_seed(31 + frames)
+        spec = torch.rand(B, n_fft // 2 + 1, frames, generator=g) ** 2 * 3.0
+        init = torch.rand(B, n_fft // 2 + 1, frames, 2, generator=g)
+        init = torch.view_as_complex(init.contiguous())
+        tr = T.GriffinLim(n_fft=n_fft, n_iter=n_iter, win_length=win, hop_length=hop, power=2.0)
+        real = torch.rand
+        torch.rand = lambda *a, **k: init.clone()
+        try:
+            wave = tr(spec)
+        finally:
+            torch.rand = real
+        cases[name] = dict(cfg=(n_fft, win, hop, n_iter, frames, B), seed=31 + frames, wave=wave)
+    torch.save(dict(meta=meta, cases=cases), os.path.join(OUT, "griffinlim.pt"))
+
+
 def make_fsq_encoder(ref, meta):
     """FSQEncoder.forward / encode / decode of the reference (models/fsq.py:135-222) with synthetic projections, and the
     reference SemanticEncoder's quantiser choice (encoder.py:49-57) recorded as state-dict keys."""
@@ -164,6 +187,9 @@ def main(only=None):
         return
     if only == "fsq":
         make_fsq(ref, meta)
+        return
+    if only == "griffinlim":
+        make_griffinlim(ref, meta)
         return
     if only == "fsq_encoder":
         make_fsq_encoder(ref, meta)
@@ -280,6 +306,7 @@ def main(only=None):
     make_dpm(ref, meta)
     make_fsq(ref, meta)
     make_fsq_encoder(ref, meta)
+    make_griffinlim(ref, meta)
     make_inpaint(ref, meta)
     make_longform(ref, meta)
     make_invmel(ref, meta)
