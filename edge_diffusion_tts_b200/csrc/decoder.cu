@@ -39,81 +39,83 @@ int launch_attn_simt(const AttnArgs& a, int B, cudaStream_t stream) {
 // ---------------------------------------------------------------------------
 // Conditioning: t -> sinusoid -> Linear -> GELU -> Linear (+ step_emb) -> cond,
 // then the 8 AdaLayerNorm projections (decoder.py:77-80, transformer.py:64-66).
-// One block per CU utterances, so that every weight row fetched from L2 serves CU
-// dot products; a thread owns one output feature for 4 utterances at a time.
+// One block per CU utterances and per quarter of one AdaLayerNorm projection (the small time MLP is recomputed per block:
+// 2 x 102 KB of weights from L2).  A WARP owns an output feature: the lanes split the 160-long weight row (one coalesced
+// 640-byte read, 5 values per lane), multiply it with the CU input rows in shared memory and reduce with shuffles -- the
+// weight read latency of several features overlaps (unrolled), instead of one thread walking a row serially.  A row's
+// result does not depend on its position in the batch (fixed lane partition, fixed shuffle tree).
 // ---------------------------------------------------------------------------
 constexpr int CU = 8;
+constexpr int CSPLIT = 4;                 // blocks per AdaLayerNorm projection (80 of its 320 outputs each)
 
-// acc[u] = bias + sum_k w[k] * x[u0 + u][k], u < 4; w is one nn.Linear row (160 floats)
-__device__ __forceinline__ void dot160x4(const float* __restrict__ w, const float (*x)[H], int u0, float bias, float* acc) {
-  float a0 = bias, a1 = bias, a2 = bias, a3 = bias;
-#pragma unroll 4
-  for (int k = 0; k < H; k += 4) {
-    const float4 wv = *reinterpret_cast<const float4*>(w + k);
-    const float4 x0 = *reinterpret_cast<const float4*>(&x[u0][k]);
-    const float4 x1 = *reinterpret_cast<const float4*>(&x[u0 + 1][k]);
-    const float4 x2 = *reinterpret_cast<const float4*>(&x[u0 + 2][k]);
-    const float4 x3 = *reinterpret_cast<const float4*>(&x[u0 + 3][k]);
-    a0 = fmaf(wv.x, x0.x, a0); a0 = fmaf(wv.y, x0.y, a0); a0 = fmaf(wv.z, x0.z, a0); a0 = fmaf(wv.w, x0.w, a0);
-    a1 = fmaf(wv.x, x1.x, a1); a1 = fmaf(wv.y, x1.y, a1); a1 = fmaf(wv.z, x1.z, a1); a1 = fmaf(wv.w, x1.w, a1);
-    a2 = fmaf(wv.x, x2.x, a2); a2 = fmaf(wv.y, x2.y, a2); a2 = fmaf(wv.z, x2.z, a2); a2 = fmaf(wv.w, x2.w, a2);
-    a3 = fmaf(wv.x, x3.x, a3); a3 = fmaf(wv.y, x3.y, a3); a3 = fmaf(wv.z, x3.z, a3); a3 = fmaf(wv.w, x3.w, a3);
+constexpr int CTHREADS = 1024, CWARPS = CTHREADS / 32;
+
+// One stage of NOUT_ outputs starting at j0: warp w owns outputs j0 + w, j0 + w + 32, ...  ALL weight values of the warp's
+// outputs are requested before the first dot product (the rows come from L2 or HBM: one exposed latency per stage instead of
+// one per output); lane l takes k = l, l + 32, ..., l + 128 of a row.  fn(j, u, value) receives the dot product (without
+// bias) of output j for row u in lane u.
+template <int NOUT_, typename F>
+__device__ __forceinline__ void warp_stage(const float* __restrict__ W, int j0, const float (*x)[H], int warp, int lane, F fn) {
+  constexpr int PER = (NOUT_ + CWARPS - 1) / CWARPS;
+  float wv[PER][5];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = warp + CWARPS * i;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) wv[i][q] = j < NOUT_ ? __ldg(W + (int64_t)(j0 + j) * H + lane + 32 * q) : 0.f;
   }
-  acc[0] = a0; acc[1] = a1; acc[2] = a2; acc[3] = a3;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) {
+    const int j = warp + CWARPS * i;
+    if (j >= NOUT_) break;                                // warp-uniform
+    float mine = 0.f;
+#pragma unroll
+    for (int u = 0; u < CU; ++u) {
+      float p = 0.f;
+#pragma unroll
+      for (int q = 0; q < 5; ++q) p = fmaf(wv[i][q], x[u][lane + 32 * q], p);
+      p = warp_sum(p);
+      mine = lane == u ? p : mine;
+    }
+    if (lane < CU) fn(j0 + j, lane, mine);
+  }
 }
 
-__global__ void __launch_bounds__(256) cond_kernel(const edtts_decoder_weights w, const int64_t* __restrict__ t,
-                                                   const int64_t* __restrict__ step_idx, float* __restrict__ cond_out,
-                                                   float* __restrict__ mod_out, int B) {
+__global__ void __launch_bounds__(CTHREADS) cond_kernel(const edtts_decoder_weights w, const int64_t* __restrict__ t,
+                                                        const int64_t* __restrict__ step_idx, float* __restrict__ cond_out,
+                                                        float* __restrict__ mod_out, int B) {
   __shared__ __align__(16) float e[CU][H], h1[CU][H], c[CU][H];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b0 = blockIdx.x * CU;
   const int nu = min(CU, B - b0);
-  for (int i = tid; i < CU * (H / 2); i += 256) {
+  for (int i = tid; i < CU * (H / 2); i += CTHREADS) {
     const int u = i / (H / 2), k = i % (H / 2);
     const float arg = u < nu ? (float)t[b0 + u] * w.time_freqs[k] : 0.f;   // embeddings.py:42-43
     e[u][k] = sinf(arg);
     e[u][k + H / 2] = cosf(arg);
   }
   __syncthreads();
-  for (int it = tid; it < H * (CU / 4); it += 256) {
-    const int o = it % H, u0 = (it / H) * 4;
-    float acc[4];
-    dot160x4(w.time1_w + o * H, e, u0, w.time1_b[o], acc);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) h1[u0 + u][o] = gelu_erf(acc[u]);
-  }
+  warp_stage<H>(w.time1_w, 0, e, warp, lane, [&](int o, int u, float v) { h1[u][o] = gelu_erf(v + w.time1_b[o]); });
   __syncthreads();
-  for (int it = tid; it < H * (CU / 4); it += 256) {
-    const int o = it % H, u0 = (it / H) * 4;
-    float acc[4];
-    dot160x4(w.time3_w + o * H, h1, u0, w.time3_b[o], acc);
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float s = acc[u];
-      if (u0 + u < nu) {
-        if (step_idx) s += w.step_emb[step_idx[b0 + u0 + u] * H + o];
-        if (cond_out && blockIdx.y == 0) cond_out[(int64_t)(b0 + u0 + u) * H + o] = s;
-      }
-      c[u0 + u][o] = s;
+  warp_stage<H>(w.time3_w, 0, h1, warp, lane, [&](int o, int u, float v) {
+    float s = v + w.time3_b[o];
+    if (u < nu) {
+      if (step_idx) s += w.step_emb[step_idx[b0 + u] * H + o];
+      if (cond_out && blockIdx.y == 0) cond_out[(int64_t)(b0 + u) * H + o] = s;
     }
-  }
+    c[u][o] = s;
+  });
   __syncthreads();
   if (!mod_out) return;
-  // blockIdx.y selects one of the 8 AdaLayerNorms (the small time MLP above is recomputed per block)
+  // blockIdx.y: which of the 8 AdaLayerNorms, and which quarter of its 2 H outputs
   constexpr int NOUT = 2 * H;
-  for (int it = tid; it < NOUT * (CU / 4); it += 256) {
-    const int j = it % NOUT, u0 = (it / NOUT) * 4;
-    const int which = blockIdx.y;
-    const edtts_layer_weights& L = w.layers[which >> 1];
-    const float* pw = (which & 1) ? L.norm3_proj_w : L.norm1_proj_w;
-    const float* pb = (which & 1) ? L.norm3_proj_b : L.norm1_proj_b;
-    float acc[4];
-    dot160x4(pw + j * H, c, u0, pb[j], acc);
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (u0 + u < nu) mod_out[((int64_t)(b0 + u0 + u) * 2 * NL + which) * 2 * H + j] = acc[u];
-  }
+  const int which = blockIdx.y / CSPLIT, part = blockIdx.y % CSPLIT;
+  const edtts_layer_weights& L = w.layers[which >> 1];
+  const float* pw = (which & 1) ? L.norm3_proj_w : L.norm1_proj_w;
+  const float* pb = (which & 1) ? L.norm3_proj_b : L.norm1_proj_b;
+  warp_stage<NOUT / CSPLIT>(pw, part * (NOUT / CSPLIT), c, warp, lane, [&](int j, int u, float v) {
+    if (u < nu) mod_out[((int64_t)(b0 + u) * 2 * NL + which) * 2 * H + j] = v + pb[j];
+  });
 }
 
 // ctx[b,s,:] = token_emb[sem_idx[b,s]] + pe[s]   (decoder.py:88,93)
@@ -139,7 +141,7 @@ extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t*
                                   float* cond_out, float* mod_out, int32_t B, void* stream) {
   EDTTS_REQUIRE(w && t && B > 0 && (cond_out || mod_out), EDTTS_EINVAL, "cond_prepare: null argument");
   LaunchScope ls(KC_COND, as_stream(stream));
-  cond_kernel<<<dim3((B + CU - 1) / CU, mod_out ? 2 * NL : 1), 256, 0, as_stream(stream)>>>(*w, t, step_idx, cond_out, mod_out, B);
+  cond_kernel<<<dim3((B + CU - 1) / CU, mod_out ? 2 * NL * CSPLIT : 1), CTHREADS, 0, as_stream(stream)>>>(*w, t, step_idx, cond_out, mod_out, B);
   return check_launch("cond_kernel");
 }
 
