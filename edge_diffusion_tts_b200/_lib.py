@@ -58,7 +58,8 @@ SIGNATURES = {
     "edtts_prof_enable": (C.c_int, [C.c_int]),
     "edtts_prof_collect": (C.c_int, [_p, _p, C.c_int]),
     "edtts_vq_argmin": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
-    "edtts_vq_workspace_bytes": (_i64, [_i32]),
+    "edtts_vq_workspace_bytes": (_i64, [_i32, _i32]),
+    "edtts_encoder_proj_workspace_bytes": (_i64, [_i64, _i32]),
     "edtts_vq_gather_ste": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "edtts_vq_bincount": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "edtts_encoder_proj": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),

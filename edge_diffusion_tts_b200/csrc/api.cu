@@ -9,6 +9,8 @@
 #include "gemm_simt.cuh"
 #include "attention_simt.cuh"
 #include "tc_path.cuh"
+#include "tf32x3.cuh"
+#include <stdlib.h>
 
 namespace edtts {
 
@@ -131,14 +133,36 @@ extern "C" int edtts_device_supported(void) {
   return major == 10 ? 1 : 0;
 }
 
-// SemanticEncoder.proj (models/encoder.py:41-46): Linear(768,128) -> GELU ->
-// LayerNorm(128) -> Linear(128,128); the LayerNorm is the prologue of the second GEMM.
+// SemanticEncoder.proj (models/encoder.py:41-46): Linear(768,128) -> GELU -> LayerNorm(128) -> Linear(128,128).
+// Tensor-core route (in_dim % 4 == 0): two launches of the tf32 x 3 GEMM kernel -- Linear + GELU + LayerNorm fused in the
+// first one's epilogue, the second Linear on its output; the weight images are packed per call into the workspace.
+// CUDA-core route otherwise (the LayerNorm is the prologue of the second FFMA GEMM).
+static bool proj_tc(int in_dim) {
+  static const bool off = getenv("EDTTS_PROJ_SIMT") != nullptr;       // development: force the CUDA-core route
+  return !off && in_dim % 4 == 0;
+}
+extern "C" int64_t edtts_encoder_proj_workspace_bytes(int64_t rows, int32_t in_dim) {
+  const int D = EDTTS_SEMANTIC_DIM;
+  return align_up(rows * D * 4, 256) + align_up(t3::w_image_bytes(in_dim, D), 256) + align_up(t3::w_image_bytes(D, D), 256);
+}
 extern "C" int edtts_encoder_proj(const float* h, const float* w0, const float* b0, const float* ln_w,
                                   const float* ln_b, const float* w3, const float* b3, float* z_out, float* workspace,
                                   int64_t rows, int32_t in_dim, void* stream) {
   EDTTS_REQUIRE(h && w0 && b0 && ln_w && ln_b && w3 && b3 && z_out && workspace && rows > 0, EDTTS_EINVAL,
                 "encoder_proj: null argument");
   const int D = EDTTS_SEMANTIC_DIM;
+  if (proj_tc(in_dim)) {
+    cudaStream_t st = as_stream(stream);
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* y = reinterpret_cast<float*>(ws);
+    float* img0 = reinterpret_cast<float*>(ws + align_up(rows * D * 4, 256));
+    float* img3 = reinterpret_cast<float*>(ws + align_up(rows * D * 4, 256) + align_up(t3::w_image_bytes(in_dim, D), 256));
+    int rc = t3::pack_w_tf32(w0, img0, in_dim, D, in_dim, st);
+    if (!rc) rc = t3::pack_w_tf32(w3, img3, D, D, D, st);
+    if (!rc) rc = t3::launch_t3_linear(h, rows, in_dim, in_dim, img0, b0, D, y, D, t3::EPI_T3_GELU_LN, ln_w, ln_b, 1e-5f, st);
+    if (!rc) rc = t3::launch_t3_linear(y, rows, D, D, img3, b3, D, z_out, D, t3::EPI_T3_NONE, nullptr, nullptr, 0.f, st);
+    return rc;
+  }
   GemmArgs a;
   a.A = h; a.rows = rows; a.K = in_dim; a.lda = in_dim; a.W = w0; a.N = D; a.bias = b0; a.out = workspace; a.ldo = D;
   a.epi = EPI_GELU;

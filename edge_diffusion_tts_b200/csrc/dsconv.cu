@@ -29,6 +29,7 @@
 // Kernel 3: normalise + affine + GELU in place.
 #include "common.cuh"
 #include "umma.cuh"
+#include "tf32x3.cuh"
 #include <stdlib.h>
 
 
@@ -135,30 +136,11 @@ __global__ void __launch_bounds__(256) dsconv_norm_gelu_kernel(float* __restrict
 // =====================================================================================================================
 namespace dctc {
 using namespace tc;
+using namespace t3;
 
-constexpr int TM = 128;          // output frames per tile (MMA M)
-constexpr int KC = 32;           // input channels per chunk
 constexpr int THREADS = 256;
-constexpr int A_BYTES = (KC / 4) * TM * 16;          // one operand half (hi or lo): 8 slabs of 128 rows x 16 B
+constexpr int A_BYTES = A_HALF;
 
-// Instruction descriptor, kind::tf32: D = f32 (1 << 4), A = B = tf32 (2 << 7, 2 << 10), both K-major, N >> 3, M >> 4.
-__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M_, uint32_t N_) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((N_ >> 3) << 17) | ((M_ >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
-      : "memory");
-}
-// 32 lanes x 4 consecutive columns, NOT waited for
-__device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, float* v) {
-  uint32_t r0, r1, r2, r3;
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
-  v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-}
 template <int K>
 __device__ __forceinline__ float taps(const float* __restrict__ wr, const float* __restrict__ xr, int k) {
   float s = 0.f;
@@ -169,26 +151,6 @@ __device__ __forceinline__ float taps(const float* __restrict__ wr, const float*
     for (int j = 0; j < k; ++j) s = fmaf(wr[j], xr[j], s);
   }
   return s;
-}
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
-
-// Weight image: per 32-channel chunk c: [hi | lo][slab s < 8][n < c_out][4 floats] = element (n, 32 c + 4 s + j); channels
-// beyond c_in are zero.
-__global__ void pack_pw_kernel(const float* __restrict__ pw, float* __restrict__ img, int c_in, int c_out, int nchunk) {
-  const int total = nchunk * 8 * c_out * 4;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int j = i & 3, n = (i >> 2) % c_out, s = ((i >> 2) / c_out) & 7, c = (i >> 2) / (c_out * 8);
-    const int k = KC * c + 4 * s + j;
-    const float w = k < c_in ? pw[(int64_t)n * c_in + k] : 0.f;
-    const float hi = tf32_rna(w);
-    const int64_t base = (int64_t)c * (2 * 8 * c_out * 4);
-    img[base + ((int64_t)s * c_out + n) * 4 + j] = hi;
-    img[base + 8 * c_out * 4 + ((int64_t)s * c_out + n) * 4 + j] = w - hi;
-  }
 }
 
 struct Args {
@@ -488,9 +450,7 @@ extern "C" int edtts_dsconv_forward(const float* x, const float* dw_w, const flo
     }
     {
       LaunchScope ls(KC_DSCONV, st);
-      const int total = a.nchunk * 8 * c_out * 4;
-      pack_pw_kernel<<<(total + 255) / 256, 256, 0, st>>>(pw_w, wimg, c_in, c_out, a.nchunk);
-      if (int rc = check_launch("dsconv pack")) return rc;
+      if (int rc = pack_w_tf32(pw_w, wimg, c_in, c_out, c_in, st)) return rc;
     }
     {
       LaunchScope ls(KC_DSCONV, st);

@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(256) fsq_encoder_kernel(const float* __restric
                                                           int64_t rows) {
   extern __shared__ float sm[];
   float* swd = sm;                       // [dim][D]
-  float* swu = sm + p.dim * D;           // [D][dim] as stored by nn.Linear(dim, D)
+  float* swu = sm + p.dim * D;           // [dim][D]: transposed copy of nn.Linear(dim, D).weight (conflict-free lane reads)
   float* sbu = swu + p.dim * D;          // [D]
   for (int i = threadIdx.x; i < p.dim * D; i += blockDim.x) {
     swd[i] = wd ? wd[i] : 0.f;
-    swu[i] = wu[i];
+    swu[(i % p.dim) * D + i / p.dim] = wu[i];
   }
   for (int i = threadIdx.x; i < D; i += blockDim.x) sbu[i] = bu[i];
   __syncthreads();
@@ -98,17 +98,31 @@ __global__ void __launch_bounds__(256) fsq_encoder_kernel(const float* __restric
           acc[d] = fmaf(v.x, w.x, fmaf(v.y, w.y, fmaf(v.z, w.z, fmaf(v.w, w.w, acc[d]))));
         }
       }
+      // lane d quantises dimension d (tanh, rounding, straight-through value); the 8 results travel back by shuffles
+      float mine = 0.f;
 #pragma unroll
       for (int d = 0; d < FSQ_MAX_DIM; ++d) {
         if (d >= p.dim) break;
-        const float lv = (float)p.levels[d];
+        const float sd = warp_sum(acc[d]);
+        mine = lane == d ? sd : mine;
+      }
+      float q_mine = 0.f;
+      int code_mine = 0;
+      if (lane < p.dim) {
+        const float lv = (float)p.levels[lane];
         const float half = __fdiv_rn(__fsub_rn(lv, 1.0f), 2.0f);
-        const float zb = tanhf(warp_sum(acc[d]) + bd[d]);
+        const float zb = tanhf(mine + bd[lane]);
         float s = rintf(__fmul_rn(__fadd_rn(zb, 1.0f), half));
         s = fminf(fmaxf(s, 0.0f), __fsub_rn(lv, 1.0f));
         const float out = __fsub_rn(__fdiv_rn(s, half), 1.0f);
-        q[d] = __fadd_rn(zb, __fsub_rn(out, zb));                         // straight-through value, fsq.py:104
-        flat += (long long)rintf(__fmul_rn(__fadd_rn(q[d], 1.0f), half)) * p.basis[d];
+        q_mine = __fadd_rn(zb, __fsub_rn(out, zb));                       // straight-through value, fsq.py:104
+        code_mine = (int)rintf(__fmul_rn(__fadd_rn(q_mine, 1.0f), half));
+      }
+#pragma unroll
+      for (int d = 0; d < FSQ_MAX_DIM; ++d) {
+        if (d >= p.dim) break;
+        q[d] = __shfl_sync(0xffffffffu, q_mine, d);
+        flat += (long long)__shfl_sync(0xffffffffu, code_mine, d) * p.basis[d];
       }
       if (idx_out && lane == 0) idx_out[r] = flat;
     } else {
@@ -131,7 +145,7 @@ __global__ void __launch_bounds__(256) fsq_encoder_kernel(const float* __restric
 #pragma unroll
           for (int d = 0; d < FSQ_MAX_DIM; ++d) {
             if (d >= p.dim) break;
-            a = fmaf(q[d], swu[(4 * c + j) * p.dim + d], a);
+            a = fmaf(q[d], swu[d * D + 4 * c + j], a);
           }
           o[j] = a;
         }

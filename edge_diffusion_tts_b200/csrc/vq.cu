@@ -14,6 +14,7 @@
 // the reference's fp32 argmin equals it on every seed tested (tests/test_gpu_vq.py
 // checks against both the fp32 oracle and its fp64 restatement).
 #include "common.cuh"
+#include "tf32x3.cuh"
 
 namespace edtts {
 
@@ -209,7 +210,9 @@ __global__ void vq_bincount_kernel(const int64_t* __restrict__ idx, int32_t* __r
 
 using namespace edtts;
 
-extern "C" int64_t edtts_vq_workspace_bytes(int32_t codebook_size) { return align_up((int64_t)codebook_size * 4, 256); }
+extern "C" int64_t edtts_vq_workspace_bytes(int32_t codebook_size, int32_t dim) {
+  return align_up((int64_t)codebook_size * 4, 256) + (t3::t3_vq_ok(dim, codebook_size) ? t3::t3_vq_image_bytes(dim) : 0);
+}
 
 extern "C" int edtts_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, int64_t rows, int32_t dim,
                                int32_t codebook_size, void* workspace, void* stream) {
@@ -226,6 +229,9 @@ extern "C" int edtts_vq_argmin(const float* z, const float* codebook, int64_t* i
     rc = check_launch("vq_code_norms");
   }
   if (rc) return rc;
+  if (t3::t3_vq_ok(dim, codebook_size))       // distance product on the tensor cores (tf32 x 3), same candidates / re-rank
+    return t3::launch_t3_vq(z, codebook, ee, reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up((int64_t)codebook_size * 4, 256)),
+                            idx_out, rows, dim, codebook_size, st);
   LaunchScope ls(KC_VQ, st);
   vq_argmin_kernel<<<(unsigned)((rows + VQ_BM - 1) / VQ_BM), VQ_THREADS, 0, st>>>(z, codebook, ee, idx_out, rows, dim,
                                                                                  codebook_size);

@@ -56,7 +56,7 @@ class SemanticEncoder(nn.Module):
         z = torch.empty(B, S, D, dtype=torch.float32, device=h.device)
         if B * S == 0:
             return z
-        ws = self._ws.get(B * S * D * 4, h.device)
+        ws = self._ws.get(lib.edtts_encoder_proj_workspace_bytes(B * S, Din), h.device)
         p = self.proj
         W = [_lib.f32(t.detach()) for t in (p[0].weight, p[0].bias, p[2].weight, p[2].bias, p[3].weight, p[3].bias)]
         _lib.check(lib.edtts_encoder_proj(_lib.ptr(h), *[_lib.ptr(t) for t in W], _lib.ptr(z), _lib.ptr(ws), B * S,

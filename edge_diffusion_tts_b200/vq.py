@@ -34,7 +34,7 @@ class VectorQuantizer(nn.Module):
         idx = torch.empty(B, T, dtype=torch.int64, device=z.device)
         if B * T == 0:
             return idx
-        ws = self._ws.get(lib.edtts_vq_workspace_bytes(self.codebook_size), z.device)
+        ws = self._ws.get(lib.edtts_vq_workspace_bytes(self.codebook_size, D), z.device)
         cb = _lib.f32(self.codebook.weight.detach())
         _lib.check(lib.edtts_vq_argmin(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(idx), B * T, D, self.codebook_size,
                                        _lib.ptr(ws), _lib.stream_ptr(z.device)), "vq_argmin")

@@ -133,10 +133,10 @@ int edtts_prof_collect(double* ms_out, uint64_t* n_out, int n);
 /* --- VectorQuantizer (models/vq.py) --------------------------------------- */
 /* vq.py:75-82 / :153-159: idx[r] = argmin_k ||z_r - E_k||^2, first minimum.
  * fp32 FFMA distances; near-ties are re-ranked in fp64 so the result equals the
- * exact argmin.  workspace: edtts_vq_workspace_bytes(K) bytes. */
+ * exact argmin.  workspace: edtts_vq_workspace_bytes(K, D) bytes. */
 int edtts_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, int64_t rows, int32_t dim,
                     int32_t codebook_size, void* workspace, void* stream);
-int64_t edtts_vq_workspace_bytes(int32_t codebook_size);
+int64_t edtts_vq_workspace_bytes(int32_t codebook_size, int32_t dim);
 /* vq.py:83,98: z_q = z + (E[idx] - z)  (straight-through rounding included). */
 int edtts_vq_gather_ste(const float* z, const float* codebook, const int64_t* idx, float* zq_out, int64_t rows,
                         int32_t dim, int32_t codebook_size, void* stream);
@@ -144,7 +144,9 @@ int edtts_vq_gather_ste(const float* z, const float* codebook, const int64_t* id
 int edtts_vq_bincount(const int64_t* idx, int32_t* counts_out, int64_t rows, int32_t codebook_size, void* stream);
 
 /* --- SemanticEncoder.proj (models/encoder.py:41-46) ------------------------ */
-/* z = Linear(128,128)(LayerNorm(GELU(Linear(768,128)(h)))); workspace rows*128 floats. */
+/* z = Linear(128,128)(LayerNorm(GELU(Linear(768,128)(h)))); workspace: edtts_encoder_proj_workspace_bytes(rows, in_dim)
+ * (the intermediate rows and, for the tensor-core route, the tf32 hi | lo weight images packed per call). */
+int64_t edtts_encoder_proj_workspace_bytes(int64_t rows, int32_t in_dim);
 int edtts_encoder_proj(const float* h, const float* w0, const float* b0, const float* ln_w, const float* ln_b,
                        const float* w3, const float* b3, float* z_out, float* workspace, int64_t rows,
                        int32_t in_dim, void* stream);

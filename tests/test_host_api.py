@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
         assert hasattr(lib, n), n
     assert lib.edtts_version() >= 100
     assert lib.edtts_packed_bf16_bytes() >= 0
-    assert lib.edtts_vq_workspace_bytes(512) >= 2048
+    assert lib.edtts_vq_workspace_bytes(512, 128) >= 2048
     assert lib.edtts_decoder_workspace_bytes(2, 100, 50, 0) >= 2 * 100 * 800 * 4
     assert lib.edtts_context_workspace_bytes(2, 50) >= 2 * 50 * 240 * 4
 
