@@ -60,6 +60,11 @@ SIGNATURES = {
     "edtts_vq_argmin": (C.c_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p]),
     "edtts_vq_workspace_bytes": (_i64, [_i32, _i32]),
     "edtts_encoder_proj_workspace_bytes": (_i64, [_i64, _i32]),
+    "edtts_encoder_proj_image_bytes": (_i64, [_i32]),
+    "edtts_encoder_proj_pack": (C.c_int, [_p, _p, _i32, _p, _p]),
+    "edtts_encoder_proj_packed": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),
+    "edtts_vq_pack": (C.c_int, [_p, _i32, _i32, _p, _p]),
+    "edtts_vq_argmin_packed": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "edtts_vq_gather_ste": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _p]),
     "edtts_vq_bincount": (C.c_int, [_p, _p, _i64, _i32, _p]),
     "edtts_encoder_proj": (C.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _p]),

@@ -174,6 +174,35 @@ extern "C" int edtts_encoder_proj(const float* h, const float* w0, const float* 
   return launch_gemm_simt(b, as_stream(stream));
 }
 
+// The two weight images of the tensor-core route (tf32 hi | lo, core-matrix layout), packed once per weight set:
+// images_out holds edtts_encoder_proj_image_bytes(in_dim) bytes.
+extern "C" int64_t edtts_encoder_proj_image_bytes(int32_t in_dim) {
+  const int D = EDTTS_SEMANTIC_DIM;
+  return align_up(t3::w_image_bytes(in_dim, D), 256) + align_up(t3::w_image_bytes(D, D), 256);
+}
+extern "C" int edtts_encoder_proj_pack(const float* w0, const float* w3, int32_t in_dim, void* images_out, void* stream) {
+  EDTTS_REQUIRE(w0 && w3 && images_out && in_dim > 0, EDTTS_EINVAL, "encoder_proj_pack: null argument");
+  const int D = EDTTS_SEMANTIC_DIM;
+  char* img = reinterpret_cast<char*>(images_out);
+  int rc = t3::pack_w_tf32(w0, reinterpret_cast<float*>(img), in_dim, D, in_dim, as_stream(stream));
+  if (!rc) rc = t3::pack_w_tf32(w3, reinterpret_cast<float*>(img + align_up(t3::w_image_bytes(in_dim, D), 256)), D, D, D, as_stream(stream));
+  return rc;
+}
+// edtts_encoder_proj with images packed earlier by edtts_encoder_proj_pack (tensor-core route only: in_dim % 4 == 0);
+// workspace: rows * 128 floats.
+extern "C" int edtts_encoder_proj_packed(const float* h, const void* images, const float* b0, const float* ln_w, const float* ln_b,
+                                         const float* b3, float* z_out, float* workspace, int64_t rows, int32_t in_dim, void* stream) {
+  EDTTS_REQUIRE(h && images && b0 && ln_w && ln_b && b3 && z_out && workspace && rows > 0, EDTTS_EINVAL, "encoder_proj_packed: null argument");
+  EDTTS_REQUIRE(in_dim % 4 == 0, EDTTS_ENOTSUP, "encoder_proj_packed: in_dim=%d (multiple of 4)", in_dim);
+  const int D = EDTTS_SEMANTIC_DIM;
+  const char* img = reinterpret_cast<const char*>(images);
+  const float* img0 = reinterpret_cast<const float*>(img);
+  const float* img3 = reinterpret_cast<const float*>(img + align_up(t3::w_image_bytes(in_dim, D), 256));
+  int rc = t3::launch_t3_linear(h, rows, in_dim, in_dim, img0, b0, D, workspace, D, t3::EPI_T3_GELU_LN, ln_w, ln_b, 1e-5f, as_stream(stream));
+  if (!rc) rc = t3::launch_t3_linear(workspace, rows, D, D, img3, b3, D, z_out, D, t3::EPI_T3_NONE, nullptr, nullptr, 0.f, as_stream(stream));
+  return rc;
+}
+
 extern "C" int edtts_test_linear(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K,
                                  int32_t N, int32_t precision, void* stream) {
   EDTTS_REQUIRE(x && w && y && rows > 0, EDTTS_EINVAL, "test_linear: null argument");

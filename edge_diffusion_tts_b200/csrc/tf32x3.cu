@@ -396,16 +396,19 @@ bool t3_vq_ok(int D, int K) {
 }
 int64_t t3_vq_image_bytes(int D) { return (int64_t)((D + KC - 1) / KC) * 4 * 8 * 256 * 16; }
 
-int launch_t3_vq(const float* z, const float* E, const float* ee, float* wimg, int64_t* idx, int64_t rows, int D, int K, cudaStream_t st) {
+int pack_codebook(const float* E, float* wimg, int D, int K, cudaStream_t st) {
+  const int nchunk = (D + KC - 1) / KC;
+  LaunchScope ls(KC_VQ, st);
+  const int total = nchunk * 2 * 8 * 256 * 4;
+  pack_codebook_kernel<<<(total + 255) / 256, 256, 0, st>>>(E, wimg, D, K, nchunk);
+  return check_launch("pack_codebook");
+}
+
+int launch_t3_vq_packed(const float* z, const float* E, const float* ee, const float* wimg, int64_t* idx, int64_t rows, int D, int K,
+                        cudaStream_t st) {
   VqArgs a;
   a.z = z; a.E = E; a.wimg = wimg; a.ee = ee; a.idx = idx; a.rows = rows; a.D = D; a.K = K;
   a.nchunk = (D + KC - 1) / KC;
-  {
-    LaunchScope ls(KC_VQ, st);
-    const int total = a.nchunk * 2 * 8 * 256 * 4;
-    pack_codebook_kernel<<<(total + 255) / 256, 256, 0, st>>>(E, wimg, D, K, a.nchunk);
-    if (int rc = check_launch("pack_codebook")) return rc;
-  }
   static PerDeviceOnce configured;
   if (configured.need()) {
     if (cudaFuncSetAttribute(t3_vq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, vq_smem()) != cudaSuccess)
@@ -415,6 +418,11 @@ int launch_t3_vq(const float* z, const float* E, const float* ee, float* wimg, i
   LaunchScope ls(KC_VQ, st);
   t3_vq_kernel<<<(unsigned)((rows + TM - 1) / TM), THREADS, vq_smem(), st>>>(a);
   return check_launch("t3_vq");
+}
+
+int launch_t3_vq(const float* z, const float* E, const float* ee, float* wimg, int64_t* idx, int64_t rows, int D, int K, cudaStream_t st) {
+  if (int rc = pack_codebook(E, wimg, D, K, st)) return rc;
+  return launch_t3_vq_packed(z, E, ee, wimg, idx, rows, D, K, st);
 }
 
 }  // namespace t3

@@ -77,6 +77,9 @@ int launch_t3_linear(const float* A, int64_t rows, int K, int lda, const float* 
 bool t3_vq_ok(int D, int K);
 int64_t t3_vq_image_bytes(int D);
 int launch_t3_vq(const float* z, const float* E, const float* ee, float* wimg, int64_t* idx, int64_t rows, int D, int K, cudaStream_t st);
+int pack_codebook(const float* E, float* wimg, int D, int K, cudaStream_t st);
+int launch_t3_vq_packed(const float* z, const float* E, const float* ee, const float* wimg, int64_t* idx, int64_t rows, int D, int K,
+                        cudaStream_t st);
 static inline int64_t w_image_bytes(int k, int n) { return (int64_t)((k + KC - 1) / KC) * 2 * 8 * n * 16; }
 
 }  // namespace t3

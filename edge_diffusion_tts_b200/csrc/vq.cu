@@ -238,6 +238,36 @@ extern "C" int edtts_vq_argmin(const float* z, const float* codebook, int64_t* i
   return check_launch("vq_argmin");
 }
 
+// Code norms + the tensor-core codebook image, packed once per codebook: packed_out holds edtts_vq_workspace_bytes(K, D) bytes.
+extern "C" int edtts_vq_pack(const float* codebook, int32_t dim, int32_t codebook_size, void* packed_out, void* stream) {
+  EDTTS_REQUIRE(codebook && packed_out && dim > 0 && dim % VQ_BK == 0 && codebook_size > 0, EDTTS_EINVAL, "vq_pack: bad argument");
+  cudaStream_t st = as_stream(stream);
+  float* ee = reinterpret_cast<float*>(packed_out);
+  {
+    LaunchScope ls(KC_VQ, st);
+    vq_code_norms_kernel<<<(codebook_size * 32 + 255) / 256, 256, 0, st>>>(codebook, ee, codebook_size, dim);
+    if (int rc = check_launch("vq_code_norms")) return rc;
+  }
+  if (!t3::t3_vq_ok(dim, codebook_size)) return EDTTS_OK;
+  return t3::pack_codebook(codebook, reinterpret_cast<float*>(reinterpret_cast<char*>(packed_out) + align_up((int64_t)codebook_size * 4, 256)), dim,
+                           codebook_size, st);
+}
+// edtts_vq_argmin with the norms / image packed earlier by edtts_vq_pack (one kernel launch)
+extern "C" int edtts_vq_argmin_packed(const float* z, const float* codebook, const void* packed, int64_t* idx_out, int64_t rows,
+                                      int32_t dim, int32_t codebook_size, void* stream) {
+  EDTTS_REQUIRE(z && codebook && packed && idx_out, EDTTS_EINVAL, "vq_argmin_packed: null argument");
+  EDTTS_REQUIRE(dim > 0 && dim % VQ_BK == 0 && codebook_size > 0, EDTTS_EINVAL, "vq_argmin_packed: dim=%d codebook_size=%d", dim, codebook_size);
+  if (rows == 0) return EDTTS_OK;
+  cudaStream_t st = as_stream(stream);
+  const float* ee = reinterpret_cast<const float*>(packed);
+  if (t3::t3_vq_ok(dim, codebook_size))
+    return t3::launch_t3_vq_packed(z, codebook, ee, reinterpret_cast<const float*>(reinterpret_cast<const char*>(packed) + align_up((int64_t)codebook_size * 4, 256)),
+                                   idx_out, rows, dim, codebook_size, st);
+  LaunchScope ls(KC_VQ, st);
+  vq_argmin_kernel<<<(unsigned)((rows + VQ_BM - 1) / VQ_BM), VQ_THREADS, 0, st>>>(z, codebook, ee, idx_out, rows, dim, codebook_size);
+  return check_launch("vq_argmin");
+}
+
 extern "C" int edtts_vq_gather_ste(const float* z, const float* codebook, const int64_t* idx, float* zq_out,
                                    int64_t rows, int32_t dim, int32_t codebook_size, void* stream) {
   EDTTS_REQUIRE(z && codebook && idx && zq_out, EDTTS_EINVAL, "vq_gather_ste: null argument");

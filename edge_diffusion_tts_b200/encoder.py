@@ -56,9 +56,23 @@ class SemanticEncoder(nn.Module):
         z = torch.empty(B, S, D, dtype=torch.float32, device=h.device)
         if B * S == 0:
             return z
-        ws = self._ws.get(lib.edtts_encoder_proj_workspace_bytes(B * S, Din), h.device)
         p = self.proj
         W = [_lib.f32(t.detach()) for t in (p[0].weight, p[0].bias, p[2].weight, p[2].bias, p[3].weight, p[3].bias)]
+        if Din % 4 == 0:
+            # tensor-core route: the two tf32 hi | lo weight images are packed once per weight version, then two launches per call
+            key = (W[0].data_ptr(), p[0].weight._version, W[4].data_ptr(), p[3].weight._version, str(h.device))
+            c = self.__dict__.get("_proj_images")
+            if c is None or c[0] != key:
+                img = torch.empty(int(lib.edtts_encoder_proj_image_bytes(Din)), dtype=torch.uint8, device=h.device)
+                _lib.check(lib.edtts_encoder_proj_pack(_lib.ptr(W[0]), _lib.ptr(W[4]), Din, _lib.ptr(img), _lib.stream_ptr(h.device)),
+                           "encoder_proj_pack")
+                c = (key, img)
+                self.__dict__["_proj_images"] = c
+            ws = self._ws.get(B * S * D * 4, h.device)
+            _lib.check(lib.edtts_encoder_proj_packed(_lib.ptr(h), _lib.ptr(c[1]), _lib.ptr(W[1]), _lib.ptr(W[2]), _lib.ptr(W[3]), _lib.ptr(W[5]),
+                                                     _lib.ptr(z), _lib.ptr(ws), B * S, Din, _lib.stream_ptr(h.device)), "encoder_proj_packed")
+            return z
+        ws = self._ws.get(lib.edtts_encoder_proj_workspace_bytes(B * S, Din), h.device)
         _lib.check(lib.edtts_encoder_proj(_lib.ptr(h), *[_lib.ptr(t) for t in W], _lib.ptr(z), _lib.ptr(ws), B * S,
                                           Din, _lib.stream_ptr(h.device)), "encoder_proj")
         return z

@@ -34,10 +34,17 @@ class VectorQuantizer(nn.Module):
         idx = torch.empty(B, T, dtype=torch.int64, device=z.device)
         if B * T == 0:
             return idx
-        ws = self._ws.get(lib.edtts_vq_workspace_bytes(self.codebook_size, D), z.device)
         cb = _lib.f32(self.codebook.weight.detach())
-        _lib.check(lib.edtts_vq_argmin(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(idx), B * T, D, self.codebook_size,
-                                       _lib.ptr(ws), _lib.stream_ptr(z.device)), "vq_argmin")
+        # code norms + tensor-core codebook image: packed once per codebook version, then one launch per call
+        key = (cb.data_ptr(), self.codebook.weight._version, str(z.device))
+        c = self.__dict__.get("_packed")
+        if c is None or c[0] != key:
+            packed = torch.empty(max(int(lib.edtts_vq_workspace_bytes(self.codebook_size, D)), 16), dtype=torch.uint8, device=z.device)
+            _lib.check(lib.edtts_vq_pack(_lib.ptr(cb), D, self.codebook_size, _lib.ptr(packed), _lib.stream_ptr(z.device)), "vq_pack")
+            c = (key, packed, cb)
+            self.__dict__["_packed"] = c
+        _lib.check(lib.edtts_vq_argmin_packed(_lib.ptr(z), _lib.ptr(cb), _lib.ptr(c[1]), _lib.ptr(idx), B * T, D, self.codebook_size,
+                                              _lib.stream_ptr(z.device)), "vq_argmin_packed")
         return idx
 
     def decode(self, idx: torch.Tensor) -> torch.Tensor:

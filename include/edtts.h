@@ -137,6 +137,11 @@ int edtts_prof_collect(double* ms_out, uint64_t* n_out, int n);
 int edtts_vq_argmin(const float* z, const float* codebook, int64_t* idx_out, int64_t rows, int32_t dim,
                     int32_t codebook_size, void* workspace, void* stream);
 int64_t edtts_vq_workspace_bytes(int32_t codebook_size, int32_t dim);
+/* The same search with the per-codebook work (code norms, tensor-core codebook image) done once: edtts_vq_pack fills
+ * packed_out (edtts_vq_workspace_bytes(K, D) bytes); edtts_vq_argmin_packed is then ONE kernel launch per call. */
+int edtts_vq_pack(const float* codebook, int32_t dim, int32_t codebook_size, void* packed_out, void* stream);
+int edtts_vq_argmin_packed(const float* z, const float* codebook, const void* packed, int64_t* idx_out, int64_t rows, int32_t dim,
+                           int32_t codebook_size, void* stream);
 /* vq.py:83,98: z_q = z + (E[idx] - z)  (straight-through rounding included). */
 int edtts_vq_gather_ste(const float* z, const float* codebook, const int64_t* idx, float* zq_out, int64_t rows,
                         int32_t dim, int32_t codebook_size, void* stream);
@@ -147,6 +152,12 @@ int edtts_vq_bincount(const int64_t* idx, int32_t* counts_out, int64_t rows, int
 /* z = Linear(128,128)(LayerNorm(GELU(Linear(768,128)(h)))); workspace: edtts_encoder_proj_workspace_bytes(rows, in_dim)
  * (the intermediate rows and, for the tensor-core route, the tf32 hi | lo weight images packed per call). */
 int64_t edtts_encoder_proj_workspace_bytes(int64_t rows, int32_t in_dim);
+/* Weight images packed once per weight set (edtts_encoder_proj_image_bytes(in_dim) bytes), then two launches per call;
+ * in_dim % 4 == 0; workspace: rows * 128 floats. */
+int64_t edtts_encoder_proj_image_bytes(int32_t in_dim);
+int edtts_encoder_proj_pack(const float* w0, const float* w3, int32_t in_dim, void* images_out, void* stream);
+int edtts_encoder_proj_packed(const float* h, const void* images, const float* b0, const float* ln_w, const float* ln_b,
+                              const float* b3, float* z_out, float* workspace, int64_t rows, int32_t in_dim, void* stream);
 int edtts_encoder_proj(const float* h, const float* w0, const float* b0, const float* ln_w, const float* ln_b,
                        const float* w3, const float* b3, float* z_out, float* workspace, int64_t rows,
                        int32_t in_dim, void* stream);
