@@ -165,6 +165,8 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
   const int64_t rows = (int64_t)B * S;
   float* ctx = reinterpret_cast<float*>(workspace);
   float* craw = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256));
+  if (sem_idx && precision == EDTTS_PREC_BF16)   // embedding + positional rows -> bf16 operand image -> k | v of all layers
+    return tc_context_kv(w, nullptr, sem_idx, S, craw, kv_out, rows, st);
   if (sem_idx) {
     const int64_t n4 = rows * (H / 4);
     LaunchScope ls(KC_EMBED, st);
@@ -181,7 +183,7 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     if (rc) return rc;
   }
   if (precision == EDTTS_PREC_BF16)   // kv_down -> kv_norm -> kv_up on the tensor cores, stored as the attention operand image
-    return tc_context_kv(w, ctx, craw, kv_out, rows, st);
+    return tc_context_kv(w, ctx, nullptr, S, craw, kv_out, rows, st);
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     GemmArgs d;   // kv_down_proj (mla.py:146)

@@ -332,14 +332,215 @@ int tc_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
   return EDTTS_OK;
 }
 
-int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, void* kv_out, int64_t rows, cudaStream_t st) {
+// ---- context K | V of all four layers in ONE launch (mla.py:144-153, step-invariant) -----------------------
+// k | v = kv_up_proj(kv_norm(kv_down_proj(ctx))) per layer.  Persistent CTAs, blockIdx.y = layer: the layer's two weight
+// images (kv_down 25.6 KB, kv_up 51.2 KB) are fetched once per CTA; per 128-token tile the bf16 chunk-major context rows
+// arrive by bulk copies (double-buffered: the next tile streams in under this one), c = ctx Wd^T is a tcgen05 GEMM into
+// tensor memory, the RMSNorm runs on the accumulator rows in registers (thread = token, the two column halves meet in
+// shared memory) and writes the bf16 A operand of the second GEMM, k | v = n Wu^T (two 160-column accumulators) leaves as the
+// chunk-major attention operand image (k bf16, v f16).  The fp32 intermediate never touches HBM; 1 launch instead of 8.
+constexpr int CK_THREADS = 256;
+constexpr int CK_SLAB = TILE_M * 16;
+constexpr int CK_OFF_X = 0;                                  // two context tiles: 2 x 20 slabs
+constexpr int CK_OFF_WD = CK_OFF_X + 2 * 20 * CK_SLAB;       // kv_down image [20][80][8]
+constexpr int CK_OFF_WU = CK_OFF_WD + RANK * H * 2;          // kv_up image [2][10][160][8]
+constexpr int CK_OFF_C = CK_OFF_WU + 2 * H * RANK * 2;       // normalised c: 10 slabs
+constexpr int CK_OFF_RED = CK_OFF_C + 10 * CK_SLAB;          // [2][128] partial sums of squares
+constexpr int CK_OFF_BAR = CK_OFF_RED + 2 * TILE_M * 4;
+constexpr int CK_SMEM = CK_OFF_BAR + 64;
+
+struct CtxKvArgs {
+  const __nv_bfloat16* ctx_chunk;    // [20][R][8] bf16
+  const uint8_t* packed;             // packed bf16 weight image
+  int64_t off_down[NL], off_up[NL];
+  const float* norm_w[NL];           // kv_norm.weight [80]
+  __nv_bfloat16* kv_out;             // [NL][40][R][8]: k chunks 0..19 bf16, v chunks 20..39 f16
+  int64_t R;
+};
+
+__global__ void __launch_bounds__(CK_THREADS, 1) ctx_kv_kernel(const CtxKvArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sX = smem + CK_OFF_X;
+  uint8_t* sWd = smem + CK_OFF_WD;
+  uint8_t* sWu = smem + CK_OFF_WU;
+  uint8_t* sC = smem + CK_OFF_C;
+  float* sRed = reinterpret_cast<float*>(smem + CK_OFF_RED);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(smem + CK_OFF_BAR);
+  uint64_t* bar_x = bar_w + 1;                                // [2]
+  uint64_t* bar_mma = bar_w + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_w + 4);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = blockIdx.y;
+  const int64_t ntiles = (a.R + TILE_M - 1) / TILE_M;
+
+  for (int i = tid * 16; i < CK_OFF_WD; i += CK_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);   // finite rows
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_x, 1);
+    mbar_init(bar_x + 1, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  constexpr uint32_t TM_C = 0, TM_KV = 128;                   // accumulators: c (80 columns), k | v (320 columns)
+
+  auto issue_x = [&](int64_t tile, int buf) {                 // thread 0
+    const int64_t row0 = tile * TILE_M;
+    const uint32_t valid = (uint32_t)min((int64_t)TILE_M, a.R - row0);
+    mbar_expect_tx(bar_x + buf, 20 * valid * 16);
+#pragma unroll 1
+    for (int c = 0; c < 20; ++c)
+      bulk_g2s(sX + (buf * 20 + c) * CK_SLAB, a.ctx_chunk + ((int64_t)c * a.R + row0) * 8, valid * 16, bar_x + buf);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(bar_w, RANK * H * 2 + 2 * H * RANK * 2);
+    bulk_g2s(sWd, a.packed + a.off_down[l], RANK * H * 2, bar_w);
+    bulk_g2s(sWu, a.packed + a.off_up[l], 2 * H * RANK * 2, bar_w);
+    if (blockIdx.x < ntiles) issue_x(blockIdx.x, 0);
+  }
+  const int lq = warp & 3, half = warp >> 2;
+  const int r = lq * 32 + lane;
+  const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+  float nw[40];
+#pragma unroll
+  for (int j = 0; j < 40; ++j) nw[j] = a.norm_w[l][40 * half + j];
+  __nv_bfloat16* kvl = a.kv_out + (int64_t)l * a.R * 2 * H;
+  uint32_t ph_m = 0;
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const int64_t row0 = tile * TILE_M;
+    if (tid == 0) {
+      if (tile + gridDim.x < ntiles) issue_x(tile + gridDim.x, buf ^ 1);      // its last reader (tile it - 1's GEMM) has retired
+      if (it == 0) mbar_wait(bar_w, 0);
+      mbar_wait(bar_x + buf, (it >> 1) & 1);
+      tc_fence_after();
+      constexpr uint32_t ID_C = make_idesc(TILE_M, RANK);
+#pragma unroll
+      for (int ks = 0; ks < H / 16; ++ks)
+        umma_bf16(tmem + TM_C, make_desc(smem_u32(sX) + (buf * 20 + 2 * ks) * CK_SLAB, CK_SLAB, 128),
+                  make_desc(smem_u32(sWd) + ks * 2 * RANK * 16, RANK * 16, 128), ID_C, ks > 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_m);
+    ph_m ^= 1;
+    tc_fence_after();
+    {  // kv_norm on the accumulator row: this thread's 40 of the 80 columns
+      float v[40];
+      tmem_ld32(trow + TM_C + 40 * half, v);
+      tmem_ld8(trow + TM_C + 40 * half + 32, v + 32);
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < 40; ++j) ss = fmaf(v[j], v[j], ss);
+      sRed[half * TILE_M + r] = ss;
+      __syncthreads();
+      const float rstd = 1.0f / sqrtf((sRed[r] + sRed[TILE_M + r]) / (float)RANK + 1e-6f);
+#pragma unroll
+      for (int g = 0; g < 5; ++g) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[8 * g + j] * rstd) * nw[8 * g + j];
+        *reinterpret_cast<uint4*>(sC + (5 * half + g) * CK_SLAB + r * 16) = pack_bf16x8(o);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t ID_KV = make_idesc(TILE_M, H);
+#pragma unroll
+      for (int y = 0; y < 2; ++y)
+#pragma unroll
+        for (int ks = 0; ks < RANK / 16; ++ks)
+          umma_bf16(tmem + TM_KV + y * H, make_desc(smem_u32(sC) + ks * 2 * CK_SLAB, CK_SLAB, 128),
+                    make_desc(smem_u32(sWu) + y * (H * RANK * 2) + ks * 2 * H * 16, H * 16, 128), ID_KV, ks > 0);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, ph_m);
+    ph_m ^= 1;
+    tc_fence_after();
+    {  // k (half 0, bf16) | v (half 1, f16) -> chunk-major operand image
+      const int64_t row = row0 + r;
+#pragma unroll 1
+      for (int c0 = 0; c0 < H; c0 += 16) {
+        float v[16];
+        tmem_ld16(trow + TM_KV + half * H + c0, v);
+        if (row < a.R) {
+          __nv_bfloat16* o = kvl + ((int64_t)((half * H + c0) >> 3) * a.R + row) * 8;
+          *reinterpret_cast<uint4*>(o) = half ? pack_f16x8(v) : pack_bf16x8(v);
+          *reinterpret_cast<uint4*>(o + a.R * 8) = half ? pack_f16x8(v + 8) : pack_bf16x8(v + 8);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                           // accumulators and sC are free for the next tile
+  }
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ctx[b, s, :] = token_emb[sem_idx[b, s]] + pe[s] (decoder.py:88,93) written straight as the bf16 chunk-major operand image
+// [20][rows][8]: a thread = (row, 8-column group); the fp32 context rows never exist
+__global__ void embed_ctx_chunk_kernel(const float* __restrict__ emb, const float* __restrict__ pe, const int64_t* __restrict__ idx,
+                                       __nv_bfloat16* __restrict__ out, int64_t rows, int S, int codebook) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (H / 8)) return;
+  const int64_t r = i % rows;
+  const int c = (int)(i / rows);
+  int64_t tok = idx[r];
+  tok = tok < 0 ? 0 : (tok >= codebook ? codebook - 1 : tok);
+  const float4* e = reinterpret_cast<const float4*>(emb + tok * H + 8 * c);
+  const float4* p = reinterpret_cast<const float4*>(pe + (r % S) * H + 8 * c);
+  const float4 e0 = e[0], e1 = e[1], p0 = p[0], p1 = p[1];
+  const float v[8] = {e0.x + p0.x, e0.y + p0.y, e0.z + p0.z, e0.w + p0.w, e1.x + p1.x, e1.y + p1.y, e1.z + p1.z, e1.w + p1.w};
+  *reinterpret_cast<uint4*>(out + i * 8) = pack_bf16x8(v);
+}
+
+// ctx: fp32 context rows [rows][160] (packed to the operand image here), or -- sem_idx given -- built directly from the
+// token embedding (ctx may then be null)
+int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, const int64_t* sem_idx, int S, float* craw, void* kv_out,
+                  int64_t rows, cudaStream_t st) {
   EDTTS_REQUIRE(w->packed_bf16, EDTTS_EINVAL, "context_prepare(bf16): weights.packed_bf16 is null");
   const PackedOff po = packed_offsets();
   const uint8_t* pk = reinterpret_cast<const uint8_t*>(w->packed_bf16);
-  // the context rows once as a bf16 chunk-major operand image (read by the four down projections through the TMA engine,
-  // no fp32 staging / conversion prologue per layer); it lives in the third region of the context workspace
+  // the context rows once as a bf16 chunk-major operand image (read through the TMA engine, no fp32 staging / conversion
+  // prologue per layer); it lives in the third region of the context workspace
   __nv_bfloat16* ctx_chunk = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(craw) + align_up(rows * RANK * 4, 256));
-  if (int rc0 = pack_activation(ctx, H, ctx_chunk, rows, H, 1 << 30, st)) return rc0;
+  if (sem_idx) {
+    const int64_t n = rows * (H / 8);
+    LaunchScope ls(KC_EMBED, st);
+    embed_ctx_chunk_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w->token_emb, w->ctx_pe, sem_idx, ctx_chunk, rows, S, w->codebook_size);
+    if (int rc0 = check_launch("embed_ctx_chunk")) return rc0;
+  } else if (int rc0 = pack_activation(ctx, H, ctx_chunk, rows, H, 1 << 30, st)) {
+    return rc0;
+  }
+  if (env_flag("EDTTS_CTX_FUSED", true)) {
+    CtxKvArgs a;
+    a.ctx_chunk = ctx_chunk; a.packed = pk; a.kv_out = reinterpret_cast<__nv_bfloat16*>(kv_out); a.R = rows;
+    for (int l = 0; l < NL; ++l) {
+      a.off_down[l] = po.layer[l].kv_down;
+      a.off_up[l] = po.layer[l].kv_up;
+      a.norm_w[l] = w->layers[l].kv_norm_w;
+    }
+    static PerDeviceOnce configured;
+    if (configured.need()) {
+      if (cudaFuncSetAttribute(ctx_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CK_SMEM) != cudaSuccess)
+        return check_launch("ctx_kv smem attribute");
+      configured.set();
+    }
+    const int64_t ntiles = (rows + TILE_M - 1) / TILE_M;
+    int64_t nx = sm_count() / NL;
+    if (nx < 1) nx = 1;
+    if (nx > ntiles) nx = ntiles;
+    LaunchScope ls(KC_TC_GEMM, st);
+    ctx_kv_kernel<<<dim3((unsigned)nx, NL), CK_THREADS, CK_SMEM, st>>>(a);
+    return check_launch("ctx_kv");
+  }
   for (int l = 0; l < NL; ++l) {
     const LayerOff& lo = po.layer[l];
     int rc;

@@ -17,7 +17,8 @@ int tc_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float
                    cudaStream_t stream);
 // cross-attention K | V of all blocks from the context embeddings (bf16 path): kv_out[l] = chunk-major [40][rows][8],
 // k as bf16, v as f16; craw = scratch rows x 80 fp32
-int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, void* kv_out, int64_t rows, cudaStream_t st);
+int tc_context_kv(const edtts_decoder_weights* w, const float* ctx, const int64_t* sem_idx, int S, float* craw, void* kv_out,
+                  int64_t rows, cudaStream_t st);
 namespace tc {
 enum LyMode : int { LM_BLOCK = 0, LM_HEAD = 1 };
 enum LyTail : int { LT_NONE = 0, LT_QKV = 1, LT_FINAL = 2 };
