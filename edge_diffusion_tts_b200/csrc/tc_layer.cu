@@ -18,19 +18,25 @@ constexpr int64_t LY_EX_IN = 0, LY_EX_OUT = LY_WCHUNK / 2, LY_EX_QKV = LY_WCHUNK
 constexpr int64_t LY_EXTRA_BYTES = LY_EX_QKV + (int64_t)NL * 3 * LY_WCHUNK;
 int64_t tc_layer_packed_bytes() { return LY_EXTRA_OFF + LY_EXTRA_BYTES; }
 
-// dst[c][n][j] = src[(row0 + n) * ld + col0 + 8 c + j], n < nrows, c < kcols / 8   (block of an nn.Linear weight)
-__global__ void pack_chunk_kernel(const float* __restrict__ src, int ld, int row0, int col0, int nrows, int kcols,
+// dst[c][n][j] = src[(r(n)) * ld + col0 + 8 c + j], n < nrows, c < kcols / 8   (block of an nn.Linear weight);
+// r(n) = row0 + n for n < split, row1 + (n - split) beyond (two row ranges of the weight in one chunk)
+__global__ void pack_chunk_kernel(const float* __restrict__ src, int ld, int row0, int row1, int split, int col0, int nrows, int kcols,
                                   __nv_bfloat16* __restrict__ dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nrows * kcols) return;
   const int j = i & 7, n = (i >> 3) % nrows, c = (i >> 3) / nrows;
-  dst[i] = __float2bfloat16_rn(src[(int64_t)(row0 + n) * ld + col0 + 8 * c + j]);
+  const int r = n < split ? row0 + n : row1 + (n - split);
+  dst[i] = __float2bfloat16_rn(src[(int64_t)r * ld + col0 + 8 * c + j]);
 }
-static int pack_chunk(const float* src, int ld, int row0, int col0, int nrows, int kcols, void* dst, cudaStream_t st) {
+static int pack_chunk2(const float* src, int ld, int row0, int row1, int split, int col0, int nrows, int kcols, void* dst,
+                       cudaStream_t st) {
   LaunchScope ls(KC_TC_MISC, st);
-  pack_chunk_kernel<<<(nrows * kcols + 255) / 256, 256, 0, st>>>(src, ld, row0, col0, nrows, kcols,
+  pack_chunk_kernel<<<(nrows * kcols + 255) / 256, 256, 0, st>>>(src, ld, row0, row1, split, col0, nrows, kcols,
                                                                 reinterpret_cast<__nv_bfloat16*>(dst));
   return check_launch("pack_chunk");
+}
+static int pack_chunk(const float* src, int ld, int row0, int col0, int nrows, int kcols, void* dst, cudaStream_t st) {
+  return pack_chunk2(src, ld, row0, 0, nrows, col0, nrows, kcols, dst, st);
 }
 
 __global__ void pack_layer_consts_kernel(const edtts_layer_weights L, float* __restrict__ dst) {
@@ -40,9 +46,9 @@ __global__ void pack_layer_consts_kernel(const edtts_layer_weights L, float* __r
     else if (i < LC_N3W) v = L.norm2_w[i - LC_N2W];
     else if (i < LC_F0B) v = L.norm3_norm_w[i - LC_N3W];
     else if (i < LC_F3B) {
-      // [half][x 160 | gate 160]: u column 160 half + c <- ffn.net.0 rows (160 half + c) and (320 + 160 half + c)
-      const int k = i - LC_F0B, half = k / 320, r = k % 320;
-      v = L.ffn0_b[r < 160 ? 160 * half + r : FFN + 160 * half + (r - 160)];
+      // [quarter][x 80 | gate 80]: u column 80 q + c <- ffn.net.0 rows (80 q + c) and (320 + 80 q + c)
+      const int k = i - LC_F0B, q = k / 160, r = k % 160;
+      v = L.ffn0_b[r < 80 ? 80 * q + r : FFN + 80 * q + (r - 80)];
     } else v = L.ffn3_b[i - LC_F3B];
     dst[i] = v;
   }
@@ -53,13 +59,15 @@ int tc_layer_pack(const edtts_decoder_weights* w, void* dst, cudaStream_t st) {
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     uint8_t* img = base + l * LY_IMG_BYTES;
-    struct Src { const float* p; int ld, row0, col0; };
+    // ffn0 quarter q: rows 80 q .. (x) then FFN + 80 q .. (gate)
+    struct Src { const float* p; int ld, row0, row1, split, col0; };
     const Src src[LY_NCHUNK] = {
-        {L.attn_proj_w, H, 0, 0},   {L.q_proj_w, H, 0, 0},       {L.cross_out_w, H, 0, 0},
-        {L.ffn0_w, H, 0, 0},        {L.ffn0_w, H, FFN, 0},       {L.ffn0_w, H, 160, 0},
-        {L.ffn0_w, H, FFN + 160, 0}, {L.ffn3_w, FFN, 0, 0},      {L.ffn3_w, FFN, 0, 160}};
+        {L.attn_proj_w, H, 0, 0, 160, 0},  {L.q_proj_w, H, 0, 0, 160, 0},       {L.cross_out_w, H, 0, 0, 160, 0},
+        {L.ffn0_w, H, 0, FFN, 80, 0},      {L.ffn0_w, H, 80, FFN + 80, 80, 0},  {L.ffn0_w, H, 160, FFN + 160, 80, 0},
+        {L.ffn0_w, H, 240, FFN + 240, 80, 0}, {L.ffn3_w, FFN, 0, 0, 160, 0},    {L.ffn3_w, FFN, 0, 0, 160, 160}};
     for (int c = 0; c < LY_NCHUNK; ++c) {
-      int rc = pack_chunk(src[c].p, src[c].ld, src[c].row0, src[c].col0, 160, 160, img + (int64_t)c * LY_WCHUNK, st);
+      int rc = pack_chunk2(src[c].p, src[c].ld, src[c].row0, src[c].row1, src[c].split, src[c].col0, 160, 160,
+                           img + (int64_t)c * LY_WCHUNK, st);
       if (rc) return rc;
     }
     LaunchScope ls(KC_TC_MISC, st);

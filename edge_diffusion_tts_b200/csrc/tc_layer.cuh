@@ -17,19 +17,22 @@
 //   cross attention (mla.py:176-180)          same machinery, keys = the S context tokens
 //   h += O Wout^T
 //   n3 = AdaRMSNorm(h)                        row pass
-//   u  = swiglu(n3 W0^T + b0)                 two halves of 160 u-columns, each 128 x 320 in TMEM
-//   h += u W3^T (+ b3)                        tcgen05.mma into h, then h -> HBM
+//   u  = swiglu(n3 W0^T + b0)                 four quarters of 80 u-columns (x 80 | gate 80 = one 160-row weight chunk), two
+//                                             TMEM buffers: the GEMM of quarter k+1 runs under the SwiGLU pass of quarter k
+//   h += u W3^T (+ b3)                        tcgen05.mma into h (first half under the last SwiGLU pass), then h -> HBM
 //
 // 384 threads, warp-specialised:
 //   warps 0-3 / 4-7   compute warpgroups (thread <-> frame, TMEM lane = frame).  In the attention
 //                     phases warpgroup g owns heads g and g+2; in the row passes it handles columns
-//                     80g .. 80g+79 of every row.  Thread 0 also issues the GEMM-chain MMAs and
-//                     weight-chunk copies (they are strictly ordered with the row passes anyway).
+//                     80g .. 80g+79 of every row.
 //   warp 8 / 10       TMA producer of warpgroup 0 / 1 (lane 0): K (4 stages) and V (2 stages) blocks of 64 keys; between
 //                     two items it prefetches the next item's h / q | k | v rows into L2.  Lane 1 of warp 8 is the
 //                     "agent" of the merged launch: gpu-scope acquire / release of the per-item flags
 //   warp 9 / 11       MMA issuer of warpgroup 0 / 1 (converged warp, elected lane):  S = Q K^T into a
-//                     double-buffered TMEM block, O += P V accumulating in TMEM
+//                     double-buffered TMEM block, O += P V accumulating in TMEM.  Warp 11 is also the GEMM-CHAIN issuer: between
+//                     the attention phases it streams the weight chunks and issues every projection / FFN / QKV GEMM of the
+//                     item, woken by per-warp arrivals of the compute warps (bar_go / bar_free), so no compute warp is ever
+//                     held by an MMA queue and the row pass of one GEMM overlaps the next GEMM
 // Attention is a single streaming pass per head in which no thread waits for a tensor-core round
 // trip: S blocks (64 keys) arrive in a double-buffered TMEM block, p = exp2(s*c - m) is written back as
 // f16x2 over the first 32 columns of the SAME S block (tcgen05.st) and feeds O += P V as a tensor-memory
@@ -54,7 +57,8 @@ constexpr int LY_SLAB = 128 * 16;             // one 8-wide K slab of a 128-row 
 constexpr int LY_WSLAB = 160 * 16;            // one 8-wide K slab of a 160-row weight chunk
 constexpr int LY_WCHUNK = 20 * LY_WSLAB;      // 51,200 B: W[160 out][160 in] bf16
 constexpr int LY_NCHUNK = 9;                  // proj, q_proj, out_proj, ffn0 x4, ffn3 x2
-enum LyChunk : int { WC_PROJ = 0, WC_Q, WC_OUT, WC_F0_X0, WC_F0_G0, WC_F0_X1, WC_F0_G1, WC_F3_K0, WC_F3_K1 };
+// ffn0 quarter q: rows 0..79 = ffn.net.0 rows 80q.. (x part of u columns 80q..80q+79), rows 80..159 = rows 320+80q.. (their gates)
+enum LyChunk : int { WC_PROJ = 0, WC_Q, WC_OUT, WC_F0_Q0, WC_F0_Q1, WC_F0_Q2, WC_F0_Q3, WC_F3_K0, WC_F3_K1 };
 constexpr int LY_KB = 64;                     // keys per attention block
 constexpr int LY_KSLAB = LY_KB * 16;          // one 8-wide slab of a 64-key K / V block
 constexpr int LY_KBUF = 6 * LY_KSLAB;         // K (or V) block, head_dim padded 40 -> 48
@@ -71,21 +75,24 @@ constexpr int LO_A = 0;                                   // 21 slabs: A operand
 constexpr int LO_W0 = LO_A + 21 * LY_SLAB;                // weight slot 0
 constexpr int LO_X = LO_W0 + LY_WCHUNK;                   // overlay region
 constexpr int LO_W1 = LO_X;                               //   GEMM chain: weight slot 1
-constexpr int LO_U = LO_X + LY_WCHUNK;                    //   GEMM chain: u half (128 x 160 bf16)
+constexpr int LO_U = LO_X + LY_WCHUNK;                    //   GEMM chain: u quarters 0..2 (128 x 240 bf16; quarter 3 goes to sA)
 constexpr int LY_KST = 4, LY_VST = 2;                     //   K / V stages per warpgroup (S blocks: 2, so K stage = S op % 4)
 constexpr int LO_KV = LO_U;                               //   attention: wg: K0 | K1 | K2 | V0 | V1 (K/V stream in while
                                                           //   weight slot 1 is in use, so they only overlay the u half)
 constexpr int LO_X_END = LO_KV + 2 * (LY_KST + LY_VST) * LY_KBUF;
-static_assert(LO_U + 20 * LY_SLAB <= LO_X_END, "u half must fit in the overlay region");
+static_assert(LO_U + 30 * LY_SLAB <= LO_X_END, "u quarters 0..2 must fit in the overlay region");
 constexpr int LO_CONST = LO_X_END;
 constexpr int LO_RED = LO_CONST + LS_COUNT * 4;
 constexpr int LO_BAR = LO_RED + 4 * 128 * 4;
-constexpr int LY_NBAR = 9 + 2 * 16;
+constexpr int LY_NBAR = 13 + 2 * 16;
 constexpr int LY_SMEM = LO_BAR + LY_NBAR * 8 + 16;
 static_assert(LY_SMEM <= 232448, "shared memory budget");
 
 // mbarrier indices
-enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_DEP = 6 /* two */, LB_FIN = 8, LB_WG0 = 9 };
+// LB_G / LB_G2: GEMM-chain completions (tcgen05.commit); LB_GO: "A operand written" and LB_FREE[2]: "TMEM buffer b read out / result
+// seen" -- one arrival per compute warp (count 8), waited for by the GEMM-chain issuer
+enum LyBar : int { LB_W0 = 0, LB_W1, LB_Q, LB_G, LB_KVGO, LB_ATTGO, LB_DEP = 6 /* two */, LB_FIN = 8, LB_G2 = 9, LB_GO = 10,
+                   LB_FREE = 11 /* two */, LB_WG0 = 13 };
 // One commit per MMA group: WB_SK[n % 4] = "S op n retired" tells the softmax warps that S block n % 2 is full AND the TMA
 // producer that K stage n % 4 is free; WB_PV[n % 2] = "P V op n retired" frees V stage / P block n % 2 (lazy rescale).
 enum LyWgBar : int { WB_KFULL = 0, WB_SK = 4, WB_VFULL = 8, WB_PV = 10, WB_PFULL = 12, WB_OFULL = 14, WB_OFREE = 15, WB_COUNT = 16 };
@@ -93,7 +100,7 @@ static_assert(LY_KST == 4 && LY_VST == 2, "barrier indexing assumes 4 K stages, 
 
 // tensor memory map (columns)
 constexpr uint32_t TM_H = 0;                              // residual stream, 160 columns
-constexpr uint32_t TM_G = 160;                            // GEMM chain scratch, 320 columns
+constexpr uint32_t TM_G = 160;                            // GEMM chain scratch, 320 columns (FFN: two buffers of x 80 | gate 80)
 constexpr uint32_t TM_S0 = 160, TM_WG = 176;              // attention, per warpgroup: S0 (64) | S1 (64) | O (48); the f16
                                                           // probabilities P(i) overwrite columns 0..31 of their S block
 
@@ -179,6 +186,15 @@ __device__ __forceinline__ void ly_issue_gemm(uint32_t d_tmem, uint32_t a_addr, 
   for (int ks = 0; ks < 10; ++ks)
     umma_bf16(d_tmem, make_desc(a_addr + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(w_addr + ks * 2 * LY_WSLAB, LY_WSLAB, 128),
               IDESC, accumulate || ks > 0);
+}
+
+// k-steps ks0 .. ks0+nks-1 of a 160-row weight chunk against A slabs starting at a_addr (accumulating)
+__device__ __forceinline__ void ly_issue_gemm_part(uint32_t d_tmem, uint32_t a_addr, uint32_t w_addr, int ks0, int nks) {
+  constexpr uint32_t IDESC = make_idesc(128, 160);
+#pragma unroll
+  for (int ks = 0; ks < nks; ++ks)
+    umma_bf16(d_tmem, make_desc(a_addr + ks * 2 * LY_SLAB, LY_SLAB, 128), make_desc(w_addr + (ks0 + ks) * 2 * LY_WSLAB, LY_WSLAB, 128),
+              IDESC, true);
 }
 
 // D[128 x n] (+)= A[128 x 16 ksteps] * W[n x 16 ksteps]^T; W slabs are n rows of 16 bytes
@@ -753,6 +769,9 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
   uint64_t* bar_attgo = bars + LB_ATTGO;
   uint64_t* bar_dep = bars + LB_DEP;                      // [2]: item it's predecessors are visible (agent -> compute, TMA)
   uint64_t* bar_fin = bars + LB_FIN;                      // item finished, its stores are issued (compute -> agent)
+  uint64_t* bar_g2 = bars + LB_G2;
+  uint64_t* bar_go = bars + LB_GO;
+  uint64_t* bar_free = bars + LB_FREE;                    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + LY_NBAR);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -761,7 +780,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
   for (int i = tid * 16; i < LO_BAR; i += LY_THREADS * 16) *reinterpret_cast<uint4*>(smem + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   if (tid == 0) {
-    for (int i = 0; i < LB_WG0; ++i) mbar_init(bars + i, 1);
+    for (int i = 0; i < LB_WG0; ++i) mbar_init(bars + i, (i == LB_GO || i == LB_FREE || i == LB_FREE + 1) ? 8 : 1);
     for (int w = 0; w < 2; ++w) {
       uint64_t* wbi = bars + LB_WG0 + w * WB_COUNT;
       for (int i = 0; i < WB_COUNT; ++i) {
@@ -796,7 +815,173 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     const int cwg = cw >> 1;
     const bool is_mma = cw & 1;
     const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
-    if (is_mma || lane == 0) {
+    if (cw == 3) {
+      // ================= warp 11: attention MMAs of warpgroup 1 AND the whole GEMM chain (converged warp, elected lane) =========
+      // The script mirrors the compute threads' item script step by step.  wait_go(): all eight compute warps have written (and
+      // fenced) the A operand of the next GEMM and are done with the TMEM columns it overwrites; wait_free(b): they have read out
+      // TMEM buffer b (FFN) / seen the previous completion of bar_g (QKV tail).  Every weight chunk is requested as soon as its
+      // slot is free; completions go to bar_g / bar_g2 alternately so that two GEMMs can be in flight.
+      uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
+      uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;
+      uint32_t pw0 = 0, pw1 = 0, ng = 0, ng2 = 0, ngo = 0, nf0 = 0, nf1 = 0;
+      const uint32_t aA = smem_u32(sA), aW0 = smem_u32(sW0), aW1 = smem_u32(sW1), aU = smem_u32(sU), aU2 = aU + 20 * LY_SLAB;
+      auto ld = [&](const __nv_bfloat16* src, int bytes, uint8_t* slot, uint64_t* bar) {
+        if (elect_one()) {
+          mbar_expect_tx(bar, bytes);
+          bulk_g2s(slot, src, bytes, bar);
+        }
+        __syncwarp();
+      };
+      auto ld_first = [&](const LayerArgs& x) {            // first weight chunk of an item (slot 0)
+        if (x.mode == LM_HEAD) ld(x.w_in, LY_WCHUNK / 2, sW0, bar_w0);
+        else ld(x.wimg + (int64_t)WC_PROJ * (LY_WCHUNK / 2), LY_WCHUNK, sW0, bar_w0);
+      };
+      auto wait_w0 = [&]() { mbar_wait(bar_w0, pw0); pw0 ^= 1; tc_fence_after(); };
+      auto wait_w1 = [&]() { mbar_wait(bar_w1, pw1); pw1 ^= 1; tc_fence_after(); };
+      auto wait_go = [&]() { mbar_wait(bar_go, ngo & 1); ++ngo; tc_fence_after(); };
+      auto wait_free = [&](int b) {
+        if (b == 0) { mbar_wait(bar_free, nf0 & 1); ++nf0; } else { mbar_wait(bar_free + 1, nf1 & 1); ++nf1; }
+        tc_fence_after();
+      };
+      auto wait_g = [&]() { mbar_wait(bar_g, (ng - 1) & 1); tc_fence_after(); };      // the latest commit on bar_g has retired
+      auto wait_g2 = [&]() { mbar_wait(bar_g2, (ng2 - 1) & 1); tc_fence_after(); };
+      // one 160 x 160 chunk GEMM, completion on bar_g (which = 0), bar_g2 (1) or none (-1)
+      auto gemm = [&](uint32_t dcol, uint32_t a_addr, uint32_t w_addr, bool acc, int which) {
+        if (elect_one()) {
+          ly_issue_gemm(tmem_u + dcol, a_addr, w_addr, acc);
+          if (which == 0) umma_commit(bar_g);
+          else if (which == 1) umma_commit(bar_g2);
+        }
+        __syncwarp();
+        if (which == 0) ++ng; else if (which == 1) ++ng2;
+      };
+      if ((int)blockIdx.x < nitems) ld_first(p.a[blockIdx.x / ntiles]);
+      for (int g = blockIdx.x; g < nitems; g += gridDim.x) {
+        const int l = g / ntiles;
+        const LayerArgs& a = p.a[l];
+        const LyTile tl = ly_tile(d, g - l * ntiles);
+        const bool more = g + (int)gridDim.x < nitems;
+        const LayerArgs& an = p.a[more ? (g + (int)gridDim.x) / ntiles : l];
+        auto ldc = [&](int chunk, uint8_t* slot, uint64_t* bar) { ld(a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, slot, bar); };
+        if (a.mode == LM_HEAD) {
+          wait_go();                                        // x tile (bf16) in sA
+          wait_w0();
+          if (elect_one()) {
+            ly_issue_gemm_ex(tmem_u + TM_H, aA, aW0, M / 16, H, false);
+            umma_commit(bar_g);
+          }
+          __syncwarp();
+          ++ng;
+          wait_g();                                         // slot 0 is free again
+        } else {
+          // ---- banded self-attention (warpgroup 1's heads) ----
+          mbar_wait(bar_attgo, n_phase & 1);
+          tc_fence_after();
+          ly_mma_phase<true>(d, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
+          ++n_phase;
+          // ---- h += O Wproj^T ----
+          wait_go();                                        // all heads' outputs are in sA; every attention MMA of the phase has retired
+          if (a.stop_phase != 1) {
+            if (elect_one()) mbar_arrive(bar_kvgo);         // context K/V may stream in during the GEMM chain
+            __syncwarp();
+          }
+          ldc(WC_Q, sW1, bar_w1);
+          wait_w0();
+          gemm(TM_H, aA, aW0, true, 0);
+          wait_g();
+          if (a.stop_phase == 1) {                          // debug stop: drain the prefetch, hand slot 0 to the next item
+            wait_w1();
+            if (more) ld_first(an);
+            continue;
+          }
+          ldc(WC_OUT, sW0, bar_w0);
+          // ---- q = n2 Wq^T ----
+          wait_go();
+          wait_w1();
+          gemm(TM_G, aA, aW1, false, 0);
+          // ---- cross attention ----
+          mbar_wait(bar_attgo, n_phase & 1);
+          tc_fence_after();
+          ly_mma_phase<false>(d, tl, smem, tmem_u, cwb, cwg, c0, c1, c2);
+          ++n_phase;
+          // ---- h += O Wout^T ----
+          wait_go();
+          ldc(WC_F0_Q0, sW1, bar_w1);
+          wait_w0();
+          gemm(TM_H, aA, aW0, true, 0);
+          wait_g();
+          if (a.stop_phase == 2) {
+            wait_w1();
+            if (more) ld_first(an);
+            continue;
+          }
+          ldc(WC_F0_Q1, sW0, bar_w0);
+          // ---- feed-forward: quarters 0..3 into TMEM buffers 0 / 1, then h += u W3^T ----
+          wait_go();                                        // n3 in sA
+          wait_w1();
+          gemm(TM_G, aA, aW1, false, 0);                    // quarter 0
+          wait_w0();
+          gemm(TM_G + 160, aA, aW0, false, 1);              // quarter 1
+          wait_g();
+          ldc(WC_F0_Q2, sW1, bar_w1);
+          wait_free(0);                                     // buffer 0 read out (u quarter 0 written)
+          wait_w1();
+          gemm(TM_G, aA, aW1, false, 0);                    // quarter 2
+          wait_g2();
+          ldc(WC_F0_Q3, sW0, bar_w0);
+          wait_free(1);
+          wait_w0();
+          gemm(TM_G + 160, aA, aW0, false, 1);              // quarter 3
+          wait_g();
+          ldc(WC_F3_K0, sW1, bar_w1);
+          wait_free(0);                                     // u quarters 0..2 written
+          wait_w1();
+          gemm(TM_H, aU, aW1, true, -1);                    // h += u[0..159] W3[:, 0..159]^T
+          wait_g2();
+          ldc(WC_F3_K1, sW0, bar_w0);
+          wait_free(1);                                     // u quarter 3 written (sA)
+          wait_w0();
+          if (elect_one()) {                                // h += u[160..319] W3[:, 160..319]^T: quarter 2 from sU2, quarter 3 from sA
+            ly_issue_gemm_part(tmem_u + TM_H, aU2, aW0, 0, 5);
+            ly_issue_gemm_part(tmem_u + TM_H, aA, aW0, 5, 5);
+            umma_commit(bar_g);
+          }
+          __syncwarp();
+          ++ng;
+          wait_g();                                         // both weight slots are free
+        }
+        // ---- tail ----
+        if (a.tail == LT_QKV) {
+          ld(a.w_qkv, LY_WCHUNK, sW1, bar_w1);
+          ld(a.w_qkv + LY_WCHUNK / 2, LY_WCHUNK, sW0, bar_w0);
+          wait_go();                                        // norm1 of the next block in sA, h read out
+          wait_w1();
+          gemm(0, aA, aW1, false, 0);                       // q
+          wait_w0();
+          gemm(160, aA, aW0, false, 1);                     // k
+          wait_g();
+          ld(a.w_qkv + 2 * (LY_WCHUNK / 2), LY_WCHUNK, sW1, bar_w1);
+          wait_free(0);                                     // every compute warp has seen q's completion on bar_g
+          wait_w1();
+          gemm(320, aA, aW1, false, 0);                     // v
+          wait_g2();
+          if (more) ld_first(an);
+        } else if (a.tail == LT_FINAL) {
+          ld(a.w_out, LY_WCHUNK / 2, sW1, bar_w1);
+          if (more) ld_first(an);
+          wait_go();
+          wait_w1();
+          if (elect_one()) {
+            ly_issue_gemm_ex(tmem_u + 0, aA, aW1, H / 16, M, false);
+            umma_commit(bar_g);
+          }
+          __syncwarp();
+          ++ng;
+        } else {
+          if (more) ld_first(an);
+        }
+      }
+    } else if (is_mma || lane == 0) {
       uint64_t* cwb = bars + LB_WG0 + cwg * WB_COUNT;
       uint32_t n_phase = 0, c0 = 0, c1 = 0, c2 = 0;       // TMA: c0 = K loads, c1 = V loads; MMA: S ops, PV ops, heads
       uint32_t it = 0;                                    // the CTA's item counter (head items included)
@@ -891,22 +1076,22 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
   const int cb = 80 * wg;                                 // this thread's column half in the row passes
   uint64_t* wb = bars + LB_WG0 + wg * WB_COUNT;
   const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-  uint32_t ph_w0 = 0, ph_w1 = 0, ph_q = 0, ph_g = 0, cs = 0, cp = 0, co = 0;
+  uint32_t ph_q = 0, ph_g = 0, ph_g2 = 0, cs = 0, cp = 0, co = 0;
   auto csync = [&]() { named_bar_sync(3, LY_CTHREADS); };
-  auto load_w = [&](const __nv_bfloat16* src, int bytes, uint8_t* slot, uint64_t* bar) {   // tid 0 only
-    mbar_expect_tx(bar, bytes);
-    bulk_g2s(slot, src, bytes, bar);
-  };
+  // completion of the next GEMM the issuer commits on bar_g / bar_g2 (every commit is waited for exactly once, in order)
   auto gemm_wait = [&]() {
     mbar_wait(bar_g, ph_g);
     ph_g ^= 1;
     tc_fence_after();
   };
-  // first weight chunk of an item (slot 0); x = the item's layer arguments
-  auto load_first = [&](const LayerArgs& x) {
-    if (x.mode == LM_HEAD) load_w(x.w_in, LY_WCHUNK / 2, sW0, bar_w0);
-    else load_w(x.wimg + (int64_t)WC_PROJ * (LY_WCHUNK / 2), LY_WCHUNK, sW0, bar_w0);
+  auto gemm_wait2 = [&]() {
+    mbar_wait(bar_g2, ph_g2);
+    ph_g2 ^= 1;
+    tc_fence_after();
   };
+  // hand-off to the GEMM-chain issuer: this warp's part of the A operand is written and fenced (fence.proxy.async), its
+  // reads of the TMEM columns the GEMM overwrites are complete (tcgen05.fence::before_thread_sync); one arrival per warp
+  auto go = [&]() { ly_warp_arrive(bar_go, lane); };
   // h (TMEM) of the valid rows -> HBM, chunk-major (debug stops only; the tail stores from registers)
   auto store_h = [&](const LayerArgs& a, const LyTile& tl) {
 #pragma unroll 1
@@ -932,7 +1117,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
   }
   if (tid == 0 && (int)blockIdx.x < nitems) {
     const LayerArgs& a0 = p.a[blockIdx.x / ntiles];
-    load_first(a0);
     if (a0.mode == LM_BLOCK) mbar_arrive(bar_kvgo);       // K/V buffers are free: first window phase may load
   }
 
@@ -944,7 +1128,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     const LyTile tl = ly_tile(d, g - l * ntiles);
     const bool more = g + (int)gridDim.x < nitems;
     const LayerArgs& an = p.a[more ? (g + (int)gridDim.x) / ntiles : l];      // the next item's layer
-    auto load_wc = [&](int chunk, uint8_t* slot, uint64_t* bar) { load_w(a.wimg + (int64_t)chunk * (LY_WCHUNK / 2), LY_WCHUNK, slot, bar); };
     // end of an item: every compute thread has issued its stores (csync before); the agent publishes them
     auto item_fin = [&]() {
       if (p.done && tid == 0) mbar_arrive(bar_fin);
@@ -1017,14 +1200,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
       }
       fence_proxy_async();
       tc_fence_before();
-      csync();
-      if (tid == 0) {
-        mbar_wait(bar_w0, ph_w0);
-        tc_fence_after();
-        ly_issue_gemm_ex(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), M / 16, H, false);
-        umma_commit(bar_g);
-      }
-      ph_w0 ^= 1;
+      go();                                               // issuer: h = x W_in^T
       gemm_wait();
       LY_PHASE(0)
     } else {
@@ -1071,21 +1247,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
 
     // ---- banded self-attention -------------------------------------------------------------------------------
     ly_softmax_phase<true, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
-    csync();
+    go();                                                 // issuer: context K/V go-ahead, h += O Wproj^T
     LY_PHASE(1)
 
     // ---- h += O Wproj^T ------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      if (a.stop_phase != 1) mbar_arrive(bar_kvgo);       // context K/V may stream in during the GEMM chain
-      load_wc(WC_Q, sW1, bar_w1);
-      mbar_wait(bar_w0, ph_w0);
-      tc_fence_after();
-      ly_issue_gemm(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), true);
-      umma_commit(bar_g);
-    }
-    ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0) load_wc(WC_OUT, sW0, bar_w0);
 
     // ---- n2 = RMSNorm(h + b_proj) * w2 -> sA ; h + b_proj back to TMEM ---------------------------------------------
     {
@@ -1118,32 +1284,18 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     }
     fence_proxy_async();
     tc_fence_before();
-    csync();
-    if (a.stop_phase == 1) {
-      tc_fence_after();
+    if (a.stop_phase == 1) {                              // debug stop (the issuer drains its prefetch and moves on)
       store_h(a, tl);
-      // drain the prefetches so that the barrier phases stay consistent
-      if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
-      ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
-      if (tid == 0 && more) {
-        load_first(an);
-        mbar_arrive(bar_kvgo);
-      }
+      if (tid == 0 && more) mbar_arrive(bar_kvgo);
       item_fin();
       continue;
     }
+    go();                                                 // issuer: q = n2 Wq^T
     LY_PHASE(2)
 
     // ---- q = n2 Wq^T -> bf16 Q operand in sA -------------------------------------------------------------------------
-    if (tid == 0) {
-      mbar_wait(bar_w1, ph_w1);
-      tc_fence_after();
-      ly_issue_gemm(tmem_base + TM_G, smem_u32(sA), smem_u32(sW1), false);
-      umma_commit(bar_g);
-    }
-    ph_w1 ^= 1;
     gemm_wait();
     {
       float v[80];
@@ -1159,20 +1311,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
 
     // ---- cross attention over the context tokens ---------------------------------------------------------------------
     ly_softmax_phase<false, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
-    csync();
+    go();                                                 // issuer: h += O Wout^T
     LY_PHASE(4)
 
     // ---- h += O Wout^T -----------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      load_wc(WC_F0_X0, sW1, bar_w1);
-      mbar_wait(bar_w0, ph_w0);
-      tc_fence_after();
-      ly_issue_gemm(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), true);
-      umma_commit(bar_g);
-    }
-    ph_w0 ^= 1;
     gemm_wait();
-    if (tid == 0) load_wc(WC_F0_G0, sW0, bar_w0);
 
     // ---- n3 = AdaRMSNorm(h) -> sA --------------------------------------------------------------------------------------
     {
@@ -1197,84 +1340,55 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     }
     fence_proxy_async();
     tc_fence_before();
-    csync();
     if (a.stop_phase == 2) {
-      tc_fence_after();
       store_h(a, tl);
-      if (tid == 0) { mbar_wait(bar_w1, ph_w1); mbar_wait(bar_w0, ph_w0); }
-      ph_w1 ^= 1; ph_w0 ^= 1;
       tc_fence_before();
       csync();
-      if (tid == 0 && more) {
-        load_first(an);
-        mbar_arrive(bar_kvgo);
-      }
+      if (tid == 0 && more) mbar_arrive(bar_kvgo);
       item_fin();
       continue;
     }
+    go();                                                 // issuer: FFN quarters 0 and 1
     LY_PHASE(5)
 
-    // ---- feed-forward: two halves of 160 u columns ---------------------------------------------------------------------
+    // ---- feed-forward in quarters of 80 u columns ------------------------------------------------------------------------
+    // Quarter q = one weight chunk (x rows | gate rows) = one N = 160 GEMM into TMEM buffer q & 1 (TM_G + 160 (q & 1): x 80 | gate 80),
+    // completion on bar_g (even) / bar_g2 (odd).  While the compute threads run the SwiGLU pass of quarter q the tensor core
+    // runs quarter q + 1; a warp's arrival on bar_free[q & 1] tells the issuer that it has read the buffer out and written its
+    // part of u.  u quarters 0..2 go to sU (30 slabs), quarter 3 to sA (n3 is dead once quarter 3's MMAs retired);
+    // h += u W3^T: the k-half of quarters 0 | 1 runs under the last SwiGLU pass.
+    {
+      uint8_t* sU2 = sU + 20 * LY_SLAB;
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-      if (tid == 0) {
-        mbar_wait(bar_w1, ph_w1);
-        mbar_wait(bar_w0, ph_w0);
-        tc_fence_after();
-        ly_issue_gemm(tmem_base + TM_G, smem_u32(sA), smem_u32(sW1), false);          // x part
-        ly_issue_gemm(tmem_base + TM_G + 160, smem_u32(sA), smem_u32(sW0), false);    // gate part
-        umma_commit(bar_g);
-      }
-      ph_w1 ^= 1;
-      ph_w0 ^= 1;
-      gemm_wait();
-      if (tid == 0) {
-        load_wc(half == 0 ? WC_F0_X1 : WC_F3_K0, sW1, bar_w1);
-        load_wc(half == 0 ? WC_F0_G1 : WC_F3_K1, sW0, bar_w0);
-      }
-      uint8_t* dst = half == 0 ? sU : sA;                 // sA (n3) is dead once the second half's MMAs retired
-      const float* bx = sC + LC_F0B + half * 320 + cb;
-      const float* bg = bx + 160;
-#pragma unroll 1
-      for (int i = 0; i < 5; ++i) {
-        float x[16], g[16];
-        tmem_ld16x2(trow + TM_G + cb + 16 * i, x, trow + TM_G + 160 + cb + 16 * i, g);
+      for (int q = 0; q < 4; ++q) {
+        const int b = q & 1;
+        if (b == 0) gemm_wait(); else gemm_wait2();       // quarter q is in TMEM buffer b
+        uint8_t* dst = q < 2 ? sU + q * 10 * LY_SLAB : q == 2 ? sU2 : sA;
+        const float* bx = sC + LC_F0B + q * 160 + 40 * wg;
+        const float* bg = bx + 80;
+        {
+          float x[40], g[40];
+          tmem_ld40(trow + TM_G + 160 * b + 40 * wg, x);
+          tmem_ld40(trow + TM_G + 160 * b + 80 + 40 * wg, g);
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) swiglu2(x + j, g + j, bx + 16 * i + j, bg + 16 * i + j);
-        *reinterpret_cast<uint4*>(dst + (cb / 8 + 2 * i) * LY_SLAB + row * 16) = pack_bf16x8(x);
-        *reinterpret_cast<uint4*>(dst + (cb / 8 + 2 * i + 1) * LY_SLAB + row * 16) = pack_bf16x8(x + 8);
+          for (int j = 0; j < 40; j += 2) swiglu2(x + j, g + j, bx + j, bg + j);
+#pragma unroll
+          for (int i = 0; i < 5; ++i) *reinterpret_cast<uint4*>(dst + (5 * wg + i) * LY_SLAB + row * 16) = pack_bf16x8(x + 8 * i);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        ly_warp_arrive(bar_free + b, lane);
       }
-      fence_proxy_async();
-      tc_fence_before();
-      csync();
     }
     LY_PHASE(6)
 
-    // ---- h += u W3^T --------------------------------------------------------------------------------------------------------
-    if (tid == 0) {
-      mbar_wait(bar_w1, ph_w1);
-      mbar_wait(bar_w0, ph_w0);
-      tc_fence_after();
-      ly_issue_gemm(tmem_base + TM_H, smem_u32(sU), smem_u32(sW1), true);
-      ly_issue_gemm(tmem_base + TM_H, smem_u32(sA), smem_u32(sW0), true);
-      umma_commit(bar_g);
-    }
-    ph_w1 ^= 1;
-    ph_w0 ^= 1;
+    // ---- h += u W3^T (issued by the issuer behind quarter 3) ------------------------------------------------------------------
     gemm_wait();
     if (tid == 0 && more) mbar_arrive(bar_kvgo);          // overlay K/V region is free: next tile's window K/V may load
     }   // LM_BLOCK
     LY_PHASE(7)
 
     // =============== tail: the finished h rows leave the SM; what consumes them next runs right here ===============
-    if (tid == 0) {                                       // both weight slots are free
-      if (a.tail == LT_QKV) {
-        load_w(a.w_qkv, LY_WCHUNK, sW1, bar_w1);
-        load_w(a.w_qkv + LY_WCHUNK / 2, LY_WCHUNK, sW0, bar_w0);
-      } else if (a.tail == LT_FINAL) {
-        load_w(a.w_out, LY_WCHUNK / 2, sW1, bar_w1);
-      }
-    }
     if (lq == 0) LY_TR(wg, 50)
     {
       float v[80];
@@ -1355,39 +1469,21 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     }
     tc_fence_before();
     if (lq == 0) LY_TR(wg, 56)
-    csync();
+    if (a.tail != LT_NONE) go();                          // issuer: the tail's GEMMs (h has been read out, the A operand is in sA)
     if (lq == 0) LY_TR(wg, 57)
     LY_PHASE(8)
 
     if (a.tail == LT_QKV) {
-      // ---- q | k | v of the next block: three 160-column chunks into TMEM columns 0..479 (h is dead) -------------
-      if (tid == 0) {
-        mbar_wait(bar_w1, ph_w1);
-        mbar_wait(bar_w0, ph_w0);
-        tc_fence_after();
-        ly_issue_gemm(tmem_base + 0, smem_u32(sA), smem_u32(sW1), false);
-        ly_issue_gemm(tmem_base + 160, smem_u32(sA), smem_u32(sW0), false);
-        umma_commit(bar_g);
-      }
-      ph_w1 ^= 1;
-      ph_w0 ^= 1;
-      gemm_wait();
-      LY_PHASE(9)
-      if (tid == 0) {
-        load_w(a.w_qkv + 2 * (LY_WCHUNK / 2), LY_WCHUNK, sW1, bar_w1);
-        mbar_wait(bar_w1, ph_w1);
-        tc_fence_after();
-        ly_issue_gemm(tmem_base + 320, smem_u32(sA), smem_u32(sW1), false);
-        umma_commit(bar_g);
-        if (more) load_first(an);                         // slot 0: first chunk of the next item
-      }
-      ph_w1 ^= 1;
-      LY_PHASE(10)
+      // ---- q | k | v of the next block: three 160-column chunks into TMEM columns 0..479 (h is dead), completions on
+      // bar_g, bar_g2, bar_g: each part is converted and stored while the next one is still in the tensor pipe ----
 #pragma unroll 1
       for (int part = 0; part < 3; ++part) {              // q, k as bf16; v as f16 (P V operand)
+        if (part == 1) gemm_wait2(); else gemm_wait();
+        if (part == 0) {
+          ly_warp_arrive(bar_free, lane);                 // q's completion seen: the issuer may commit v on bar_g
+          LY_PHASE(9)
+        }
         if (part == 2) {
-          LY_PHASE(11)
-          gemm_wait();
           LY_PHASE(12)
         }
         {
@@ -1403,15 +1499,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
       }
     } else if (a.tail == LT_FINAL) {
       // ---- eps = out_proj(final_norm(h)) with the update rule applied in registers -----------------------------------
-      if (tid == 0) {
-        mbar_wait(bar_w1, ph_w1);
-        tc_fence_after();
-        ly_issue_gemm_ex(tmem_base + 0, smem_u32(sA), smem_u32(sW1), H / 16, M, false);
-        umma_commit(bar_g);
-      }
-      ph_w1 ^= 1;
       gemm_wait();
-      if (tid == 0 && more) load_first(an);
       const edtts_step_args& sa = p.step;
       // Per-utterance coefficients: the same for every row of the tile (all threads load them, the loads broadcast).
       float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
@@ -1491,8 +1579,6 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
         }
       }
       fence_proxy_async();                                // sA is written next by the following item's bulk copies
-    } else {
-      if (tid == 0 && more) load_first(an);
     }
     // a head item is followed by a block item: its K/V buffers are free
     if (tid == 0 && a.mode == LM_HEAD && more && an.mode == LM_BLOCK) mbar_arrive(bar_kvgo);
