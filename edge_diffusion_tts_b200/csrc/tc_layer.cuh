@@ -426,6 +426,11 @@ __device__ __forceinline__ uint32_t ly_exp2_f16x2(float x_lo, float x_hi) {
 #ifndef LY_POLY_EVERY
 #define LY_POLY_EVERY 0
 #endif
+// -DEDTTS_DEBUG_CLOCKS builds: per-phase clocks of thread 0 only (cheap); -DLY_SOFTMAX_CLOCKS=1 adds the per-section counters
+// inside the softmax steps (~50 registers, they change the schedule of the loop they measure)
+#ifndef LY_SOFTMAX_CLOCKS
+#define LY_SOFTMAX_CLOCKS 0
+#endif
 __device__ __forceinline__ float ly_exp2_poly(float x) {
   x = fmaxf(x, -30.0f);                                   // 2^-30 is far below the smallest f16: no exponent underflow
   const float t = x + 12582912.0f;                        // 1.5 * 2^23: the low mantissa bits of t hold round(x)
@@ -1166,20 +1171,24 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     }
 #endif
 
-    if (tid < H) {                                        // per-utterance AdaLN vectors: gain = w * (1 + scale), shift
-      if (a.mode == LM_BLOCK) {
-        const float* m = a.mod3 + (int64_t)tl.b * d.mod_stride;
-        sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
-        sC[LS_SH3 + tid] = m[H + tid];
+    // per-utterance AdaLN vectors: gain = w * (1 + scale), shift (read after the next CTA barrier at the earliest: n3 / the tail)
+    auto load_adaln = [&]() {
+      if (tid < H) {
+        if (a.mode == LM_BLOCK) {
+          const float* m = a.mod3 + (int64_t)tl.b * d.mod_stride;
+          sC[LS_G3 + tid] = sC[LC_N3W + tid] * (1.0f + m[tid]);
+          sC[LS_SH3 + tid] = m[H + tid];
+        }
+        if (a.tail == LT_QKV) {
+          const float* m = a.mod1 + (int64_t)tl.b * d.mod_stride;
+          sC[LS_TG + tid] = a.n1w[tid] * (1.0f + m[tid]);
+          sC[LS_TS + tid] = m[H + tid];
+        }
       }
-      if (a.tail == LT_QKV) {
-        const float* m = a.mod1 + (int64_t)tl.b * d.mod_stride;
-        sC[LS_TG + tid] = a.n1w[tid] * (1.0f + m[tid]);
-        sC[LS_TS + tid] = m[H + tid];
-      }
-    }
+    };
 
     if (a.mode == LM_HEAD) {
+      load_adaln();
       // ---- h = in_proj(x_t): x tile -> bf16 A operand (K = 80), one MMA chain into the h columns -----------------------
       {
         // 128 rows x 10 groups of 8 columns, consecutive threads on consecutive 32-byte pieces of the (contiguous) tile
@@ -1243,10 +1252,11 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     csync();
     if (lq == 0) LY_TR(wg, 45)
     if (tid == 0) mbar_arrive(bar_attgo);                 // Q in place, attention TMEM columns and P buffers free
+    load_adaln();                                         // (after the go-ahead: read at n3 / in the tail only)
     LY_PHASE(0)
 
     // ---- banded self-attention -------------------------------------------------------------------------------
-    ly_softmax_phase<true, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
+    ly_softmax_phase<true, PROF && LY_SOFTMAX_CLOCKS>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcw : nullptr);
     go();                                                 // issuer: context K/V go-ahead, h += O Wproj^T
     LY_PHASE(1)
 
@@ -1310,7 +1320,7 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
     LY_PHASE(3)
 
     // ---- cross attention over the context tokens ---------------------------------------------------------------------
-    ly_softmax_phase<false, PROF>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
+    ly_softmax_phase<false, PROF && LY_SOFTMAX_CLOCKS>(d, tl, smem, tmem_base, wb, cs, cp, co, (PROF && a.phase_clocks && tid == 0) ? fcx : nullptr);
     go();                                                 // issuer: h += O Wout^T
     LY_PHASE(4)
 
@@ -1416,14 +1426,17 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
           }
         }
       }
-      // h -> HBM: 20 x 16 bytes per thread (the LSU queue makes this ~3 k cycles per tile; interleaving the stores with the
-      // normalisation below was measured slower)
-      if (a.tail != LT_FINAL && row < tl.nq) {
+      // h -> HBM: 20 x 16 bytes per thread (the store path makes this ~3 k cycles per tile).  With a QKV tail the stores are
+      // issued AFTER the hand-off to the issuer below, i.e. under the q | k GEMMs
+      auto store_rows = [&]() {
+        if (row < tl.nq) {
 #pragma unroll
-        for (int q = 0; q < 20; ++q)
-          __stcs(reinterpret_cast<float4*>(d.hc + ((int64_t)(cb / 4 + q) * d.R + tl.row0 + row) * 4),
-                 make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));    // streaming: read next by another SM's launch
-      }
+          for (int q = 0; q < 20; ++q)
+            __stcs(reinterpret_cast<float4*>(d.hc + ((int64_t)(cb / 4 + q) * d.R + tl.row0 + row) * 4),
+                   make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));    // streaming: read next by another SM's launch
+        }
+      };
+      if (a.tail == LT_NONE) store_rows();
       if (lq == 0) LY_TR(wg, 52)
       if (a.tail != LT_NONE) {
         // next norm: AdaRMSNorm (LT_QKV) or LayerNorm (LT_FINAL, exact two-step variance) -> bf16 A operand
@@ -1465,11 +1478,12 @@ __global__ void __launch_bounds__(LY_THREADS, 1) tc_layer_kernel(const __grid_co
         }
         if (lq == 0) LY_TR(wg, 55)
         fence_proxy_async();
+        tc_fence_before();
+        go();                                             // issuer: the tail's GEMMs (h has been read out, the A operand is in sA)
+        if (a.tail == LT_QKV) store_rows();
       }
     }
     tc_fence_before();
-    if (lq == 0) LY_TR(wg, 56)
-    if (a.tail != LT_NONE) go();                          // issuer: the tail's GEMMs (h has been read out, the A operand is in sA)
     if (lq == 0) LY_TR(wg, 57)
     LY_PHASE(8)
 
