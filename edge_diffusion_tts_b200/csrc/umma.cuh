@@ -32,24 +32,37 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// One probe of the phase with the given parity.  The suspend-time hint lets the hardware park the thread until the
-// phase completes (wake-up on completion is immediate) instead of returning to a software spin loop.
+// One probe of the phase with the given parity: mbarrier.try_wait with the implementation's default (short) time limit, called
+// from a software spin loop.  The variant with a suspend-time hint (20 us) parks the warp until the phase completes, but its
+// wake-up latency sits on every hand-off of the kernels here (softmax warp <-> MMA issuer <-> TMA producer chains of a few
+// hundred cycles each): measured on the fused decoder step, hint 9.06 - 9.15 ms, plain try_wait 8.71 - 8.73 ms, non-blocking
+// test_wait 8.78 - 8.80 ms per cfg3 generate (profiles/r2_kernel_experiments.txt).  -DEDTTS_MBAR_SUSPEND_NS=<ns> restores the hint.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
+#ifdef EDTTS_MBAR_SUSPEND_NS
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)(EDTTS_MBAR_SUSPEND_NS))
       : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+#endif
   return ok != 0;
 }
 // Bounded wait: a protocol bug must become a trapped launch (error code at the next
 // CUDA call), never a hung GPU.  (-DEDTTS_MBAR_DEBUG prints the barrier before trapping.)
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 20)) {
+    if (spin > (1u << 24)) {
 #ifdef EDTTS_MBAR_DEBUG
       printf("edtts: mbarrier wait timed out (block %d thread %d, barrier @%u parity %u)\n", blockIdx.x, threadIdx.x,
              smem_u32(bar), parity);
