@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # EDTTS_LIB: development override to A/B a differently compiled build of the same library (tools/build_variant.sh)
 LIB_PATH = os.environ.get("EDTTS_LIB") or os.path.join(_HERE, "lib", "libedtts.so")
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_TF32X3 = 0, 1, 2
 STEP_EPS, STEP_DDIM, STEP_DDPM, STEP_DPM = 0, 1, 2, 3
 N_LAYERS = 4
 
@@ -95,6 +95,9 @@ SIGNATURES = {
     "edtts_dsconv_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "edtts_test_linear": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "edtts_test_attention": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
+    "edtts_test_gemm": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, C.c_float, _p, _i32, _p, _p, _i32, _i32,
+                                  _p, _i64, _p]),
+    "edtts_test_gemm_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "edtts_test_hidden": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32,
                                     _i32, _p]),
 }

@@ -10,6 +10,7 @@
 #include "attention_simt.cuh"
 #include "tc_path.cuh"
 #include "tf32x3.cuh"
+#include "t3_decoder.cuh"
 #include <stdlib.h>
 
 namespace edtts {
@@ -84,7 +85,8 @@ extern "C" int edtts_kernel_classes(void) { return KC_COUNT; }
 extern "C" const char* edtts_kernel_class_name(int cls) {
   static const char* names[KC_COUNT] = {"gemm_simt_fp32", "attn_window_simt_fp32", "attn_cross_simt_fp32", "cond",
                                         "embed_ctx", "vq", "schedule", "dsconv", "tc_gemm_bf16",
-                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc", "tc_layer_bf16", "mel_longform"};
+                                        "tc_attn_window_bf16", "tc_attn_cross_bf16", "tc_misc", "tc_layer_bf16", "mel_longform",
+                                        "t3_gemm_tf32x3", "t3_attn_window_tf32x3", "t3_attn_cross_tf32x3"};
   return (cls >= 0 && cls < KC_COUNT) ? names[cls] : "?";
 }
 
@@ -220,7 +222,34 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
   if (precision == EDTTS_PREC_BF16)
     return tc_test_attention(q, q_stride, k, v, kv_stride, o, B, Tq, Tk, window, as_stream(stream));
   AttnArgs a{q, q_stride, k, v, kv_stride, o, H, Tq, Tk, window, 1.0f / sqrtf((float)HD)};
+  if (precision == EDTTS_PREC_TF32X3) return t3::launch_t3_attn(a, B, as_stream(stream));
   return launch_attn_simt(a, B, as_stream(stream));
+}
+
+extern "C" int64_t edtts_test_gemm_workspace_bytes(int32_t K, int32_t N, int32_t epi) {
+  const bool swi = epi == EPI_SWIGLU;
+  const int NB = (N % 160 == 0 || swi) ? 160 : 80;
+  return t3::t3_gemm_image_floats(K, N, NB, swi) * 4;
+}
+
+extern "C" int edtts_test_gemm(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K, int32_t N,
+                               int32_t pro, int32_t epi, const float* norm_w, const float* norm_b, float norm_eps, const float* mod,
+                               int32_t rows_per_batch, const float* resid, const float* pe, int32_t pe_period, int32_t use_tc,
+                               void* workspace, int64_t workspace_bytes, void* stream) {
+  EDTTS_REQUIRE(x && w && y && rows > 0, EDTTS_EINVAL, "test_gemm: null argument");
+  EDTTS_REQUIRE(pro >= PRO_NONE && pro <= PRO_LN && epi >= EPI_STORE && epi <= EPI_SWIGLU, EDTTS_EINVAL, "test_gemm: pro=%d epi=%d", pro, epi);
+  GemmArgs g;
+  g.A = x; g.rows = rows; g.K = K; g.lda = K; g.W = w; g.N = N; g.bias = bias; g.out = y; g.ldo = N; g.pro = pro; g.epi = epi;
+  g.norm_w = norm_w; g.norm_b = norm_b; g.norm_eps = norm_eps; g.mod = mod; g.mod_stride = 2 * K;
+  g.rows_per_batch = rows_per_batch > 0 ? rows_per_batch : 1; g.resid = resid; g.pe = pe; g.pe_period = pe_period > 0 ? pe_period : 1;
+  if (!use_tc) return launch_gemm_simt(g, as_stream(stream));
+  const bool swi = epi == EPI_SWIGLU;
+  EDTTS_REQUIRE(N % 80 == 0, EDTTS_ENOTSUP, "test_gemm: N=%d (multiple of 80)", N);
+  const int NB = (N % 160 == 0 || swi) ? 160 : 80;
+  EDTTS_REQUIRE(workspace && workspace_bytes >= edtts_test_gemm_workspace_bytes(K, N, epi), EDTTS_ENOSPC, "test_gemm: workspace");
+  int rc = t3::pack_w_blocks(w, reinterpret_cast<float*>(workspace), K, N, NB, swi, as_stream(stream));
+  if (rc) return rc;
+  return t3::launch_t3_gemm(g, reinterpret_cast<const float*>(workspace), t3::t3_gemm_block_stride(K, NB), NB, as_stream(stream));
 }
 
 extern "C" int edtts_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,

@@ -38,7 +38,8 @@ int check_launch(const char* what);          // cudaPeekAtLastError -> EDTTS_ECU
 // (edtts_prof_*): bench.py uses them to time the dominant kernel live.
 enum KernelClass : int {
   KC_GEMM_SIMT = 0, KC_ATTN_WINDOW_SIMT, KC_ATTN_CROSS_SIMT, KC_COND, KC_EMBED, KC_VQ, KC_SCHEDULE, KC_DSCONV,
-  KC_TC_GEMM, KC_TC_ATTN_WINDOW, KC_TC_ATTN_CROSS, KC_TC_MISC, KC_TC_LAYER, KC_MEL, KC_COUNT
+  KC_TC_GEMM, KC_TC_ATTN_WINDOW, KC_TC_ATTN_CROSS, KC_TC_MISC, KC_TC_LAYER, KC_MEL, KC_T3_GEMM, KC_T3_ATTN_WINDOW,
+  KC_T3_ATTN_CROSS, KC_COUNT
 };
 
 // RAII around one kernel launch: counts it and, when profiling is on and the stream is

@@ -5,6 +5,7 @@
 #include "gemm_simt.cuh"
 #include "attention_simt.cuh"
 #include "tc_path.cuh"
+#include "t3_decoder.cuh"
 
 namespace edtts {
 
@@ -204,6 +205,7 @@ extern "C" int64_t edtts_decoder_workspace_bytes(int32_t B, int32_t T, int32_t S
   const int64_t R = (int64_t)B * T;
   (void)S;
   if (precision == EDTTS_PREC_BF16) return tc_decoder_workspace_bytes(B, T, S);
+  if (precision == EDTTS_PREC_TF32X3) return t3::t3_decoder_workspace_bytes(B, T, S);
   return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256);
 }
 
@@ -317,6 +319,7 @@ extern "C" int edtts_decoder_step(const edtts_decoder_weights* w, const float* x
   if (precision == EDTTS_PREC_FP32) return decoder_step_fp32(w, x_t, mod, kv, args, workspace, B, T, S, as_stream(stream));
   if (precision == EDTTS_PREC_BF16)
     return tc_decoder_step(w, x_t, mod, kv, args, workspace, B, T, S, as_stream(stream));
+  if (precision == EDTTS_PREC_TF32X3) return t3::t3_decoder_step(w, x_t, mod, kv, args, workspace, B, T, S, as_stream(stream));
   set_error("decoder_step: unknown precision %d", precision);
   return EDTTS_EINVAL;
 }

@@ -1,0 +1,694 @@
+// EDTTS_PREC_TF32X3: the fp32-grade (max-abs 1e-4) decoder step on the tensor cores.
+//
+// The CUDA-core parity path (decoder.cu: gemm_simt_kernel + attn_simt_kernel) spends 115 ms in its GEMMs and 55 ms in its
+// attentions per cfg3 generate.  Here the same sequence of launches (models/decoder.py:96-109, layers/transformer.py:141-160)
+// runs on tcgen05 with every operand split into a tf32 head and tail (tf32x3.cuh: three kind::tf32 MMAs per k-step, fp32
+// accumulator in tensor memory, ~2^-21 relative per product -- as good as an FFMA chain):
+//
+//   t3_gemm_kernel   y = epi(pro(A) W^T + b) for 128 rows x one NB-column block of W.  A rows stream in 32 columns at a time
+//                    (16-byte cp.async, double-buffered); the RMSNorm / AdaRMSNorm / LayerNorm prologue of gemm_simt.cuh is
+//                    applied on the way into the operand image (row statistics from a pre-pass over the tile); weight chunks
+//                    arrive by one bulk copy each from images packed per step (t3_pack_jobs_kernel: one launch for all 62
+//                    blocks); epilogues: bias, residual, positional table, SwiGLU (x 80 | gate 80 per block), and the fused
+//                    DDIM / DDPM / DPM update rule of the last GEMM.
+//   t3_attn_kernel   one CTA = (utterance, head, 128 queries), 128 threads (thread <-> query <-> tensor-memory lane), keys in
+//                    blocks of 32: S = Q K^T (15 MMAs) -> online softmax in registers (exp2, fp32) -> P split hi / lo into a
+//                    shared-memory operand image -> O_blk = P V (12 MMAs, V staged transposed) -> acc = acc * corr + O_blk in
+//                    registers.  Band (|i - j| <= 64, attention.py:94-111) or full context (mla.py:176-180) by a per-element
+//                    mask; only the key blocks a tile can see are visited.  Two CTAs per SM overlap each other's round trips.
+//
+// A row's result does not depend on the other rows of a launch (batch invariance).
+#define EDTTS_DECL_ONLY
+#include "t3_decoder.cuh"
+#include "tf32x3.cuh"
+
+namespace edtts {
+namespace t3 {
+
+constexpr int GT = 256;                               // threads of the GEMM kernel
+constexpr int XS_LD = KC + 4;                         // padded row of the fp32 staging tile
+
+// ---- weight images ------------------------------------------------------------------------------------------------------
+struct PackJob {
+  const float* W;        // first source row
+  float* img;            // image of the block this job writes into
+  int k, ldw, nrows, row_off, ntot, nchunk;            // rows [row_off, row_off + nrows) of an image with ntot rows
+};
+constexpr int MAX_JOBS = 64;
+struct PackJobs {
+  PackJob j[MAX_JOBS];
+};
+
+// image of a block, per 32-element chunk c: [hi | lo][slab s < 8][row < ntot][4] = W[row][32 c + 4 s + j] (tf32x3.cuh)
+__global__ void t3_pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
+  const PackJob& J = jobs.j[blockIdx.y];
+  const int total = J.nchunk * 8 * J.nrows * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = i & 3, row = (i >> 2) % J.nrows, s = ((i >> 2) / J.nrows) & 7, c = (i >> 2) / (J.nrows * 8);
+    const int kk = KC * c + 4 * s + j;
+    const float w = kk < J.k ? J.W[(int64_t)row * J.ldw + kk] : 0.f;
+    const float hi = tf32_rna(w);
+    const int64_t o = (int64_t)c * (64 * J.ntot) + ((int64_t)s * J.ntot + J.row_off + row) * 4 + j;
+    J.img[o] = hi;
+    J.img[o + 8 * J.ntot * 4] = tf32_rna(w - hi);
+  }
+}
+
+int64_t t3_gemm_block_stride(int K, int NB) { return (int64_t)((K + KC - 1) / KC) * 64 * NB; }
+int64_t t3_gemm_image_floats(int K, int N, int NB, bool swiglu) {
+  const int nblocks = swiglu ? N / (NB / 2) : N / NB;
+  return nblocks * t3_gemm_block_stride(K, NB);
+}
+
+// appends the jobs of one matrix; returns the number of jobs added (or -1)
+static int add_jobs(PackJobs& pj, int n, const float* W, float* img, int K, int N, int NB, bool swiglu) {
+  const int nchunk = (K + KC - 1) / KC;
+  const int64_t stride = t3_gemm_block_stride(K, NB);
+  if (swiglu) {
+    const int half = NB / 2, nblocks = N / half;
+    if (n + 2 * nblocks > MAX_JOBS) return -1;
+    for (int b = 0; b < nblocks; ++b) {
+      pj.j[n++] = PackJob{W + (int64_t)b * half * K, img + b * stride, K, K, half, 0, NB, nchunk};
+      pj.j[n++] = PackJob{W + (int64_t)(N + b * half) * K, img + b * stride, K, K, half, half, NB, nchunk};
+    }
+    return 2 * nblocks;
+  }
+  const int nblocks = N / NB;
+  if (n + nblocks > MAX_JOBS) return -1;
+  for (int b = 0; b < nblocks; ++b) pj.j[n++] = PackJob{W + (int64_t)b * NB * K, img + b * stride, K, K, NB, 0, NB, nchunk};
+  return nblocks;
+}
+static int launch_pack(const PackJobs& pj, int n, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  t3_pack_jobs_kernel<<<dim3(40, n), 256, 0, st>>>(pj);
+  return check_launch("t3_pack_jobs");
+}
+int pack_w_blocks(const float* W, float* img, int K, int N, int NB, bool swiglu, cudaStream_t st) {
+  PackJobs pj;
+  const int n = add_jobs(pj, 0, W, img, K, N, NB, swiglu);
+  EDTTS_REQUIRE(n > 0, EDTTS_EINVAL, "t3 pack: K=%d N=%d NB=%d", K, N, NB);
+  return launch_pack(pj, n, st);
+}
+
+// ---- GEMM -----------------------------------------------------------------------------------------------------------------
+struct T3GemmArgs {
+  GemmArgs g;
+  const float* wimg;
+  int64_t img_stride;
+  int NB, nchunk;
+};
+
+// columns [32 c, 32 c + 32) of the tile's 128 rows -> xs (fp32, row stride XS_LD); rows >= rows and columns >= K are zero
+__device__ __forceinline__ void g_stage_rows(const float* __restrict__ A, int64_t row0, int64_t rows, int K, int lda, int c, float* xs) {
+  for (int i = threadIdx.x; i < TM * (KC / 4); i += GT) {
+    const int r = i >> 3, p = i & 7;
+    const int col = KC * c + 4 * p;
+    float* dst = xs + r * XS_LD + 4 * p;
+    if (row0 + r < rows && col + 3 < K) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(A + (row0 + r) * lda + col) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // K % 4 == 0: a 16-byte piece is all in or all out
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+// thread (r = tid & 127, h = tid >> 7): 16 of the chunk's 32 values of row r, prologue applied (the operation order of
+// gemm_simt_kernel), split into the operand image
+__device__ __forceinline__ void g_split_rows(const GemmArgs& g, const float* xs, uint8_t* sAh, uint8_t* sAl, int c, int64_t row0,
+                                             const float* s_rstd, const float* s_mean) {
+  const int r = threadIdx.x & (TM - 1), h = threadIdx.x >> 7;
+  const int64_t row = row0 + r;
+  const bool live = row < g.rows;
+  float rstd = 1.f, mean = 0.f;
+  const float* m = nullptr;
+  if (g.pro != PRO_NONE) {
+    rstd = s_rstd[r];
+    mean = s_mean[r];
+    if (g.pro == PRO_ADARMS && live) m = g.mod + (row / g.rows_per_batch) * (int64_t)g.mod_stride;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 v4 = *reinterpret_cast<const float4*>(xs + r * XS_LD + 16 * h + 4 * q);
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    if (g.pro != PRO_NONE) {
+      const int k0 = KC * c + 16 * h + 4 * q;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = k0 + j;
+        float x = 0.f;
+        if (live && k < g.K) {
+          x = v[j];
+          if (g.pro == PRO_LN) {
+            x = (x - mean) * rstd * __ldg(g.norm_w + k) + __ldg(g.norm_b + k);
+          } else {
+            x = (x * rstd) * __ldg(g.norm_w + k);
+            if (m) x = x * (1.0f + __ldg(m + k)) + __ldg(m + g.K + k);
+          }
+        }
+        v[j] = x;
+      }
+    }
+    split_store_r(sAh, sAl, 4 * h + q, TM, r, v);
+  }
+}
+
+__global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ T3GemmArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const GemmArgs& g = a.g;
+  const int NB = a.NB;
+  uint8_t* sAh = smem;
+  uint8_t* sAl = smem + A_HALF;
+  uint8_t* sW = smem + 2 * A_HALF;
+  const int w_half = 8 * NB * 16;
+  float* xs0 = reinterpret_cast<float*>(sW + 2 * w_half);
+  float* s_rstd = xs0 + 2 * TM * XS_LD;
+  float* s_mean = s_rstd + TM;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mean + TM);
+  uint64_t* bar_w = bars;
+  uint64_t* bar_mma = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t row0 = (int64_t)blockIdx.x * TM;
+  const float* wimg = a.wimg + (int64_t)blockIdx.y * a.img_stride;
+  const int K = g.K;
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  uint32_t ph_w = 0, ph_m = 0;
+
+  g_stage_rows(g.A, row0, g.rows, K, g.lda, 0, xs0);
+
+  // ---- row statistics of the normalisation prologues (K <= 192), a warp per row ----
+  if (g.pro != PRO_NONE) {
+    for (int r = warp; r < TM; r += GT / 32) {
+      const int64_t row = row0 + r;
+      float v[6];
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int k = lane + 32 * i;
+        v[i] = (row < g.rows && k < K) ? g.A[row * g.lda + k] : 0.f;
+        s += (g.pro == PRO_LN) ? v[i] : v[i] * v[i];
+      }
+      s = warp_sum(s);
+      float mean = 0.f, var;
+      if (g.pro == PRO_LN) {
+        mean = s / (float)K;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int k = lane + 32 * i;
+          const float d = (k < K) ? v[i] - mean : 0.f;
+          q += d * d;
+        }
+        var = warp_sum(q) / (float)K;
+      } else {
+        var = s / (float)K;
+      }
+      if (lane == 0) {
+        s_rstd[r] = 1.0f / sqrtf(var + g.norm_eps);
+        s_mean[r] = mean;
+      }
+    }
+  }
+
+  for (int c = 0; c < a.nchunk; ++c) {
+    const float* xs = xs0 + (c & 1) * TM * XS_LD;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // chunk c staged by every thread; (c = 0) the statistics are written
+    if (c + 1 < a.nchunk) g_stage_rows(g.A, row0, g.rows, K, g.lda, c + 1, xs0 + ((c + 1) & 1) * TM * XS_LD);
+    if (c > 0) {                                       // operand image and weight slot are free once chunk c - 1's MMAs retired
+      mbar_wait(bar_mma, ph_m);
+      ph_m ^= 1;
+      tc_fence_after();
+    }
+    if (tid == 0) {
+      mbar_expect_tx(bar_w, 2 * w_half);
+      bulk_g2s(sW, wimg + (int64_t)c * (2 * w_half / 4), 2 * w_half, bar_w);
+    }
+    g_split_rows(g, xs, sAh, sAl, c, row0, s_rstd, s_mean);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      mbar_wait(bar_w, ph_w);
+      tc_fence_after();
+      const int nks = min(KC, K - KC * c + 7) / 8;
+      issue_chunk(tmem, smem_u32(sAh), smem_u32(sAl), smem_u32(sW), smem_u32(sW) + w_half, nks, NB, c > 0);
+      umma_commit(bar_mma);
+    }
+    ph_w ^= 1;
+  }
+  mbar_wait(bar_mma, ph_m);
+  tc_fence_after();
+
+  // ---- epilogue: thread = (row r, half of the block's output columns), 8 columns at a time --------------------------------
+  {
+    const int lq = warp & 3, half = warp >> 2;
+    const int r = lq * 32 + lane;
+    const int64_t row = row0 + r;
+    const bool valid = row < g.rows;
+    const bool swi = g.epi == EPI_SWIGLU;
+    const int NOUT = swi ? NB / 2 : NB;                // output columns of this block
+    const int n_out0 = blockIdx.y * NOUT;
+    const int ncol = NOUT / 2;                         // a multiple of 8
+    const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+    float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
+    int64_t bidx = 0;
+    if (g.epi == EPI_STEP && valid) {
+      bidx = row / g.rows_per_batch;
+      if (g.step.mode == EDTTS_STEP_DDIM || g.step.mode == EDTTS_STEP_DDPM) {
+        const int64_t t = g.step.t[bidx];
+        ab_t = g.step.alpha_bar[t];
+        if (g.step.mode == EDTTS_STEP_DDIM) {
+          const int64_t tp = g.step.t_prev[bidx];
+          ab_p = (tp >= 0) ? g.step.alpha_bar[tp] : 1.0f;
+        } else {
+          al = g.step.alphas[t];
+          be = g.step.betas[t];
+          pv = g.step.posterior_var[t];
+          nzm = (t > 0) ? 1.0f : 0.0f;
+        }
+      }
+    }
+    for (int c8 = 0; c8 < ncol; c8 += 8) {
+      const int cc = half * ncol + c8;                 // column inside the block
+      float v[8], gt[8];
+      tmem_ld8(trow + cc, v);
+      if (swi) tmem_ld8(trow + NOUT + cc, gt);
+      if (!valid) continue;
+      const int col0 = n_out0 + cc;
+      const int64_t o0 = row * g.ldo + col0;
+      float res[8];
+      if (g.epi == EPI_RESID) {
+        const float4 r0 = *reinterpret_cast<const float4*>(g.resid + o0), r1 = *reinterpret_cast<const float4*>(g.resid + o0 + 4);
+        res[0] = r0.x; res[1] = r0.y; res[2] = r0.z; res[3] = r0.w; res[4] = r1.x; res[5] = r1.y; res[6] = r1.z; res[7] = r1.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = col0 + j;
+        float x = v[j];
+        if (g.bias) x += __ldg(g.bias + col);
+        switch (g.epi) {
+          case EPI_GELU: x = gelu_erf(x); break;
+          case EPI_RESID: x = res[j] + x; break;
+          case EPI_PE: x += __ldg(g.pe + (int64_t)(row % g.pe_period) * g.N + col); break;
+          case EPI_SWIGLU: {
+            float gate = gt[j];
+            if (g.bias) gate += __ldg(g.bias + g.N + col);
+            x = x * silu(gate);
+          } break;
+          default: break;
+        }
+        v[j] = x;
+      }
+      if (g.epi == EPI_STEP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int64_t o = o0 + j;
+          const float e = v[j];
+          if (g.step.eps_out) g.step.eps_out[o] = e;
+          if (g.step.mode == EDTTS_STEP_DDIM) {
+            float xp, x0;
+            ddim_update(g.x_t[o], e, 0.f, ab_t, ab_p, 0.f, xp, x0);
+            if (g.step.x0_out) g.step.x0_out[o] = x0;
+            if (g.step.write_x_prev && g.step.x_prev_out) g.step.x_prev_out[o] = xp;
+          } else if (g.step.mode == EDTTS_STEP_DDPM) {
+            g.step.x_prev_out[o] = ddpm_update(g.x_t[o], e, g.step.noise[o], al, ab_t, be, pv, nzm);
+          } else if (g.step.mode == EDTTS_STEP_DPM) {
+            const int ord = g.step.dpm_order;
+            float xp, x0;
+            dpm_update(g.x_t[o], e, ord >= 2 ? g.step.dpm_hist1[o] : 0.f, ord >= 3 ? g.step.dpm_hist2[o] : 0.f,
+                       g.step.dpm_coef + bidx * 8, ord, g.step.dpm_predict_x0 ? 1 : 0, xp, x0);
+            if (g.step.x0_out) g.step.x0_out[o] = x0;
+            g.step.x_prev_out[o] = xp;
+          }
+        }
+      } else {
+        *reinterpret_cast<float4*>(g.out + o0) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(g.out + o0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+static int gemm_smem(int NB) { return 2 * A_HALF + 2 * 8 * NB * 16 + 2 * TM * XS_LD * 4 + 2 * TM * 4 + 64; }
+
+int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st) {
+  const bool swi = g.epi == EPI_SWIGLU;
+  const int nout = swi ? NB / 2 : NB;
+  EDTTS_REQUIRE(g.rows > 0 && g.K % 4 == 0 && g.lda % 4 == 0 && g.ldo % 4 == 0 && NB % 16 == 0 && NB <= 256 && nout % 16 == 0 &&
+                    g.N % nout == 0,
+                EDTTS_EINVAL, "t3_gemm: rows=%lld K=%d N=%d NB=%d unsupported", (long long)g.rows, g.K, g.N, NB);
+  EDTTS_REQUIRE(g.pro == PRO_NONE || g.K <= 192, EDTTS_EINVAL, "t3_gemm: norm prologue needs K <= 192 (K=%d)", g.K);
+  T3GemmArgs a;
+  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = (g.K + KC - 1) / KC;
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160)) != cudaSuccess)
+      return check_launch("t3_gemm smem attribute");
+    configured.set();
+  }
+  EDTTS_REQUIRE(NB <= 160, EDTTS_EINVAL, "t3_gemm: NB=%d (<= 160: two CTAs per SM)", NB);
+  LaunchScope ls(KC_T3_GEMM, st);
+  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT, gemm_smem(NB), st>>>(a);
+  return check_launch("t3_gemm");
+}
+
+// ---- attention --------------------------------------------------------------------------------------------------------------
+constexpr int AQ = 128;                               // queries per CTA (= threads = MMA M)
+constexpr int AKB = 32;                               // keys per block
+constexpr int A_Q_HALF = (HD / 4) * AQ * 16;          // 10 slabs x 128 rows x 16 B
+constexpr int A_K_HALF = (HD / 4) * AKB * 16;         // 10 slabs x 32 keys x 16 B
+constexpr int A_VN = 48;                              // head_dim padded to an MMA N (rows 40..47 of the V^T image stay zero)
+constexpr int A_V_HALF = (AKB / 4) * A_VN * 16;       // 8 slabs x 48 rows x 16 B
+constexpr int A_P_HALF = (AKB / 4) * AQ * 16;         // 8 slabs x 128 rows x 16 B
+constexpr int A_SMEM = 2 * (A_Q_HALF + A_K_HALF + A_V_HALF + A_P_HALF) + 64;
+constexpr int A_NLD = (AKB * (HD / 4) + AQ - 1) / AQ; // 16-byte pieces of a K (or V) block per thread: 320 / 128 -> 3
+
+__global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sQh = smem;
+  uint8_t* sQl = sQh + A_Q_HALF;
+  uint8_t* sKh = sQl + A_Q_HALF;
+  uint8_t* sKl = sKh + A_K_HALF;
+  uint8_t* sVh = sKl + A_K_HALF;
+  uint8_t* sVl = sVh + A_V_HALF;
+  uint8_t* sPh = sVl + A_V_HALF;
+  uint8_t* sPl = sPh + A_P_HALF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPl + A_P_HALF);
+  uint64_t* bar_s = bars;
+  uint64_t* bar_o = bars + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int q0 = blockIdx.x * AQ;
+  const int qi = q0 + tid;
+  const bool active = qi < a.Tq;
+  const int W = a.window;
+
+  if (tid == 0) {
+    mbar_init(bar_s, 1);
+    mbar_init(bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<128>(tmem_slot);
+  if (tid < 64) {                                      // padding rows 40..47 of the V^T images
+    const int slab = tid >> 3, row = HD + (tid & 7);
+    *reinterpret_cast<float4*>(sVh + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sVl + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  {                                                    // this thread's query row, pre-scaled by scale * log2(e)
+    const float qs = a.scale * 1.4426950408889634f;
+    const float* qp = a.q + ((int64_t)b * a.Tq + (active ? qi : 0)) * a.q_stride + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) t = *reinterpret_cast<const float4*>(qp + d);
+      const float v[4] = {t.x * qs, t.y * qs, t.z * qs, t.w * qs};
+      split_store_r(sQh, sQl, d >> 2, AQ, tid, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tS = 0, tO = AKB;                     // columns: S block (32) | O block (48)
+
+  int klo = 0, khi = a.Tk;
+  if (W >= 0) {
+    klo = max(0, q0 - W);
+    khi = min(a.Tk, q0 + AQ + W);
+  }
+  const int nblk = (khi - klo + AKB - 1) / AKB;
+  const float* kbase = a.k + (int64_t)b * a.Tk * a.kv_stride + h * HD;
+  const float* vbase = a.v + (int64_t)b * a.Tk * a.kv_stride + h * HD;
+
+  float4 kreg[A_NLD], vreg[A_NLD];
+  auto fetch = [&](int kc) {                           // K / V rows kc .. kc + 31 -> registers (zeros beyond khi)
+#pragma unroll
+    for (int it = 0; it < A_NLD; ++it) {
+      const int idx = tid + it * AQ;
+      const int key = idx / (HD / 4), c4 = idx % (HD / 4);
+      kreg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vreg[it] = kreg[it];
+      if (idx < AKB * (HD / 4) && kc + key < khi) {
+        kreg[it] = *reinterpret_cast<const float4*>(kbase + (int64_t)(kc + key) * a.kv_stride + 4 * c4);
+        vreg[it] = *reinterpret_cast<const float4*>(vbase + (int64_t)(kc + key) * a.kv_stride + 4 * c4);
+      }
+    }
+  };
+  auto stash = [&]() {                                 // registers -> operand images: K [slab = dim / 4][key][4], V^T [key / 4][dim][4]
+#pragma unroll
+    for (int it = 0; it < A_NLD; ++it) {
+      const int idx = tid + it * AQ;
+      if (idx >= AKB * (HD / 4)) continue;
+      const int key = idx / (HD / 4), c4 = idx % (HD / 4);
+      {
+        const float v[4] = {kreg[it].x, kreg[it].y, kreg[it].z, kreg[it].w};
+        split_store_r(sKh, sKl, c4, AKB, key, v);
+      }
+      {
+        const float v[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
+        const int off = (key >> 2) * (A_VN * 16) + (key & 3) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float hi = tf32_rna(v[j]);
+          *reinterpret_cast<float*>(sVh + off + (4 * c4 + j) * 16) = hi;
+          *reinterpret_cast<float*>(sVl + off + (4 * c4 + j) * 16) = tf32_rna(v[j] - hi);
+        }
+      }
+    }
+  };
+
+  float m = -INFINITY, l = 0.f;
+  float acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  uint32_t ph = 0;
+
+  if (nblk > 0) fetch(klo);
+  for (int blk = 0; blk < nblk; ++blk) {
+    const int kc = klo + blk * AKB;
+    // the previous block's MMAs have retired (this thread waited for bar_o): K / V / P images are free
+    stash();
+    if (blk + 1 < nblk) fetch(kc + AKB);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chunk(tmem + tS, smem_u32(sQh), smem_u32(sQl), smem_u32(sKh), smem_u32(sKl), HD / 8, AKB, false);
+      umma_commit(bar_s);
+    }
+    mbar_wait(bar_s, ph);
+    tc_fence_after();
+    float s[AKB];
+    tmem_ld32(trow + tS, s);
+    // ---- online softmax (exp2 domain; the scores already carry scale * log2 e) ----
+    float bm = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < AKB; ++j) {
+      const int key = kc + j;
+      const bool ok = active && key < khi && (W < 0 || (key >= qi - W && key <= qi + W));
+      s[j] = ok ? s[j] : -INFINITY;
+      bm = fmaxf(bm, s[j]);
+    }
+    const float m_new = fmaxf(m, bm);
+    const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m - m_new);
+    l *= corr;
+#pragma unroll
+    for (int j = 0; j < AKB; ++j) {
+      const float p = (s[j] == -INFINITY) ? 0.f : exp2f(s[j] - m_new);
+      l += p;
+      s[j] = p;
+    }
+    m = m_new;
+#pragma unroll
+    for (int q4 = 0; q4 < AKB / 4; ++q4) split_store_r(sPh, sPl, q4, AQ, tid, s + 4 * q4);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, false);
+      umma_commit(bar_o);
+    }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] *= corr;
+    mbar_wait(bar_o, ph);
+    tc_fence_after();
+    float o[HD];
+    tmem_ld40(trow + tO, o);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) acc[d] += o[d];
+    ph ^= 1;
+  }
+  if (active) {
+    const float inv = 1.0f / l;
+    float* op = a.o + ((int64_t)b * a.Tq + qi) * a.o_stride + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4)
+      *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st) {
+  EDTTS_REQUIRE(a.q_stride % 4 == 0 && a.kv_stride % 4 == 0 && a.o_stride % 4 == 0, EDTTS_EINVAL, "t3_attn: strides must be multiples of 4");
+  static PerDeviceOnce configured;
+  if (configured.need()) {
+    if (cudaFuncSetAttribute(t3_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM) != cudaSuccess)
+      return check_launch("t3_attn smem attribute");
+    configured.set();
+  }
+  dim3 grid((a.Tq + AQ - 1) / AQ, NH, B);
+  LaunchScope ls(a.window >= 0 ? KC_T3_ATTN_WINDOW : KC_T3_ATTN_CROSS, st);
+  t3_attn_kernel<<<grid, AQ, A_SMEM, st>>>(a);
+  return check_launch("t3_attn");
+}
+
+// ---- one decoder evaluation ---------------------------------------------------------------------------------------------------
+// weight images, in the order the step uses them (floats)
+struct ImgLayout {
+  int64_t in_proj, out_proj, layer[NL], total;
+  int64_t qkv, proj, q, out, f0, f3;                   // offsets inside a layer
+};
+static ImgLayout img_layout() {
+  ImgLayout L;
+  int64_t o = 0;
+  L.in_proj = o; o += t3_gemm_image_floats(M, H, 160, false);
+  L.out_proj = o; o += t3_gemm_image_floats(H, M, 80, false);
+  int64_t p = 0;
+  L.qkv = p; p += t3_gemm_image_floats(H, 3 * H, 160, false);
+  L.proj = p; p += t3_gemm_image_floats(H, H, 160, false);
+  L.q = p; p += t3_gemm_image_floats(H, H, 160, false);
+  L.out = p; p += t3_gemm_image_floats(H, H, 160, false);
+  L.f0 = p; p += t3_gemm_image_floats(H, FFN, 160, true);
+  L.f3 = p; p += t3_gemm_image_floats(FFN, H, 160, false);
+  for (int l = 0; l < NL; ++l) { L.layer[l] = o; o += p; }
+  L.total = o;
+  return L;
+}
+
+int64_t t3_decoder_workspace_bytes(int B, int T, int S) {
+  (void)S;
+  const int64_t R = (int64_t)B * T;
+  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256);
+}
+
+int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
+                    void* workspace, int B, int T, int S, cudaStream_t st) {
+  const int64_t R = (int64_t)B * T;
+  char* ws = reinterpret_cast<char*>(workspace);
+  float* h = reinterpret_cast<float*>(ws);
+  float* a = reinterpret_cast<float*>(ws + align_up(R * H * 4, 256));
+  float* big = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256));
+  float* img = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256));
+  const ImgLayout IL = img_layout();
+  const float scale = 1.0f / sqrtf((float)HD);
+  const int64_t s160 = t3_gemm_block_stride(H, 160), s80 = t3_gemm_block_stride(H, 80), s_in = t3_gemm_block_stride(M, 160),
+                s320 = t3_gemm_block_stride(FFN, 160);
+  int rc;
+  {  // weight images of this step (the parameters are read live, as on the CUDA-core path): one launch
+    PackJobs pj;
+    int n = 0, k;
+    if ((k = add_jobs(pj, n, w->in_proj_w, img + IL.in_proj, M, H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+    if ((k = add_jobs(pj, n, w->out_proj_w, img + IL.out_proj, H, M, 80, false)) < 0) return EDTTS_EINVAL; n += k;
+    for (int l = 0; l < NL; ++l) {
+      const edtts_layer_weights& L = w->layers[l];
+      float* li = img + IL.layer[l];
+      if ((k = add_jobs(pj, n, L.attn_qkv_w, li + IL.qkv, H, 3 * H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.attn_proj_w, li + IL.proj, H, H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.q_proj_w, li + IL.q, H, H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.cross_out_w, li + IL.out, H, H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.ffn0_w, li + IL.f0, H, FFN, 160, true)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.ffn3_w, li + IL.f3, FFN, H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+    }
+    if ((rc = launch_pack(pj, n, st))) return rc;
+  }
+  {  // h = in_proj(x_t) + pe[:T]   (decoder.py:96-97)
+    GemmArgs g;
+    g.A = x_t; g.rows = R; g.K = M; g.lda = M; g.W = w->in_proj_w; g.N = H; g.bias = w->in_proj_b;
+    g.out = h; g.ldo = H; g.epi = EPI_PE; g.pe = w->pos_pe; g.pe_period = T;
+    if ((rc = launch_t3_gemm(g, img + IL.in_proj, s_in, 160, st))) return rc;
+  }
+  for (int l = 0; l < NL; ++l) {
+    const edtts_layer_weights& L = w->layers[l];
+    const float* li = img + IL.layer[l];
+    {  // qkv = attn.qkv(norm1(h, cond))   (transformer.py:143, attention.py:90)
+      GemmArgs g;
+      g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = L.attn_qkv_w; g.N = 3 * H; g.out = big; g.ldo = 3 * H;
+      g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H;
+      g.mod_stride = 2 * NL * 2 * H; g.rows_per_batch = T;
+      if ((rc = launch_t3_gemm(g, li + IL.qkv, s160, 160, st))) return rc;
+    }
+    {  // banded self-attention (attention.py:94-111)
+      AttnArgs at{big, 3 * H, big + H, big + 2 * H, 3 * H, a, H, T, T, WIN, scale};
+      if ((rc = launch_t3_attn(at, B, st))) return rc;
+    }
+    {  // h += attn.proj(o)   (attention.py:123, transformer.py:146)
+      GemmArgs g;
+      g.A = a; g.rows = R; g.K = H; g.lda = H; g.W = L.attn_proj_w; g.N = H; g.bias = L.attn_proj_b;
+      g.out = h; g.ldo = H; g.epi = EPI_RESID; g.resid = h;
+      if ((rc = launch_t3_gemm(g, li + IL.proj, s160, 160, st))) return rc;
+    }
+    {  // q = q_proj(norm2(h))   (transformer.py:151, mla.py:139)
+      GemmArgs g;
+      g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = L.q_proj_w; g.N = H; g.out = big; g.ldo = H;
+      g.pro = PRO_RMS; g.norm_w = L.norm2_w;
+      if ((rc = launch_t3_gemm(g, li + IL.q, s160, 160, st))) return rc;
+    }
+    {  // full cross-attention over the S context tokens (mla.py:176-180)
+      const float* kvl = kv + (int64_t)l * B * S * 2 * H;
+      AttnArgs at{big, H, kvl, kvl + H, 2 * H, a, H, T, S, -1, scale};
+      if ((rc = launch_t3_attn(at, B, st))) return rc;
+    }
+    {  // h += out_proj(o)   (mla.py:194)
+      GemmArgs g;
+      g.A = a; g.rows = R; g.K = H; g.lda = H; g.W = L.cross_out_w; g.N = H; g.out = h; g.ldo = H;
+      g.epi = EPI_RESID; g.resid = h;
+      if ((rc = launch_t3_gemm(g, li + IL.out, s160, 160, st))) return rc;
+    }
+    {  // u = swiglu(ffn.net.0(norm3(h, cond)))   (transformer.py:155, :13-23)
+      GemmArgs g;
+      g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = L.ffn0_w; g.N = FFN; g.bias = L.ffn0_b;
+      g.out = big; g.ldo = FFN; g.epi = EPI_SWIGLU;
+      g.pro = PRO_ADARMS; g.norm_w = L.norm3_norm_w; g.mod = mod + (int64_t)(2 * l + 1) * 2 * H;
+      g.mod_stride = 2 * NL * 2 * H; g.rows_per_batch = T;
+      if ((rc = launch_t3_gemm(g, li + IL.f0, s160, 160, st))) return rc;
+    }
+    {  // h += ffn.net.3(u)
+      GemmArgs g;
+      g.A = big; g.rows = R; g.K = FFN; g.lda = FFN; g.W = L.ffn3_w; g.N = H; g.bias = L.ffn3_b;
+      g.out = h; g.ldo = H; g.epi = EPI_RESID; g.resid = h;
+      if ((rc = launch_t3_gemm(g, li + IL.f3, s320, 160, st))) return rc;
+    }
+  }
+  {  // eps = out_proj(final_norm(h)) + fused update   (decoder.py:108-109, schedule.py)
+    GemmArgs g;
+    g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = w->out_proj_w; g.N = M; g.bias = w->out_proj_b;
+    g.out = nullptr; g.ldo = M; g.epi = EPI_STEP; g.pro = PRO_LN; g.norm_w = w->final_norm_w;
+    g.norm_b = w->final_norm_b; g.norm_eps = 1e-5f; g.rows_per_batch = T; g.x_t = x_t; g.step = *args;
+    if ((rc = launch_t3_gemm(g, img + IL.out_proj, s80, 80, st))) return rc;
+  }
+  return EDTTS_OK;
+}
+
+}  // namespace t3
+}  // namespace edtts

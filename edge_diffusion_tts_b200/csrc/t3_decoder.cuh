@@ -1,0 +1,29 @@
+// fp32-grade decoder step on the tensor cores (EDTTS_PREC_TF32X3): every Linear of the path as a tf32 x 3 GEMM with the
+// normalisation prologues / epilogues of gemm_simt.cuh, both attentions as a tf32 x 3 streaming kernel (t3_decoder.cu).
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"        // GemmArgs; a translation unit other than decoder.cu defines EDTTS_DECL_ONLY first
+#include "attention_simt.cuh"   // AttnArgs
+
+namespace edtts {
+namespace t3 {
+
+// y = epi(pro(A) W^T + bias) with the semantics of launch_gemm_simt (g.W is only read by the packer): the weight matrix comes
+// as operand images of NB-row blocks (pack_w_blocks), block j at wimg + j * img_stride floats.  EPI_SWIGLU: block j holds the x
+// rows 80 j .. 80 j + 79 followed by their gate rows (NB = 160) and produces output columns 80 j .. 80 j + 79.
+int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st);
+// weight images of W [N or 2N][K] for launch_t3_gemm into img (t3_gemm_image_floats(K, N, swiglu) floats), one launch
+int pack_w_blocks(const float* W, float* img, int K, int N, int NB, bool swiglu, cudaStream_t st);
+int64_t t3_gemm_image_floats(int K, int N, int NB, bool swiglu);
+int64_t t3_gemm_block_stride(int K, int NB);
+
+// attention with the semantics of launch_attn_simt
+int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st);
+
+// one decoder evaluation (decoder.cu: decoder_step_fp32 with the kernels above); workspace as sized below
+int64_t t3_decoder_workspace_bytes(int B, int T, int S);
+int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
+                    void* workspace, int B, int T, int S, cudaStream_t st);
+
+}  // namespace t3
+}  // namespace edtts

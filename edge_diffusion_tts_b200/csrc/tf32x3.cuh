@@ -51,6 +51,16 @@ __device__ __forceinline__ void split_store(uint8_t* sAh, uint8_t* sAl, int slab
   *reinterpret_cast<float4*>(sAl + slab * (TM * 16) + r * 16) = lo;
 }
 
+// the same with the tail rounded to tf32 as well (cvt.rna): the MMA TRUNCATES the low 13 bits of a 32-bit operand, which on the
+// exact tail x - hi is an error of up to 2^-21 |x|, always toward zero; rounded to nearest it is 2^-22 |x| and unbiased
+__device__ __forceinline__ void split_store_r(uint8_t* sAh, uint8_t* sAl, int slab, int rows, int r, const float* v) {
+  float4 hi, lo;
+  hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+  lo.x = tf32_rna(v[0] - hi.x); lo.y = tf32_rna(v[1] - hi.y); lo.z = tf32_rna(v[2] - hi.z); lo.w = tf32_rna(v[3] - hi.w);
+  *reinterpret_cast<float4*>(sAh + slab * (rows * 16) + r * 16) = hi;
+  *reinterpret_cast<float4*>(sAl + slab * (rows * 16) + r * 16) = lo;
+}
+
 // the three MMAs of every 8-element k-step of one chunk: D[128 x n] (+)= A[128 x 8 nks] W[n x 8 nks]^T
 __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t ah, uint32_t al, uint32_t wh, uint32_t wl, int nks, int n,
                                             bool accumulate) {

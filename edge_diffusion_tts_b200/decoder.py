@@ -89,7 +89,9 @@ _next_uid = [0]
 
 
 class EdgeDiffusionDecoder(nn.Module):
-    #: arithmetic of the contractions: "fp32" (parity path) or "bf16" (tcgen05 tensor cores)
+    #: arithmetic of the contractions: "fp32" (max-abs 1e-4 parity bar; tf32 x 3 split products on the tcgen05 tensor cores,
+    #: fp32 accumulate), "bf16" (fused tcgen05 kernel, 1e-2 rel-L2) or "fp32_simt" (the CUDA-core FFMA kernels, the checker
+    #: the "fp32" path is tested against)
     precision: str = "fp32"
 
     def __init__(self, cfg):
@@ -197,9 +199,10 @@ class EdgeDiffusionDecoder(nn.Module):
         return (self._uid, self.weights_epoch)
 
     def _prec(self) -> int:
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError(f"precision must be 'fp32' or 'bf16', got {self.precision!r}")
-        return _lib.PREC_BF16 if self.precision == "bf16" else _lib.PREC_FP32
+        try:
+            return {"fp32": _lib.PREC_TF32X3, "bf16": _lib.PREC_BF16, "fp32_simt": _lib.PREC_FP32}[self.precision]
+        except KeyError:
+            raise ValueError(f"precision must be 'fp32', 'bf16' or 'fp32_simt', got {self.precision!r}") from None
 
     def workspace_bytes(self, B: int, T: int, S: int):
         """(context bytes, step bytes) a caller must provide to own the scratch itself."""

@@ -54,6 +54,9 @@ extern "C" {
 /* arithmetic of the decoder contractions */
 #define EDTTS_PREC_FP32 0    /* CUDA-core FFMA, fp32 in / fp32 accumulate (parity path, 1e-4) */
 #define EDTTS_PREC_BF16 1    /* tcgen05 tensor cores, bf16 in / fp32 accumulate (1e-2 rel-L2)  */
+#define EDTTS_PREC_TF32X3 2  /* tcgen05 tensor cores, every operand split tf32 hi + lo, three MMAs per product,
+                              * fp32 accumulate: fp32-grade (1e-4) results at tensor-core speed (decoder step only;
+                              * edtts_context_prepare computes the once-per-utterance K | V with the FP32 kernels) */
 
 /* epilogue fused into the last kernel of a decoder step */
 #define EDTTS_STEP_EPS 0     /* write eps only           (decoder.py:109)          */
@@ -325,6 +328,16 @@ int edtts_test_linear(const float* x, const float* w, const float* bias, float* 
 int edtts_test_attention(const float* q, int32_t q_stride, const float* k, const float* v, int32_t kv_stride,
                          float* o, int32_t B, int32_t Tq, int32_t Tk, int32_t window, int32_t precision,
                          void* stream);
+
+/* y[rows,N] = epi(pro(x)[rows,K] @ w^T + bias) with the fused prologues / epilogues of the fp32 paths, on the CUDA cores
+ * (use_tc = 0) or as a tf32 x 3 tensor-core GEMM (use_tc = 1; workspace: edtts_test_gemm_workspace_bytes).
+ * pro: 0 none, 1 RMSNorm(norm_w), 2 AdaRMSNorm(norm_w; mod [rows / rows_per_batch][2K] = scale | shift), 3 LayerNorm(norm_w,
+ * norm_b); epi: 0 store, 1 GELU, 2 + resid [rows,N], 3 + pe [(row % pe_period), N], 4 SwiGLU (w has 2N rows, bias 2N). */
+int edtts_test_gemm(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K, int32_t N,
+                    int32_t pro, int32_t epi, const float* norm_w, const float* norm_b, float norm_eps, const float* mod,
+                    int32_t rows_per_batch, const float* resid, const float* pe, int32_t pe_period, int32_t use_tc,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+int64_t edtts_test_gemm_workspace_bytes(int32_t K, int32_t N, int32_t epi);
 
 /* Residual stream h [B*T,160] of the bf16 path after in_proj and `n_layers` transformer blocks, the last block
  * optionally stopped early: stop_phase 1 = after x + attn(norm1(x)) (transformer.py:146), 2 = after the
