@@ -26,7 +26,6 @@ namespace edtts {
 namespace t3 {
 
 constexpr int GT = 256;                               // threads of the GEMM kernel
-constexpr int XS_LD = KC + 4;                         // padded row of the fp32 staging tile
 
 // ---- weight images ------------------------------------------------------------------------------------------------------
 struct PackJob {
@@ -91,101 +90,78 @@ int pack_w_blocks(const float* W, float* img, int K, int N, int NB, bool swiglu,
 }
 
 // ---- GEMM -----------------------------------------------------------------------------------------------------------------
+// One CTA = 128 rows x one NB-column block, 256 threads, two CTAs per SM.  The contraction runs in chunks of 16 elements (two
+// k-steps, six MMAs): the A values of a chunk are read straight from global memory into registers two chunks ahead (a warp
+// instruction covers 8 rows x 64 contiguous bytes), get the normalisation prologue, are split hi / lo and stored into one of TWO
+// operand-image buffers; the weight chunk arrives by two bulk copies (hi, lo) into one of THREE buffers, requested a whole
+// iteration before its MMAs; so chunk c + 1 is prepared while the MMAs of chunk c run.  Epilogue: accumulator -> registers
+// (+ bias, SwiGLU) -> a shared-memory tile over the operand buffers -> coalesced 16-byte global accesses for the residual / PE
+// / update-rule operands and the output (row-strided per-thread accesses cost a 32-line transaction per warp instruction).
 struct T3GemmArgs {
   GemmArgs g;
   const float* wimg;
   int64_t img_stride;
-  int NB, nchunk;
+  int NB, nchunk, main_bytes;
 };
-
-// columns [32 c, 32 c + 32) of the tile's 128 rows -> xs (fp32, row stride XS_LD); rows >= rows and columns >= K are zero
-__device__ __forceinline__ void g_stage_rows(const float* __restrict__ A, int64_t row0, int64_t rows, int K, int lda, int c, float* xs) {
-  for (int i = threadIdx.x; i < TM * (KC / 4); i += GT) {
-    const int r = i >> 3, p = i & 7;
-    const int col = KC * c + 4 * p;
-    float* dst = xs + r * XS_LD + 4 * p;
-    if (row0 + r < rows && col + 3 < K) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(A + (row0 + r) * lda + col) : "memory");
-    } else {
-      *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);   // K % 4 == 0: a 16-byte piece is all in or all out
-    }
-  }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-
-// thread (r = tid & 127, h = tid >> 7): 16 of the chunk's 32 values of row r, prologue applied (the operation order of
-// gemm_simt_kernel), split into the operand image
-__device__ __forceinline__ void g_split_rows(const GemmArgs& g, const float* xs, uint8_t* sAh, uint8_t* sAl, int c, int64_t row0,
-                                             const float* s_rstd, const float* s_mean) {
-  const int r = threadIdx.x & (TM - 1), h = threadIdx.x >> 7;
-  const int64_t row = row0 + r;
-  const bool live = row < g.rows;
-  float rstd = 1.f, mean = 0.f;
-  const float* m = nullptr;
-  if (g.pro != PRO_NONE) {
-    rstd = s_rstd[r];
-    mean = s_mean[r];
-    if (g.pro == PRO_ADARMS && live) m = g.mod + (row / g.rows_per_batch) * (int64_t)g.mod_stride;
-  }
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const float4 v4 = *reinterpret_cast<const float4*>(xs + r * XS_LD + 16 * h + 4 * q);
-    float v[4] = {v4.x, v4.y, v4.z, v4.w};
-    if (g.pro != PRO_NONE) {
-      const int k0 = KC * c + 16 * h + 4 * q;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = k0 + j;
-        float x = 0.f;
-        if (live && k < g.K) {
-          x = v[j];
-          if (g.pro == PRO_LN) {
-            x = (x - mean) * rstd * __ldg(g.norm_w + k) + __ldg(g.norm_b + k);
-          } else {
-            x = (x * rstd) * __ldg(g.norm_w + k);
-            if (m) x = x * (1.0f + __ldg(m + k)) + __ldg(m + g.K + k);
-          }
-        }
-        v[j] = x;
-      }
-    }
-    split_store_r(sAh, sAl, 4 * h + q, TM, r, v);
-  }
-}
+constexpr int GK = 16;                                // contraction elements per pipeline chunk
+constexpr int G_A_BUF = 2 * (GK / 4) * TM * 16;       // hi | lo operand image of one chunk: 16,384 B
+constexpr int G_NW = 3;                               // weight chunk buffers
 
 __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ T3GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const GemmArgs& g = a.g;
   const int NB = a.NB;
-  uint8_t* sAh = smem;
-  uint8_t* sAl = smem + A_HALF;
-  uint8_t* sW = smem + 2 * A_HALF;
-  const int w_half = 8 * NB * 16;
-  float* xs0 = reinterpret_cast<float*>(sW + 2 * w_half);
-  float* s_rstd = xs0 + 2 * TM * XS_LD;
+  const int w_half = (GK / 4) * NB * 16;              // hi (or lo) part of a weight chunk
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + 2 * G_A_BUF;
+  float* s_rstd = reinterpret_cast<float*>(smem + a.main_bytes);
   float* s_mean = s_rstd + TM;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mean + TM);
-  uint64_t* bar_w = bars;
-  uint64_t* bar_mma = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_mean + TM);     // [G_NW]
+  uint64_t* bar_mma = bar_w + G_NW;                               // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TM;
   const float* wimg = a.wimg + (int64_t)blockIdx.y * a.img_stride;
-  const int K = g.K;
+  const int K = g.K, nchunk = a.nchunk;
 
   if (tid == 0) {
-    mbar_init(bar_w, 1);
+    for (int i = 0; i < G_NW; ++i) mbar_init(bar_w + i, 1);
     mbar_init(bar_mma, 1);
+    mbar_init(bar_mma + 1, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  uint32_t ph_w = 0, ph_m = 0;
 
-  g_stage_rows(g.A, row0, g.rows, K, g.lda, 0, xs0);
+  // weight chunk c (16 elements = half of a 32-element image chunk): hi slabs, lo slabs
+  auto request_w = [&](int c) {
+    uint64_t* bar = bar_w + c % G_NW;
+    uint8_t* dst = sW + (c % G_NW) * 2 * w_half;
+    const float* src = wimg + (int64_t)(c >> 1) * (64 * NB) + (c & 1) * (16 * NB);
+    mbar_expect_tx(bar, 2 * w_half);
+    bulk_g2s(dst, src, w_half, bar);
+    bulk_g2s(dst + w_half, src + 32 * NB, w_half, bar);
+  };
+
+  // this thread's two (row, 16-byte piece) slots of every chunk
+  const int ap = lane >> 3;
+  int ar[2];
+  const float* aptr[2];
+  const float* am[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    ar[s] = (warp * 2 + s) * 8 + (lane & 7);
+    const int64_t row = row0 + ar[s];
+    aptr[s] = row < g.rows ? g.A + row * g.lda + 4 * ap : nullptr;
+    am[s] = (g.pro == PRO_ADARMS && row < g.rows) ? g.mod + (row / g.rows_per_batch) * (int64_t)g.mod_stride : nullptr;
+  }
+  auto fetch = [&](int c, float4 (&dst)[2]) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+      dst[s] = (aptr[s] && c < nchunk) ? __ldg(reinterpret_cast<const float4*>(aptr[s] + GK * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 cur[2], nx1[2], nx2[2];
+  fetch(0, cur);
+  fetch(1, nx1);
 
   // ---- row statistics of the normalisation prologues (K <= 192), a warp per row ----
   if (g.pro != PRO_NONE) {
@@ -220,52 +196,110 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       }
     }
   }
+  tc_fence_before();
+  __syncthreads();                                     // barriers initialised, TMEM allocated, statistics written
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) request_w(0);
 
-  for (int c = 0; c < a.nchunk; ++c) {
-    const float* xs = xs0 + (c & 1) * TM * XS_LD;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                   // chunk c staged by every thread; (c = 0) the statistics are written
-    if (c + 1 < a.nchunk) g_stage_rows(g.A, row0, g.rows, K, g.lda, c + 1, xs0 + ((c + 1) & 1) * TM * XS_LD);
-    if (c > 0) {                                       // operand image and weight slot are free once chunk c - 1's MMAs retired
-      mbar_wait(bar_mma, ph_m);
-      ph_m ^= 1;
+  for (int c = 0; c < nchunk; ++c) {
+    fetch(c + 2, nx2);
+    if (c >= 2) {                                      // operand buffer c & 1 (and weight buffer (c + 1) % 3) are free once chunk c - 2 retired
+      mbar_wait(bar_mma + (c & 1), ((c >> 1) - 1) & 1);
       tc_fence_after();
     }
-    if (tid == 0) {
-      mbar_expect_tx(bar_w, 2 * w_half);
-      bulk_g2s(sW, wimg + (int64_t)c * (2 * w_half / 4), 2 * w_half, bar_w);
+    if (tid == 0 && c + 1 < nchunk) request_w(c + 1);
+    uint8_t* sAh = sA + (c & 1) * G_A_BUF;
+    uint8_t* sAl = sAh + G_A_BUF / 2;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      float v[4] = {cur[s].x, cur[s].y, cur[s].z, cur[s].w};
+      if (g.pro != PRO_NONE && aptr[s]) {
+        const float rstd = s_rstd[ar[s]], mean = s_mean[ar[s]];
+        const int k0 = GK * c + 4 * ap;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int k = k0 + j;
+          float x = v[j];
+          if (g.pro == PRO_LN) {
+            x = (x - mean) * rstd * __ldg(g.norm_w + k) + __ldg(g.norm_b + k);
+          } else {
+            x = (x * rstd) * __ldg(g.norm_w + k);
+            if (am[s]) x = x * (1.0f + __ldg(am[s] + k)) + __ldg(am[s] + K + k);
+          }
+          v[j] = x;
+        }
+      }
+      split_store(sAh, sAl, ap, ar[s], v);
     }
-    g_split_rows(g, xs, sAh, sAl, c, row0, s_rstd, s_mean);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
-      mbar_wait(bar_w, ph_w);
+      mbar_wait(bar_w + c % G_NW, (c / G_NW) & 1);
       tc_fence_after();
-      const int nks = min(KC, K - KC * c + 7) / 8;
-      issue_chunk(tmem, smem_u32(sAh), smem_u32(sAl), smem_u32(sW), smem_u32(sW) + w_half, nks, NB, c > 0);
-      umma_commit(bar_mma);
+      const uint32_t wh = smem_u32(sW + (c % G_NW) * 2 * w_half);
+      issue_chunk(tmem, smem_u32(sAh), smem_u32(sAl), wh, wh + w_half, GK / 8, NB, c > 0);
+      umma_commit(bar_mma + (c & 1));
     }
-    ph_w ^= 1;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      cur[s] = nx1[s];
+      nx1[s] = nx2[s];
+    }
   }
-  mbar_wait(bar_mma, ph_m);
+  mbar_wait(bar_mma + ((nchunk - 1) & 1), ((nchunk - 1) >> 1) & 1);   // the last commit covers every earlier MMA
   tc_fence_after();
 
-  // ---- epilogue: thread = (row r, half of the block's output columns), 8 columns at a time --------------------------------
+  // ---- epilogue, phase 1: thread = (row r, half of the block's output columns) -> stage[r][col] (+ bias, SwiGLU) -----------
+  const bool swi = g.epi == EPI_SWIGLU;
+  const int NOUT = swi ? NB / 2 : NB;                  // output columns of this block
+  const int n_out0 = blockIdx.y * NOUT;
+  const int LD = NOUT + 4;                             // stage row stride (words): 4 mod 32, conflict-free 16-byte accesses
+  float* stage = reinterpret_cast<float*>(smem);       // over the operand / weight buffers: every MMA and bulk copy has retired
   {
     const int lq = warp & 3, half = warp >> 2;
     const int r = lq * 32 + lane;
-    const int64_t row = row0 + r;
-    const bool valid = row < g.rows;
-    const bool swi = g.epi == EPI_SWIGLU;
-    const int NOUT = swi ? NB / 2 : NB;                // output columns of this block
-    const int n_out0 = blockIdx.y * NOUT;
     const int ncol = NOUT / 2;                         // a multiple of 8
     const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
-    float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
-    int64_t bidx = 0;
-    if (g.epi == EPI_STEP && valid) {
-      bidx = row / g.rows_per_batch;
+    for (int c8 = 0; c8 < ncol; c8 += 8) {
+      const int cc = half * ncol + c8;                 // column inside the block
+      float v[8], gt[8];
+      tmem_ld8(trow + cc, v);
+      if (swi) tmem_ld8(trow + NOUT + cc, gt);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int col = n_out0 + cc + j;
+        float x = v[j];
+        if (g.bias) x += __ldg(g.bias + col);
+        if (swi) {
+          float gate = gt[j];
+          if (g.bias) gate += __ldg(g.bias + g.N + col);
+          x = x * silu(gate);
+        }
+        v[j] = x;
+      }
+      *reinterpret_cast<float4*>(stage + r * LD + cc) = make_float4(v[0], v[1], v[2], v[3]);
+      *reinterpret_cast<float4*>(stage + r * LD + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+
+  // ---- phase 2: consecutive threads walk consecutive 16-byte pieces of a row ---------------------------------------------------
+  const int n4 = NOUT / 4;
+  for (int i = tid; i < TM * n4; i += GT) {
+    const int r = i / n4, c4 = i - r * n4;
+    const int64_t row = row0 + r;
+    if (row >= g.rows) break;                          // rows ascend with i
+    const float4 s4 = *reinterpret_cast<const float4*>(stage + r * LD + 4 * c4);
+    float v[4] = {s4.x, s4.y, s4.z, s4.w};
+    const int col0 = n_out0 + 4 * c4;
+    const int64_t o0 = row * g.ldo + col0;
+    if (g.epi == EPI_STEP) {
+      const int64_t bidx = row / g.rows_per_batch;
+      float ab_t = 0.f, ab_p = 1.f, al = 0.f, be = 0.f, pv = 0.f, nzm = 0.f;
       if (g.step.mode == EDTTS_STEP_DDIM || g.step.mode == EDTTS_STEP_DDPM) {
         const int64_t t = g.step.t[bidx];
         ab_t = g.step.alpha_bar[t];
@@ -279,91 +313,79 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
           nzm = (t > 0) ? 1.0f : 0.0f;
         }
       }
-    }
-    for (int c8 = 0; c8 < ncol; c8 += 8) {
-      const int cc = half * ncol + c8;                 // column inside the block
-      float v[8], gt[8];
-      tmem_ld8(trow + cc, v);
-      if (swi) tmem_ld8(trow + NOUT + cc, gt);
-      if (!valid) continue;
-      const int col0 = n_out0 + cc;
-      const int64_t o0 = row * g.ldo + col0;
-      float res[8];
-      if (g.epi == EPI_RESID) {
-        const float4 r0 = *reinterpret_cast<const float4*>(g.resid + o0), r1 = *reinterpret_cast<const float4*>(g.resid + o0 + 4);
-        res[0] = r0.x; res[1] = r0.y; res[2] = r0.z; res[3] = r0.w; res[4] = r1.x; res[5] = r1.y; res[6] = r1.z; res[7] = r1.w;
-      }
+      const float4 x4 = *reinterpret_cast<const float4*>(g.x_t + o0);
+      const float xt[4] = {x4.x, x4.y, x4.z, x4.w};
+      float xp[4], x0[4];
+      if (g.step.eps_out) *reinterpret_cast<float4*>(g.step.eps_out + o0) = s4;
+      if (g.step.mode == EDTTS_STEP_DDIM) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int col = col0 + j;
-        float x = v[j];
-        if (g.bias) x += __ldg(g.bias + col);
-        switch (g.epi) {
-          case EPI_GELU: x = gelu_erf(x); break;
-          case EPI_RESID: x = res[j] + x; break;
-          case EPI_PE: x += __ldg(g.pe + (int64_t)(row % g.pe_period) * g.N + col); break;
-          case EPI_SWIGLU: {
-            float gate = gt[j];
-            if (g.bias) gate += __ldg(g.bias + g.N + col);
-            x = x * silu(gate);
-          } break;
-          default: break;
-        }
-        v[j] = x;
-      }
-      if (g.epi == EPI_STEP) {
+        for (int j = 0; j < 4; ++j) ddim_update(xt[j], v[j], 0.f, ab_t, ab_p, 0.f, xp[j], x0[j]);
+        if (g.step.x0_out) *reinterpret_cast<float4*>(g.step.x0_out + o0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+        if (g.step.write_x_prev && g.step.x_prev_out)
+          *reinterpret_cast<float4*>(g.step.x_prev_out + o0) = make_float4(xp[0], xp[1], xp[2], xp[3]);
+      } else if (g.step.mode == EDTTS_STEP_DDPM) {
+        const float4 n4v = *reinterpret_cast<const float4*>(g.step.noise + o0);
+        const float nz[4] = {n4v.x, n4v.y, n4v.z, n4v.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t o = o0 + j;
-          const float e = v[j];
-          if (g.step.eps_out) g.step.eps_out[o] = e;
-          if (g.step.mode == EDTTS_STEP_DDIM) {
-            float xp, x0;
-            ddim_update(g.x_t[o], e, 0.f, ab_t, ab_p, 0.f, xp, x0);
-            if (g.step.x0_out) g.step.x0_out[o] = x0;
-            if (g.step.write_x_prev && g.step.x_prev_out) g.step.x_prev_out[o] = xp;
-          } else if (g.step.mode == EDTTS_STEP_DDPM) {
-            g.step.x_prev_out[o] = ddpm_update(g.x_t[o], e, g.step.noise[o], al, ab_t, be, pv, nzm);
-          } else if (g.step.mode == EDTTS_STEP_DPM) {
-            const int ord = g.step.dpm_order;
-            float xp, x0;
-            dpm_update(g.x_t[o], e, ord >= 2 ? g.step.dpm_hist1[o] : 0.f, ord >= 3 ? g.step.dpm_hist2[o] : 0.f,
-                       g.step.dpm_coef + bidx * 8, ord, g.step.dpm_predict_x0 ? 1 : 0, xp, x0);
-            if (g.step.x0_out) g.step.x0_out[o] = x0;
-            g.step.x_prev_out[o] = xp;
-          }
+        for (int j = 0; j < 4; ++j) xp[j] = ddpm_update(xt[j], v[j], nz[j], al, ab_t, be, pv, nzm);
+        *reinterpret_cast<float4*>(g.step.x_prev_out + o0) = make_float4(xp[0], xp[1], xp[2], xp[3]);
+      } else if (g.step.mode == EDTTS_STEP_DPM) {
+        const int ord = g.step.dpm_order;
+        float h1[4] = {0.f, 0.f, 0.f, 0.f}, h2[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ord >= 2) {
+          const float4 t4 = *reinterpret_cast<const float4*>(g.step.dpm_hist1 + o0);
+          h1[0] = t4.x; h1[1] = t4.y; h1[2] = t4.z; h1[3] = t4.w;
         }
-      } else {
-        *reinterpret_cast<float4*>(g.out + o0) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(g.out + o0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        if (ord >= 3) {
+          const float4 t4 = *reinterpret_cast<const float4*>(g.step.dpm_hist2 + o0);
+          h2[0] = t4.x; h2[1] = t4.y; h2[2] = t4.z; h2[3] = t4.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          dpm_update(xt[j], v[j], h1[j], h2[j], g.step.dpm_coef + bidx * 8, ord, g.step.dpm_predict_x0 ? 1 : 0, xp[j], x0[j]);
+        if (g.step.x0_out) *reinterpret_cast<float4*>(g.step.x0_out + o0) = make_float4(x0[0], x0[1], x0[2], x0[3]);
+        *reinterpret_cast<float4*>(g.step.x_prev_out + o0) = make_float4(xp[0], xp[1], xp[2], xp[3]);
       }
+      continue;
     }
+    if (g.epi == EPI_GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
+    } else if (g.epi == EPI_RESID) {
+      const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o0);
+      v[0] = r4.x + v[0]; v[1] = r4.y + v[1]; v[2] = r4.z + v[2]; v[3] = r4.w + v[3];
+    } else if (g.epi == EPI_PE) {
+      const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.pe + (int64_t)(row % g.pe_period) * g.N + col0));
+      v[0] += p4.x; v[1] += p4.y; v[2] += p4.z; v[3] += p4.w;
+    }
+    *reinterpret_cast<float4*>(g.out + o0) = make_float4(v[0], v[1], v[2], v[3]);
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
-static int gemm_smem(int NB) { return 2 * A_HALF + 2 * 8 * NB * 16 + 2 * TM * XS_LD * 4 + 2 * TM * 4 + 64; }
+static int gemm_main_bytes(int NB, bool swi) {
+  const int nout = swi ? NB / 2 : NB;
+  const int pipe = 2 * G_A_BUF + G_NW * 2 * (GK / 4) * NB * 16, stage = TM * (nout + 4) * 4;
+  return (int)align_up(pipe > stage ? pipe : stage, 128);
+}
+static int gemm_smem(int NB, bool swi) { return gemm_main_bytes(NB, swi) + 2 * TM * 4 + (G_NW + 2) * 8 + 16; }
 
 int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st) {
   const bool swi = g.epi == EPI_SWIGLU;
   const int nout = swi ? NB / 2 : NB;
-  EDTTS_REQUIRE(g.rows > 0 && g.K % 4 == 0 && g.lda % 4 == 0 && g.ldo % 4 == 0 && NB % 16 == 0 && NB <= 256 && nout % 16 == 0 &&
+  EDTTS_REQUIRE(g.rows > 0 && g.K % GK == 0 && g.lda % 4 == 0 && g.ldo % 4 == 0 && NB % 16 == 0 && NB <= 160 && nout % 16 == 0 &&
                     g.N % nout == 0,
                 EDTTS_EINVAL, "t3_gemm: rows=%lld K=%d N=%d NB=%d unsupported", (long long)g.rows, g.K, g.N, NB);
   EDTTS_REQUIRE(g.pro == PRO_NONE || g.K <= 192, EDTTS_EINVAL, "t3_gemm: norm prologue needs K <= 192 (K=%d)", g.K);
   T3GemmArgs a;
-  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = (g.K + KC - 1) / KC;
+  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi);
   static PerDeviceOnce configured;
   if (configured.need()) {
-    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160)) != cudaSuccess)
+    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160, false)) != cudaSuccess)
       return check_launch("t3_gemm smem attribute");
     configured.set();
   }
-  EDTTS_REQUIRE(NB <= 160, EDTTS_EINVAL, "t3_gemm: NB=%d (<= 160: two CTAs per SM)", NB);
   LaunchScope ls(KC_T3_GEMM, st);
-  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT, gemm_smem(NB), st>>>(a);
+  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT, gemm_smem(NB, swi), st>>>(a);
   return check_launch("t3_gemm");
 }
 
@@ -418,7 +440,7 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
       float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
       if (active) t = *reinterpret_cast<const float4*>(qp + d);
       const float v[4] = {t.x * qs, t.y * qs, t.z * qs, t.w * qs};
-      split_store_r(sQh, sQl, d >> 2, AQ, tid, v);
+      split_store(sQh, sQl, d >> 2, tid, v);
     }
   }
   tc_fence_before();
@@ -459,7 +481,11 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
       const int key = idx / (HD / 4), c4 = idx % (HD / 4);
       {
         const float v[4] = {kreg[it].x, kreg[it].y, kreg[it].z, kreg[it].w};
-        split_store_r(sKh, sKl, c4, AKB, key, v);
+        float4 hi, lo;
+        hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+        lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+        *reinterpret_cast<float4*>(sKh + c4 * (AKB * 16) + key * 16) = hi;
+        *reinterpret_cast<float4*>(sKl + c4 * (AKB * 16) + key * 16) = lo;
       }
       {
         const float v[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
@@ -468,13 +494,14 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
         for (int j = 0; j < 4; ++j) {
           const float hi = tf32_rna(v[j]);
           *reinterpret_cast<float*>(sVh + off + (4 * c4 + j) * 16) = hi;
-          *reinterpret_cast<float*>(sVl + off + (4 * c4 + j) * 16) = tf32_rna(v[j] - hi);
+          *reinterpret_cast<float*>(sVl + off + (4 * c4 + j) * 16) = v[j] - hi;
         }
       }
     }
   };
 
   float m = -INFINITY, l = 0.f;
+  const int r0w = q0 + warp * 32;                      // first query row of this warp
   float acc[HD];
 #pragma unroll
   for (int d = 0; d < HD; ++d) acc[d] = 0.f;
@@ -496,29 +523,54 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     }
     mbar_wait(bar_s, ph);
     tc_fence_after();
+    // What this WARP's 32 rows see of the block's keys (warp-uniform, so the collective tensor-memory loads stay converged):
+    // empty -> p = 0, nothing else to do; full -> every (row, key) pair is valid, no masks; else per-element masks.
+    bool empty, full;
+    if (W >= 0) {
+      empty = r0w >= a.Tq || kc > r0w + 31 + W || kc + AKB - 1 < r0w - W;
+      full = r0w + 31 < a.Tq && kc >= r0w + 31 - W && kc + AKB - 1 <= r0w + W && kc + AKB <= khi;
+    } else {
+      empty = r0w >= a.Tq;
+      full = r0w + 31 < a.Tq && kc + AKB <= khi;
+    }
+    float corr = 1.0f;
     float s[AKB];
-    tmem_ld32(trow + tS, s);
-    // ---- online softmax (exp2 domain; the scores already carry scale * log2 e) ----
-    float bm = -INFINITY;
+    if (empty) {
 #pragma unroll
-    for (int j = 0; j < AKB; ++j) {
-      const int key = kc + j;
-      const bool ok = active && key < khi && (W < 0 || (key >= qi - W && key <= qi + W));
-      s[j] = ok ? s[j] : -INFINITY;
-      bm = fmaxf(bm, s[j]);
+      for (int j = 0; j < AKB; ++j) s[j] = 0.f;
+    } else {
+      tmem_ld32(trow + tS, s);
+      // ---- online softmax (exp2 domain; the scores already carry scale * log2 e) ----
+      if (!full) {
+#pragma unroll
+        for (int j = 0; j < AKB; ++j) {
+          const int key = kc + j;
+          const bool ok = active && key < khi && (W < 0 || (key >= qi - W && key <= qi + W));
+          s[j] = ok ? s[j] : -INFINITY;
+        }
+      }
+      float b0 = s[0], b1 = s[1], b2 = s[2], b3 = s[3];
+#pragma unroll
+      for (int j = 4; j < AKB; j += 4) {
+        b0 = fmaxf(b0, s[j]); b1 = fmaxf(b1, s[j + 1]); b2 = fmaxf(b2, s[j + 2]); b3 = fmaxf(b3, s[j + 3]);
+      }
+      const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;       // a row that has not met a valid key yet: every p = 0
+      corr = ex2_approx(m - m_use);                                  // m = -inf -> 0 (l and acc are 0 then)
+      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < AKB; j += 4) {
+        s[j] = ex2_approx(s[j] - m_use);                             // masked: ex2(-inf) = 0
+        s[j + 1] = ex2_approx(s[j + 1] - m_use);
+        s[j + 2] = ex2_approx(s[j + 2] - m_use);
+        s[j + 3] = ex2_approx(s[j + 3] - m_use);
+        l0 += s[j]; l1 += s[j + 1]; l2 += s[j + 2]; l3 += s[j + 3];
+      }
+      l = fmaf(l, corr, (l0 + l1) + (l2 + l3));
+      m = m_new;
     }
-    const float m_new = fmaxf(m, bm);
-    const float corr = (m_new == -INFINITY) ? 1.0f : exp2f(m - m_new);
-    l *= corr;
 #pragma unroll
-    for (int j = 0; j < AKB; ++j) {
-      const float p = (s[j] == -INFINITY) ? 0.f : exp2f(s[j] - m_new);
-      l += p;
-      s[j] = p;
-    }
-    m = m_new;
-#pragma unroll
-    for (int q4 = 0; q4 < AKB / 4; ++q4) split_store_r(sPh, sPl, q4, AQ, tid, s + 4 * q4);
+    for (int q4 = 0; q4 < AKB / 4; ++q4) split_store(sPh, sPl, q4, tid, s + 4 * q4);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -527,14 +579,14 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
       issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, false);
       umma_commit(bar_o);
     }
-#pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] *= corr;
     mbar_wait(bar_o, ph);
     tc_fence_after();
-    float o[HD];
-    tmem_ld40(trow + tO, o);
+    if (!empty) {
+      float o[HD];
+      tmem_ld40(trow + tO, o);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc[d] += o[d];
+      for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], corr, o[d]);
+    }
     ph ^= 1;
   }
   if (active) {
