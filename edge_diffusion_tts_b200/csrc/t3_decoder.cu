@@ -163,36 +163,45 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
   fetch(0, cur);
   fetch(1, nx1);
 
-  // ---- row statistics of the normalisation prologues (K <= 192), a warp per row ----
+  // ---- row statistics of the normalisation prologues (K <= 192): a warp per row, four rows per pass with all their loads in
+  // flight before the first reduction (a row at a time pays the DRAM latency 16 times per warp: 24 % of the kernel's samples) ----
   if (g.pro != PRO_NONE) {
-    for (int r = warp; r < TM; r += GT / 32) {
-      const int64_t row = row0 + r;
-      float v[6];
-      float s = 0.f;
+    constexpr int RB = 4;
+    for (int rb = warp * (TM / (GT / 32)); rb < (warp + 1) * (TM / (GT / 32)); rb += RB) {
+      float v[RB][6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int k = lane + 32 * i;
-        v[i] = (row < g.rows && k < K) ? g.A[row * g.lda + k] : 0.f;
-        s += (g.pro == PRO_LN) ? v[i] : v[i] * v[i];
-      }
-      s = warp_sum(s);
-      float mean = 0.f, var;
-      if (g.pro == PRO_LN) {
-        mean = s / (float)K;
-        float q = 0.f;
+      for (int u = 0; u < RB; ++u) {
+        const int64_t row = row0 + rb + u;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int k = lane + 32 * i;
-          const float d = (k < K) ? v[i] - mean : 0.f;
-          q += d * d;
+          v[u][i] = (row < g.rows && k < K) ? __ldg(g.A + row * g.lda + k) : 0.f;
         }
-        var = warp_sum(q) / (float)K;
-      } else {
-        var = s / (float)K;
       }
-      if (lane == 0) {
-        s_rstd[r] = 1.0f / sqrtf(var + g.norm_eps);
-        s_mean[r] = mean;
+#pragma unroll
+      for (int u = 0; u < RB; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) s += (g.pro == PRO_LN) ? v[u][i] : v[u][i] * v[u][i];
+        s = warp_sum(s);
+        float mean = 0.f, var;
+        if (g.pro == PRO_LN) {
+          mean = s / (float)K;
+          float q = 0.f;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int k = lane + 32 * i;
+            const float d = (k < K) ? v[u][i] - mean : 0.f;
+            q += d * d;
+          }
+          var = warp_sum(q) / (float)K;
+        } else {
+          var = s / (float)K;
+        }
+        if (lane == 0) {
+          s_rstd[rb + u] = 1.0f / sqrtf(var + g.norm_eps);
+          s_mean[rb + u] = mean;
+        }
       }
     }
   }
@@ -204,6 +213,23 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
 
   for (int c = 0; c < nchunk; ++c) {
     fetch(c + 2, nx2);
+    // the chunk's prologue vectors (16-byte loads, issued before the wait below): norm weight / bias of columns 16 c + 4 ap ..,
+    // AdaLN scale and shift of this thread's two rows
+    float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4[2], sh4[2];
+    if (g.pro != PRO_NONE) {
+      const int k0 = GK * c + 4 * ap;
+      w4 = __ldg(reinterpret_cast<const float4*>(g.norm_w + k0));
+      if (g.pro == PRO_LN) b4 = __ldg(reinterpret_cast<const float4*>(g.norm_b + k0));
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        sc4[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sh4[s] = sc4[s];
+        if (am[s]) {
+          sc4[s] = __ldg(reinterpret_cast<const float4*>(am[s] + k0));
+          sh4[s] = __ldg(reinterpret_cast<const float4*>(am[s] + K + k0));
+        }
+      }
+    }
     if (c >= 2) {                                      // operand buffer c & 1 (and weight buffer (c + 1) % 3) are free once chunk c - 2 retired
       mbar_wait(bar_mma + (c & 1), ((c >> 1) - 1) & 1);
       tc_fence_after();
@@ -216,16 +242,16 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       float v[4] = {cur[s].x, cur[s].y, cur[s].z, cur[s].w};
       if (g.pro != PRO_NONE && aptr[s]) {
         const float rstd = s_rstd[ar[s]], mean = s_mean[ar[s]];
-        const int k0 = GK * c + 4 * ap;
+        const float wv[4] = {w4.x, w4.y, w4.z, w4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+        const float sc[4] = {sc4[s].x, sc4[s].y, sc4[s].z, sc4[s].w}, sh[4] = {sh4[s].x, sh4[s].y, sh4[s].z, sh4[s].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int k = k0 + j;
           float x = v[j];
           if (g.pro == PRO_LN) {
-            x = (x - mean) * rstd * __ldg(g.norm_w + k) + __ldg(g.norm_b + k);
+            x = (x - mean) * rstd * wv[j] + bv[j];
           } else {
-            x = (x * rstd) * __ldg(g.norm_w + k);
-            if (am[s]) x = x * (1.0f + __ldg(am[s] + k)) + __ldg(am[s] + K + k);
+            x = (x * rstd) * wv[j];
+            if (am[s]) x = x * (1.0f + sc[j]) + sh[j];
           }
           v[j] = x;
         }
@@ -376,6 +402,10 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
                     g.N % nout == 0,
                 EDTTS_EINVAL, "t3_gemm: rows=%lld K=%d N=%d NB=%d unsupported", (long long)g.rows, g.K, g.N, NB);
   EDTTS_REQUIRE(g.pro == PRO_NONE || g.K <= 192, EDTTS_EINVAL, "t3_gemm: norm prologue needs K <= 192 (K=%d)", g.K);
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  EDTTS_REQUIRE(al16(g.A) && al16(g.norm_w) && al16(g.norm_b) && al16(g.mod) && g.mod_stride % 4 == 0 && al16(g.resid) && al16(g.pe) &&
+                    al16(g.out) && al16(g.x_t),
+                EDTTS_EINVAL, "t3_gemm: operands must be 16-byte aligned");
   T3GemmArgs a;
   a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi);
   static PerDeviceOnce configured;
@@ -390,6 +420,15 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
 }
 
 // ---- attention --------------------------------------------------------------------------------------------------------------
+// Software pipeline of one CTA (all 128 threads walk the same steps; the MMAs run behind them):
+//   iteration i:  A  K(i+1) registers -> operand image (second K buffer)           | tensor core: P V(i-1)
+//                 B  sync, S(i+1) = Q K(i+1)^T issued into the second S block       |
+//                 C  S(i) (issued an iteration ago) -> registers, softmax           | S(i+1)
+//                 D  wait P V(i-1); lazy rescale of O; V(i), P(i) -> operand images |
+//                 E  sync, O += P(i) V(i) issued (accumulates in tensor memory)     |
+// so no thread waits for an MMA round trip it has just issued.  O stays in tensor memory for the whole head: the running
+// maximum is only raised when a block exceeds it by more than 2^8 (p <= 256 otherwise, harmless in fp32 / tf32 x 2), and only
+// then does the warp rescale its O rows (tcgen05.ld / st) -- after the first block or two that does not happen.
 constexpr int AQ = 128;                               // queries per CTA (= threads = MMA M)
 constexpr int AKB = 32;                               // keys per block
 constexpr int A_Q_HALF = (HD / 4) * AQ * 16;          // 10 slabs x 128 rows x 16 B
@@ -397,23 +436,23 @@ constexpr int A_K_HALF = (HD / 4) * AKB * 16;         // 10 slabs x 32 keys x 16
 constexpr int A_VN = 48;                              // head_dim padded to an MMA N (rows 40..47 of the V^T image stay zero)
 constexpr int A_V_HALF = (AKB / 4) * A_VN * 16;       // 8 slabs x 48 rows x 16 B
 constexpr int A_P_HALF = (AKB / 4) * AQ * 16;         // 8 slabs x 128 rows x 16 B
-constexpr int A_SMEM = 2 * (A_Q_HALF + A_K_HALF + A_V_HALF + A_P_HALF) + 64;
+constexpr int A_SMEM = 2 * (A_Q_HALF + 2 * A_K_HALF + A_V_HALF + A_P_HALF) + 64;
 constexpr int A_NLD = (AKB * (HD / 4) + AQ - 1) / AQ; // 16-byte pieces of a K (or V) block per thread: 320 / 128 -> 3
+constexpr float A_GROW = 8.0f;                        // lazy running maximum: raise it only beyond 2^8
 
 __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQh = smem;
   uint8_t* sQl = sQh + A_Q_HALF;
-  uint8_t* sKh = sQl + A_Q_HALF;
-  uint8_t* sKl = sKh + A_K_HALF;
-  uint8_t* sVh = sKl + A_K_HALF;
+  uint8_t* sK = sQl + A_Q_HALF;                        // two buffers of [hi | lo]
+  uint8_t* sVh = sK + 4 * A_K_HALF;
   uint8_t* sVl = sVh + A_V_HALF;
   uint8_t* sPh = sVl + A_V_HALF;
   uint8_t* sPl = sPh + A_P_HALF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPl + A_P_HALF);
-  uint64_t* bar_s = bars;
-  uint64_t* bar_o = bars + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+  uint64_t* bar_s = bars;                              // [2]
+  uint64_t* bar_o = bars + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * AQ;
@@ -423,6 +462,7 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
 
   if (tid == 0) {
     mbar_init(bar_s, 1);
+    mbar_init(bar_s + 1, 1);
     mbar_init(bar_o, 1);
     mbar_fence_init();
   }
@@ -435,20 +475,15 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
   {                                                    // this thread's query row, pre-scaled by scale * log2(e)
     const float qs = a.scale * 1.4426950408889634f;
     const float* qp = a.q + ((int64_t)b * a.Tq + (active ? qi : 0)) * a.q_stride + h * HD;
+    float4 t[HD / 4];
 #pragma unroll
-    for (int d = 0; d < HD; d += 4) {
-      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (active) t = *reinterpret_cast<const float4*>(qp + d);
-      const float v[4] = {t.x * qs, t.y * qs, t.z * qs, t.w * qs};
-      split_store(sQh, sQl, d >> 2, tid, v);
+    for (int d = 0; d < HD / 4; ++d) t[d] = active ? *reinterpret_cast<const float4*>(qp + 4 * d) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int d = 0; d < HD / 4; ++d) {
+      const float v[4] = {t[d].x * qs, t[d].y * qs, t[d].z * qs, t[d].w * qs};
+      split_store(sQh, sQl, d, tid, v);
     }
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  const uint32_t tS = 0, tO = AKB;                     // columns: S block (32) | O block (48)
 
   int klo = 0, khi = a.Tk;
   if (W >= 0) {
@@ -459,71 +494,91 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
   const float* kbase = a.k + (int64_t)b * a.Tk * a.kv_stride + h * HD;
   const float* vbase = a.v + (int64_t)b * a.Tk * a.kv_stride + h * HD;
 
+  // this thread's (key, 4 dims) pieces of a 32-key block
+  int pkey[A_NLD], pc4[A_NLD];
+#pragma unroll
+  for (int it = 0; it < A_NLD; ++it) {
+    const int idx = tid + it * AQ;
+    pkey[it] = idx < AKB * (HD / 4) ? idx / (HD / 4) : -1;
+    pc4[it] = idx % (HD / 4);
+  }
   float4 kreg[A_NLD], vreg[A_NLD];
-  auto fetch = [&](int kc) {                           // K / V rows kc .. kc + 31 -> registers (zeros beyond khi)
+  auto fetch = [&](const float* base, int kc, float4 (&dst)[A_NLD]) {       // rows kc .. kc + 31 -> registers (zeros beyond khi)
 #pragma unroll
     for (int it = 0; it < A_NLD; ++it) {
-      const int idx = tid + it * AQ;
-      const int key = idx / (HD / 4), c4 = idx % (HD / 4);
-      kreg[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      vreg[it] = kreg[it];
-      if (idx < AKB * (HD / 4) && kc + key < khi) {
-        kreg[it] = *reinterpret_cast<const float4*>(kbase + (int64_t)(kc + key) * a.kv_stride + 4 * c4);
-        vreg[it] = *reinterpret_cast<const float4*>(vbase + (int64_t)(kc + key) * a.kv_stride + 4 * c4);
+      dst[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pkey[it] >= 0 && kc + pkey[it] < khi)
+        dst[it] = *reinterpret_cast<const float4*>(base + (int64_t)(kc + pkey[it]) * a.kv_stride + 4 * pc4[it]);
+    }
+  };
+  auto stash_k = [&](int buf) {                        // K image [slab = dim / 4][key][4]
+    uint8_t* kh = sK + buf * 2 * A_K_HALF;
+#pragma unroll
+    for (int it = 0; it < A_NLD; ++it) {
+      if (pkey[it] < 0) continue;
+      const float v[4] = {kreg[it].x, kreg[it].y, kreg[it].z, kreg[it].w};
+      float4 hi, lo;
+      hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
+      lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
+      *reinterpret_cast<float4*>(kh + pc4[it] * (AKB * 16) + pkey[it] * 16) = hi;
+      *reinterpret_cast<float4*>(kh + A_K_HALF + pc4[it] * (AKB * 16) + pkey[it] * 16) = lo;
+    }
+  };
+  auto stash_v = [&]() {                               // V^T image [slab = key / 4][dim][4]
+#pragma unroll
+    for (int it = 0; it < A_NLD; ++it) {
+      if (pkey[it] < 0) continue;
+      const float v[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
+      const int off = (pkey[it] >> 2) * (A_VN * 16) + (pkey[it] & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hi = tf32_rna(v[j]);
+        *reinterpret_cast<float*>(sVh + off + (4 * pc4[it] + j) * 16) = hi;
+        *reinterpret_cast<float*>(sVl + off + (4 * pc4[it] + j) * 16) = v[j] - hi;
       }
     }
   };
-  auto stash = [&]() {                                 // registers -> operand images: K [slab = dim / 4][key][4], V^T [key / 4][dim][4]
-#pragma unroll
-    for (int it = 0; it < A_NLD; ++it) {
-      const int idx = tid + it * AQ;
-      if (idx >= AKB * (HD / 4)) continue;
-      const int key = idx / (HD / 4), c4 = idx % (HD / 4);
-      {
-        const float v[4] = {kreg[it].x, kreg[it].y, kreg[it].z, kreg[it].w};
-        float4 hi, lo;
-        hi.x = tf32_rna(v[0]); hi.y = tf32_rna(v[1]); hi.z = tf32_rna(v[2]); hi.w = tf32_rna(v[3]);
-        lo.x = v[0] - hi.x; lo.y = v[1] - hi.y; lo.z = v[2] - hi.z; lo.w = v[3] - hi.w;
-        *reinterpret_cast<float4*>(sKh + c4 * (AKB * 16) + key * 16) = hi;
-        *reinterpret_cast<float4*>(sKl + c4 * (AKB * 16) + key * 16) = lo;
-      }
-      {
-        const float v[4] = {vreg[it].x, vreg[it].y, vreg[it].z, vreg[it].w};
-        const int off = (key >> 2) * (A_VN * 16) + (key & 3) * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float hi = tf32_rna(v[j]);
-          *reinterpret_cast<float*>(sVh + off + (4 * c4 + j) * 16) = hi;
-          *reinterpret_cast<float*>(sVl + off + (4 * c4 + j) * 16) = v[j] - hi;
-        }
-      }
-    }
-  };
+
+  // ---- prologue: K(0) staged, S(0) issued ----
+  fetch(kbase, klo, kreg);
+  stash_k(0);
+  if (nblk > 1) fetch(kbase, klo + AKB, kreg);
+  fetch(vbase, klo, vreg);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t tO = 2 * AKB;                         // columns: S0 (32) | S1 (32) | O (48)
+  if (tid == 0) {
+    issue_chunk(tmem, smem_u32(sQh), smem_u32(sQl), smem_u32(sK), smem_u32(sK) + A_K_HALF, HD / 8, AKB, false);
+    umma_commit(bar_s);
+  }
 
   float m = -INFINITY, l = 0.f;
   const int r0w = q0 + warp * 32;                      // first query row of this warp
-  float acc[HD];
-#pragma unroll
-  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
-  uint32_t ph = 0;
 
-  if (nblk > 0) fetch(klo);
   for (int blk = 0; blk < nblk; ++blk) {
     const int kc = klo + blk * AKB;
-    // the previous block's MMAs have retired (this thread waited for bar_o): K / V / P images are free
-    stash();
-    if (blk + 1 < nblk) fetch(kc + AKB);
+    // ---- A / B: K(blk+1) -> second K buffer (S(blk-1), its last reader, retired: this thread waited for it), S(blk+1) issued ----
+    if (blk + 1 < nblk) {
+      stash_k((blk + 1) & 1);
+      if (blk + 2 < nblk) fetch(kbase, kc + 2 * AKB, kreg);
+    }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && blk + 1 < nblk) {
       tc_fence_after();
-      issue_chunk(tmem + tS, smem_u32(sQh), smem_u32(sQl), smem_u32(sKh), smem_u32(sKl), HD / 8, AKB, false);
-      umma_commit(bar_s);
+      const uint32_t kh = smem_u32(sK + ((blk + 1) & 1) * 2 * A_K_HALF);
+      issue_chunk(tmem + ((blk + 1) & 1) * AKB, smem_u32(sQh), smem_u32(sQl), kh, kh + A_K_HALF, HD / 8, AKB, false);
+      umma_commit(bar_s + ((blk + 1) & 1));
     }
-    mbar_wait(bar_s, ph);
+    // ---- C: S(blk) -> registers, softmax ----
+    mbar_wait(bar_s + (blk & 1), (blk >> 1) & 1);
     tc_fence_after();
-    // What this WARP's 32 rows see of the block's keys (warp-uniform, so the collective tensor-memory loads stay converged):
+    // What this WARP's 32 rows see of the block's keys (warp-uniform, so the collective tensor-memory accesses stay converged):
     // empty -> p = 0, nothing else to do; full -> every (row, key) pair is valid, no masks; else per-element masks.
     bool empty, full;
     if (W >= 0) {
@@ -533,14 +588,14 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
       empty = r0w >= a.Tq;
       full = r0w + 31 < a.Tq && kc + AKB <= khi;
     }
-    float corr = 1.0f;
+    float f = 1.0f;                                    // factor this thread's O row needs before P V(blk) is added
+    bool grow = false;
     float s[AKB];
     if (empty) {
 #pragma unroll
       for (int j = 0; j < AKB; ++j) s[j] = 0.f;
     } else {
-      tmem_ld32(trow + tS, s);
-      // ---- online softmax (exp2 domain; the scores already carry scale * log2 e) ----
+      tmem_ld32(trow + (blk & 1) * AKB, s);
       if (!full) {
 #pragma unroll
         for (int j = 0; j < AKB; ++j) {
@@ -554,47 +609,62 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
       for (int j = 4; j < AKB; j += 4) {
         b0 = fmaxf(b0, s[j]); b1 = fmaxf(b1, s[j + 1]); b2 = fmaxf(b2, s[j + 2]); b3 = fmaxf(b3, s[j + 3]);
       }
-      const float m_new = fmaxf(fmaxf(m, fmaxf(b0, b1)), fmaxf(b2, b3));
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;       // a row that has not met a valid key yet: every p = 0
-      corr = ex2_approx(m - m_use);                                  // m = -inf -> 0 (l and acc are 0 then)
+      const float bm = fmaxf(fmaxf(b0, b1), fmaxf(b2, b3));
+      grow = bm > m + A_GROW;                          // also the first finite block maximum (m = -inf)
+      const float m_old = m;
+      m = grow ? bm : m;
+      const float m_use = (m == -INFINITY) ? 0.f : m;  // a row that has not met a valid key yet: every p = 0
+      f = grow ? ex2_approx(m_old - m_use) : 1.0f;     // m_old = -inf -> 0
       float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
 #pragma unroll
       for (int j = 0; j < AKB; j += 4) {
-        s[j] = ex2_approx(s[j] - m_use);                             // masked: ex2(-inf) = 0
+        s[j] = ex2_approx(s[j] - m_use);               // masked: ex2(-inf) = 0
         s[j + 1] = ex2_approx(s[j + 1] - m_use);
         s[j + 2] = ex2_approx(s[j + 2] - m_use);
         s[j + 3] = ex2_approx(s[j + 3] - m_use);
         l0 += s[j]; l1 += s[j + 1]; l2 += s[j + 2]; l3 += s[j + 3];
       }
-      l = fmaf(l, corr, (l0 + l1) + (l2 + l3));
-      m = m_new;
+      l = fmaf(l, f, (l0 + l1) + (l2 + l3));
     }
+    // ---- D: P V(blk-1) retired -> O may be rescaled, the V and P images rewritten ----
+    if (blk > 0) {
+      mbar_wait(bar_o, (blk - 1) & 1);
+      tc_fence_after();
+      if (!empty && __any_sync(0xffffffffu, grow)) {
+        float o[HD];
+        tmem_ld40(trow + tO, o);
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] *= f;
+        tmem_st40(trow + tO, o);
+        tmem_st_wait();
+      }
+    }
+    stash_v();
+    if (blk + 1 < nblk) fetch(vbase, kc + AKB, vreg);
 #pragma unroll
     for (int q4 = 0; q4 < AKB / 4; ++q4) split_store(sPh, sPl, q4, tid, s + 4 * q4);
+    // ---- E: O (+)= P(blk) V(blk) ----
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, false);
+      issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, blk > 0);
       umma_commit(bar_o);
     }
-    mbar_wait(bar_o, ph);
-    tc_fence_after();
-    if (!empty) {
-      float o[HD];
-      tmem_ld40(trow + tO, o);
-#pragma unroll
-      for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], corr, o[d]);
-    }
-    ph ^= 1;
   }
-  if (active) {
-    const float inv = 1.0f / l;
-    float* op = a.o + ((int64_t)b * a.Tq + qi) * a.o_stride + h * HD;
+  mbar_wait(bar_o, (nblk - 1) & 1);
+  tc_fence_after();
+  {
+    float o[HD];
+    tmem_ld40(trow + tO, o);
+    if (active) {
+      const float inv = 1.0f / l;
+      float* op = a.o + ((int64_t)b * a.Tq + qi) * a.o_stride + h * HD;
 #pragma unroll
-    for (int d = 0; d < HD; d += 4)
-      *reinterpret_cast<float4*>(op + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+      for (int d = 0; d < HD; d += 4)
+        *reinterpret_cast<float4*>(op + d) = make_float4(o[d] * inv, o[d + 1] * inv, o[d + 2] * inv, o[d + 3] * inv);
+    }
   }
   tc_fence_before();
   __syncthreads();
