@@ -247,6 +247,12 @@ extern "C" int edtts_test_gemm(const float* x, const float* w, const float* bias
   EDTTS_REQUIRE(N % 80 == 0, EDTTS_ENOTSUP, "test_gemm: N=%d (multiple of 80)", N);
   const int NB = (N % 160 == 0 || swi) ? 160 : 80;
   EDTTS_REQUIRE(workspace && workspace_bytes >= edtts_test_gemm_workspace_bytes(K, N, epi), EDTTS_ENOSPC, "test_gemm: workspace");
+  if (epi == EPI_RESID) {   // the tensor-core GEMM accumulates the residual in place (resid == out), as the decoder step uses it
+    EDTTS_REQUIRE(resid, EDTTS_EINVAL, "test_gemm: resid is null");
+    if (cudaMemcpyAsync(y, resid, (size_t)rows * N * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)) != cudaSuccess)
+      return check_launch("test_gemm residual copy");
+    g.resid = y;
+  }
   int rc = t3::pack_w_blocks(w, reinterpret_cast<float*>(workspace), K, N, NB, swi, as_stream(stream));
   if (rc) return rc;
   return t3::launch_t3_gemm(g, reinterpret_cast<const float*>(workspace), t3::t3_gemm_block_stride(K, NB), NB, as_stream(stream));

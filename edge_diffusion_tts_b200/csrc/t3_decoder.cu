@@ -116,7 +116,8 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
   uint8_t* sW = smem + 2 * G_A_BUF;
   float* s_rstd = reinterpret_cast<float*>(smem + a.main_bytes);
   float* s_mean = s_rstd + TM;
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_mean + TM);     // [G_NW]
+  float* s_bias = s_mean + TM;                                    // [NB <= 160] bias of the block's image rows
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_bias + 160);    // [G_NW]
   uint64_t* bar_mma = bar_w + G_NW;                               // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,6 +132,11 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
+  if (tid < NB) {                                      // image row j of the block <-> bias index (SwiGLU: x rows, then their gates)
+    const int nout = g.epi == EPI_SWIGLU ? NB / 2 : NB;
+    const int j = tid < nout ? blockIdx.y * nout + tid : g.N + blockIdx.y * nout + (tid - nout);
+    s_bias[tid] = g.bias ? __ldg(g.bias + j) : 0.f;
+  }
 
   // weight chunk c (16 elements = half of a 32-element image chunk): hi slabs, lo slabs
   auto request_w = [&](int c) {
@@ -295,25 +301,34 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       if (swi) tmem_ld8(trow + NOUT + cc, gt);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const int col = n_out0 + cc + j;
-        float x = v[j];
-        if (g.bias) x += __ldg(g.bias + col);
-        if (swi) {
-          float gate = gt[j];
-          if (g.bias) gate += __ldg(g.bias + g.N + col);
-          x = x * silu(gate);
-        }
+        float x = v[j] + s_bias[cc + j];
+        if (swi) x = x * silu(gt[j] + s_bias[NOUT + cc + j]);
+        if (g.epi == EPI_GELU) x = gelu_erf(x);
         v[j] = x;
       }
       *reinterpret_cast<float4*>(stage + r * LD + cc) = make_float4(v[0], v[1], v[2], v[3]);
       *reinterpret_cast<float4*>(stage + r * LD + cc + 4) = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
+  fence_proxy_async();                                 // the staged tile is read by bulk copies below
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<256>(tmem);
 
-  // ---- phase 2: consecutive threads walk consecutive 16-byte pieces of a row ---------------------------------------------------
+  // ---- phase 2a: plain / residual outputs leave by the TMA engine, one bulk copy (or bulk add: global += shared, performed in
+  // L2 -- the residual never travels to the SM) per row --------------------------------------------------------------------------
+  if (g.epi == EPI_STORE || g.epi == EPI_GELU || g.epi == EPI_SWIGLU || g.epi == EPI_RESID) {
+    if (tid < TM && row0 + tid < g.rows) {
+      float* dst = g.out + (row0 + tid) * g.ldo + n_out0;
+      if (g.epi == EPI_RESID) bulk_reduce_add_f32(dst, stage + tid * LD, NOUT * 4);
+      else bulk_s2g(dst, stage + tid * LD, NOUT * 4);
+      bulk_commit();
+      bulk_wait_all();                                 // shared memory must outlive the engine's reads; writes performed
+    }
+    return;
+  }
+
+  // ---- phase 2b (positional table, update rule): consecutive threads walk consecutive 16-byte pieces of a row --------------------
   const int n4 = NOUT / 4;
   for (int i = tid; i < TM * n4; i += GT) {
     const int r = i / n4, c4 = i - r * n4;
@@ -374,13 +389,7 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       }
       continue;
     }
-    if (g.epi == EPI_GELU) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
-    } else if (g.epi == EPI_RESID) {
-      const float4 r4 = *reinterpret_cast<const float4*>(g.resid + o0);
-      v[0] = r4.x + v[0]; v[1] = r4.y + v[1]; v[2] = r4.z + v[2]; v[3] = r4.w + v[3];
-    } else if (g.epi == EPI_PE) {
+    if (g.epi == EPI_PE) {
       const float4 p4 = __ldg(reinterpret_cast<const float4*>(g.pe + (int64_t)(row % g.pe_period) * g.N + col0));
       v[0] += p4.x; v[1] += p4.y; v[2] += p4.z; v[3] += p4.w;
     }
@@ -393,7 +402,7 @@ static int gemm_main_bytes(int NB, bool swi) {
   const int pipe = 2 * G_A_BUF + G_NW * 2 * (GK / 4) * NB * 16, stage = TM * (nout + 4) * 4;
   return (int)align_up(pipe > stage ? pipe : stage, 128);
 }
-static int gemm_smem(int NB, bool swi) { return gemm_main_bytes(NB, swi) + 2 * TM * 4 + (G_NW + 2) * 8 + 16; }
+static int gemm_smem(int NB, bool swi) { return gemm_main_bytes(NB, swi) + 2 * TM * 4 + 160 * 4 + (G_NW + 2) * 8 + 16; }
 
 int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st) {
   const bool swi = g.epi == EPI_SWIGLU;
@@ -406,6 +415,7 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
   EDTTS_REQUIRE(al16(g.A) && al16(g.norm_w) && al16(g.norm_b) && al16(g.mod) && g.mod_stride % 4 == 0 && al16(g.resid) && al16(g.pe) &&
                     al16(g.out) && al16(g.x_t),
                 EDTTS_EINVAL, "t3_gemm: operands must be 16-byte aligned");
+  EDTTS_REQUIRE(g.epi != EPI_RESID || g.resid == g.out, EDTTS_EINVAL, "t3_gemm: the residual epilogue accumulates in place (resid == out)");
   T3GemmArgs a;
   a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi);
   static PerDeviceOnce configured;
