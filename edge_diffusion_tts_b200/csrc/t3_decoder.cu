@@ -21,11 +21,13 @@
 #define EDTTS_DECL_ONLY
 #include "t3_decoder.cuh"
 #include "tf32x3.cuh"
+#include <algorithm>
 
 namespace edtts {
 namespace t3 {
 
-constexpr int GT = 256;                               // threads of the GEMM kernel
+constexpr int GT = 256;                               // compute threads of the GEMM kernel
+constexpr int GT_ALL = GT + 32;                       // + the MMA issuer warp
 
 // ---- weight images ------------------------------------------------------------------------------------------------------
 struct PackJob {
@@ -102,12 +104,13 @@ struct T3GemmArgs {
   const float* wimg;
   int64_t img_stride;
   int NB, nchunk, main_bytes;
+  int ahead;                                          // CTAs resident on the device at a time: the tile `ahead` positions on is prefetched into L2
 };
 constexpr int GK = 16;                                // contraction elements per pipeline chunk
 constexpr int G_A_BUF = 2 * (GK / 4) * TM * 16;       // hi | lo operand image of one chunk: 16,384 B
 constexpr int G_NW = 3;                               // weight chunk buffers
 
-__global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ T3GemmArgs a) {
+__global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constant__ T3GemmArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const GemmArgs& g = a.g;
   const int NB = a.NB;
@@ -117,19 +120,40 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
   float* s_rstd = reinterpret_cast<float*>(smem + a.main_bytes);
   float* s_mean = s_rstd + TM;
   float* s_bias = s_mean + TM;                                    // [NB <= 160] bias of the block's image rows
-  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_bias + 160);    // [G_NW]
-  uint64_t* bar_mma = bar_w + G_NW;                               // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 2);
+  uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_bias + 160);    // [G_NW] weight chunk landed (bulk-copy bytes)
+  uint64_t* bar_mma = bar_w + G_NW;                               // [2] MMAs of chunk c retired (tcgen05.commit)
+  uint64_t* bar_a = bar_mma + 2;                                  // [2] operand image of chunk c written (one arrival per compute warp)
+  uint64_t* bar_t = bar_a + 2;                                    // raw tile landed (statistics pass)
+  uint64_t* bar_go = bar_t + 1;                                   // statistics done: the pipeline buffers may be filled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_go + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TM;
   const float* wimg = a.wimg + (int64_t)blockIdx.y * a.img_stride;
   const int K = g.K, nchunk = a.nchunk;
+  // normalisation prologue with contiguous rows: the raw tile is pulled into shared memory by ONE bulk copy (over the still unused
+  // pipeline buffers) for the row statistics -- which also leaves it in L2 for the chunk loads of the main loop
+  const bool staged = g.pro != PRO_NONE && g.lda == K && (int64_t)TM * K * 4 <= a.main_bytes;
+#ifdef T3_CLOCKS   // development: cycle counts of one CTA's phases (thread 0), printed
+  long long ck0 = clock64(), ck_m = 0, ck_split = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0;
+#define T3_CK(var, stmt) { const long long t_ = clock64(); stmt; var += clock64() - t_; }
+#else
+#define T3_CK(var, stmt) { stmt; }
+#endif
 
   if (tid == 0) {
     for (int i = 0; i < G_NW; ++i) mbar_init(bar_w + i, 1);
     mbar_init(bar_mma, 1);
     mbar_init(bar_mma + 1, 1);
+    mbar_init(bar_a, GT / 32);
+    mbar_init(bar_a + 1, GT / 32);
+    mbar_init(bar_t, 1);
+    mbar_init(bar_go, 1);
     mbar_fence_init();
+    if (staged) {
+      const uint32_t nbytes = (uint32_t)(min((int64_t)TM, g.rows - row0) * K * 4);
+      mbar_expect_tx(bar_t, nbytes);
+      bulk_g2s(smem, g.A + row0 * g.lda, nbytes, bar_t);
+    }
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid < NB) {                                      // image row j of the block <-> bias index (SwiGLU: x rows, then their gates)
@@ -137,17 +161,52 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
     const int j = tid < nout ? blockIdx.y * nout + tid : g.N + blockIdx.y * nout + (tid - nout);
     s_bias[tid] = g.bias ? __ldg(g.bias + j) : 0.f;
   }
+  tc_fence_before();
+  __syncthreads();                                     // barriers initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
 
-  // weight chunk c (16 elements = half of a 32-element image chunk): hi slabs, lo slabs
-  auto request_w = [&](int c) {
-    uint64_t* bar = bar_w + c % G_NW;
-    uint8_t* dst = sW + (c % G_NW) * 2 * w_half;
-    const float* src = wimg + (int64_t)(c >> 1) * (64 * NB) + (c & 1) * (16 * NB);
-    mbar_expect_tx(bar, 2 * w_half);
-    bulk_g2s(dst, src, w_half, bar);
-    bulk_g2s(dst + w_half, src + 32 * NB, w_half, bar);
-  };
+  // ================= MMA issuer / weight streamer: warp 8, one elected lane =================
+  // No compute thread ever sits in the tensor core's queue: the issuer waits for "operand image c written" (bar_a) and "weight
+  // chunk c landed" (bar_w), issues the six MMAs of the chunk and commits them to bar_mma; a weight buffer is refilled as soon as
+  // the chunk that used it has retired (three buffers: chunk c + 2 is requested while chunks c and c + 1 are queued).
+  if (warp == GT / 32) {
+    if (lane == 0) {
+      auto request_w = [&](int c) {                    // chunk c (16 elements = half of a 32-element image chunk): hi slabs, lo slabs
+        uint64_t* bar = bar_w + c % G_NW;
+        uint8_t* dst = sW + (c % G_NW) * 2 * w_half;
+        const float* src = wimg + (int64_t)(c >> 1) * (64 * NB) + (c & 1) * (16 * NB);
+        mbar_expect_tx(bar, 2 * w_half);
+        bulk_g2s(dst, src, w_half, bar);
+        bulk_g2s(dst + w_half, src + 32 * NB, w_half, bar);
+      };
+      if (g.lda == K) {                                // L2 prefetch (fire and forget) of the tile a later CTA of this SM will work on
+        const int64_t r0 = row0 + (int64_t)a.ahead * TM;
+        if (r0 < g.rows) {
+          const int64_t nbytes = (min((int64_t)TM, g.rows - r0)) * K * 4;
+          const char* src = reinterpret_cast<const char*>(g.A + r0 * g.lda);
+          for (int64_t o = 0; o < nbytes; o += 16384) bulk_prefetch_l2(src + o, (uint32_t)min((int64_t)16384, nbytes - o));
+        }
+      }
+      if (staged) mbar_wait(bar_go, 0);                // the raw tile overlays the pipeline buffers until the statistics are done
+      for (int c = 0; c < G_NW && c < nchunk; ++c) request_w(c);
+      for (int c = 0; c < nchunk; ++c) {
+        mbar_wait(bar_a + (c & 1), (c >> 1) & 1);
+        mbar_wait(bar_w + c % G_NW, (c / G_NW) & 1);
+        tc_fence_after();
+        const uint32_t ah = smem_u32(sA + (c & 1) * G_A_BUF), wh = smem_u32(sW + (c % G_NW) * 2 * w_half);
+        issue_chunk(tmem, ah, ah + G_A_BUF / 2, wh, wh + w_half, GK / 8, NB, c > 0);
+        umma_commit(bar_mma + (c & 1));
+        if (c >= 1 && c + 2 < nchunk) {                // buffer (c + 2) % 3 was chunk c - 1's
+          mbar_wait(bar_mma + ((c - 1) & 1), ((c - 1) >> 1) & 1);
+          request_w(c + 2);
+        }
+      }
+    }
+    return;
+  }
 
+  // ================= compute warps 0-7 =================
   // this thread's two (row, 16-byte piece) slots of every chunk
   const int ap = lane >> 3;
   int ar[2];
@@ -165,30 +224,23 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
     for (int s = 0; s < 2; ++s)
       dst[s] = (aptr[s] && c < nchunk) ? __ldg(reinterpret_cast<const float4*>(aptr[s] + GK * c)) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  float4 cur[2], nx1[2], nx2[2];
-  fetch(0, cur);
-  fetch(1, nx1);
+  float4 cur[2], nx1[2], nx2[2], nx3[2];
 
-  // ---- row statistics of the normalisation prologues (K <= 192): a warp per row, four rows per pass with all their loads in
-  // flight before the first reduction (a row at a time pays the DRAM latency 16 times per warp: 24 % of the kernel's samples) ----
+  // ---- row statistics of the normalisation prologues (K <= 192), a warp per row ----
   if (g.pro != PRO_NONE) {
-    constexpr int RB = 4;
-    for (int rb = warp * (TM / (GT / 32)); rb < (warp + 1) * (TM / (GT / 32)); rb += RB) {
-      float v[RB][6];
-#pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        const int64_t row = row0 + rb + u;
+    constexpr int RPW = TM / (GT / 32);                // 16 rows per warp
+    if (staged) {
+      mbar_wait(bar_t, 0);
+      const float* raw = reinterpret_cast<const float*>(smem);
+      for (int r = warp * RPW; r < (warp + 1) * RPW; ++r) {
+        float v[6];
+        float s = 0.f;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int k = lane + 32 * i;
-          v[u][i] = (row < g.rows && k < K) ? __ldg(g.A + row * g.lda + k) : 0.f;
+          v[i] = (row0 + r < g.rows && k < K) ? raw[r * K + k] : 0.f;
+          s += (g.pro == PRO_LN) ? v[i] : v[i] * v[i];
         }
-      }
-#pragma unroll
-      for (int u = 0; u < RB; ++u) {
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) s += (g.pro == PRO_LN) ? v[u][i] : v[u][i] * v[u][i];
         s = warp_sum(s);
         float mean = 0.f, var;
         if (g.pro == PRO_LN) {
@@ -197,7 +249,7 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
             const int k = lane + 32 * i;
-            const float d = (k < K) ? v[u][i] - mean : 0.f;
+            const float d = (k < K) ? v[i] - mean : 0.f;
             q += d * d;
           }
           var = warp_sum(q) / (float)K;
@@ -205,20 +257,62 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
           var = s / (float)K;
         }
         if (lane == 0) {
-          s_rstd[rb + u] = 1.0f / sqrtf(var + g.norm_eps);
-          s_mean[rb + u] = mean;
+          s_rstd[r] = 1.0f / sqrtf(var + g.norm_eps);
+          s_mean[r] = mean;
+        }
+      }
+    } else {                                           // strided rows: four rows per pass straight from global memory
+      constexpr int RB = 4;
+      for (int rb = warp * RPW; rb < (warp + 1) * RPW; rb += RB) {
+        float v[RB][6];
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int64_t row = row0 + rb + u;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            const int k = lane + 32 * i;
+            v[u][i] = (row < g.rows && k < K) ? __ldg(g.A + row * g.lda + k) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) s += (g.pro == PRO_LN) ? v[u][i] : v[u][i] * v[u][i];
+          s = warp_sum(s);
+          float mean = 0.f, var;
+          if (g.pro == PRO_LN) {
+            mean = s / (float)K;
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const int k = lane + 32 * i;
+              const float d = (k < K) ? v[u][i] - mean : 0.f;
+              q += d * d;
+            }
+            var = warp_sum(q) / (float)K;
+          } else {
+            var = s / (float)K;
+          }
+          if (lane == 0) {
+            s_rstd[rb + u] = 1.0f / sqrtf(var + g.norm_eps);
+            s_mean[rb + u] = mean;
+          }
         }
       }
     }
+    named_bar_sync(1, GT);                             // statistics visible to every compute thread, the raw tile is dead
+    if (staged && tid == 0) mbar_arrive(bar_go);
   }
-  tc_fence_before();
-  __syncthreads();                                     // barriers initialised, TMEM allocated, statistics written
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (tid == 0) request_w(0);
+  fetch(0, cur);
+  fetch(1, nx1);
+  fetch(2, nx2);
+#ifdef T3_CLOCKS
+  ck1 = clock64();
+#endif
 
   for (int c = 0; c < nchunk; ++c) {
-    fetch(c + 2, nx2);
+    fetch(c + 3, nx3);
     // the chunk's prologue vectors (16-byte loads, issued before the wait below): norm weight / bias of columns 16 c + 4 ap ..,
     // AdaLN scale and shift of this thread's two rows
     float4 w4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f), sc4[2], sh4[2];
@@ -236,13 +330,14 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
         }
       }
     }
-    if (c >= 2) {                                      // operand buffer c & 1 (and weight buffer (c + 1) % 3) are free once chunk c - 2 retired
-      mbar_wait(bar_mma + (c & 1), ((c >> 1) - 1) & 1);
-      tc_fence_after();
+    if (c >= 2) {                                      // operand buffer c & 1 is free once chunk c - 2 retired
+      T3_CK(ck_m, mbar_wait(bar_mma + (c & 1), ((c >> 1) - 1) & 1))
     }
-    if (tid == 0 && c + 1 < nchunk) request_w(c + 1);
     uint8_t* sAh = sA + (c & 1) * G_A_BUF;
     uint8_t* sAl = sAh + G_A_BUF / 2;
+#ifdef T3_CLOCKS
+    const long long t_split = clock64();
+#endif
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       float v[4] = {cur[s].x, cur[s].y, cur[s].z, cur[s].w};
@@ -265,23 +360,26 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       split_store(sAh, sAl, ap, ar[s], v);
     }
     fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      mbar_wait(bar_w + c % G_NW, (c / G_NW) & 1);
-      tc_fence_after();
-      const uint32_t wh = smem_u32(sW + (c % G_NW) * 2 * w_half);
-      issue_chunk(tmem, smem_u32(sAh), smem_u32(sAl), wh, wh + w_half, GK / 8, NB, c > 0);
-      umma_commit(bar_mma + (c & 1));
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_a + (c & 1));
+#ifdef T3_CLOCKS
+    ck_split += clock64() - t_split;
+#endif
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       cur[s] = nx1[s];
       nx1[s] = nx2[s];
+      nx2[s] = nx3[s];
     }
   }
+#ifdef T3_CLOCKS
+  ck2 = clock64();
+#endif
   mbar_wait(bar_mma + ((nchunk - 1) & 1), ((nchunk - 1) >> 1) & 1);   // the last commit covers every earlier MMA
   tc_fence_after();
+#ifdef T3_CLOCKS
+  ck3 = clock64();
+#endif
 
   // ---- epilogue, phase 1: thread = (row r, half of the block's output columns) -> stage[r][col] (+ bias, SwiGLU) -----------
   const bool swi = g.epi == EPI_SWIGLU;
@@ -312,8 +410,11 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
   }
   fence_proxy_async();                                 // the staged tile is read by bulk copies below
   tc_fence_before();
-  __syncthreads();
+  named_bar_sync(1, GT);
   if (warp == 0) tmem_dealloc<256>(tmem);
+#ifdef T3_CLOCKS
+  ck4 = clock64();
+#endif
 
   // ---- phase 2a: plain / residual outputs leave by the TMA engine, one bulk copy (or bulk add: global += shared, performed in
   // L2 -- the residual never travels to the SM) per row --------------------------------------------------------------------------
@@ -325,6 +426,11 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
       bulk_commit();
       bulk_wait_all();                                 // shared memory must outlive the engine's reads; writes performed
     }
+#ifdef T3_CLOCKS
+    if (tid == 0 && blockIdx.x == 640 && blockIdx.y == 0)
+      printf("t3clk K=%d NB=%d pro=%d epi=%d: setup %lld loop %lld (mma-wait %lld split+arrive %lld) final %lld phase1 %lld bulk %lld\n", K, NB,
+             g.pro, g.epi, ck1 - ck0, ck2 - ck1, ck_m, ck_split, ck3 - ck2, ck4 - ck3, clock64() - ck4);
+#endif
     return;
   }
 
@@ -397,12 +503,13 @@ __global__ void __launch_bounds__(GT, 2) t3_gemm_kernel(const __grid_constant__ 
   }
 }
 
-static int gemm_main_bytes(int NB, bool swi) {
+// pipeline buffers, overlaid by the epilogue tile and (normalisation prologue with contiguous rows) by the raw tile of the statistics pass
+static int gemm_main_bytes(int NB, bool swi, int raw_bytes) {
   const int nout = swi ? NB / 2 : NB;
   const int pipe = 2 * G_A_BUF + G_NW * 2 * (GK / 4) * NB * 16, stage = TM * (nout + 4) * 4;
-  return (int)align_up(pipe > stage ? pipe : stage, 128);
+  return (int)align_up(std::max(std::max(pipe, stage), raw_bytes), 128);
 }
-static int gemm_smem(int NB, bool swi) { return gemm_main_bytes(NB, swi) + 2 * TM * 4 + 160 * 4 + (G_NW + 2) * 8 + 16; }
+static int gemm_smem(int NB, bool swi, int raw_bytes) { return gemm_main_bytes(NB, swi, raw_bytes) + 2 * TM * 4 + 160 * 4 + (G_NW + 6) * 8 + 16; }
 
 int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st) {
   const bool swi = g.epi == EPI_SWIGLU;
@@ -417,15 +524,17 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
                 EDTTS_EINVAL, "t3_gemm: operands must be 16-byte aligned");
   EDTTS_REQUIRE(g.epi != EPI_RESID || g.resid == g.out, EDTTS_EINVAL, "t3_gemm: the residual epilogue accumulates in place (resid == out)");
   T3GemmArgs a;
-  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi);
+  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; const int raw_bytes = (g.pro != PRO_NONE && g.lda == g.K) ? TM * g.K * 4 : 0;
+  a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi, raw_bytes);
+  a.ahead = 2 * sm_count();
   static PerDeviceOnce configured;
   if (configured.need()) {
-    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160, false)) != cudaSuccess)
+    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160, false, TM * 192 * 4)) != cudaSuccess)
       return check_launch("t3_gemm smem attribute");
     configured.set();
   }
   LaunchScope ls(KC_T3_GEMM, st);
-  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT, gemm_smem(NB, swi), st>>>(a);
+  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT_ALL, gemm_smem(NB, swi, raw_bytes), st>>>(a);
   return check_launch("t3_gemm");
 }
 
@@ -436,7 +545,9 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
 //                 C  S(i) (issued an iteration ago) -> registers, softmax           | S(i+1)
 //                 D  wait P V(i-1); lazy rescale of O; V(i), P(i) -> operand images |
 //                 E  sync, O += P(i) V(i) issued (accumulates in tensor memory)     |
-// so no thread waits for an MMA round trip it has just issued.  O stays in tensor memory for the whole head: the running
+// The MMAs are issued by a fifth warp (one elected lane), woken by per-warp mbarrier arrivals (bar_k: K image written and the S
+// block free; bar_p: V and P images written, O rescaled), so no softmax thread sits in the tensor core's queue or waits for an
+// MMA round trip it has just asked for, and the four softmax warps never wait for each other.  O stays in tensor memory for the whole head: the running
 // maximum is only raised when a block exceeds it by more than 2^8 (p <= 256 otherwise, harmless in fp32 / tf32 x 2), and only
 // then does the warp rescale its O rows (tcgen05.ld / st) -- after the first block or two that does not happen.
 constexpr int AQ = 128;                               // queries per CTA (= threads = MMA M)
@@ -449,8 +560,9 @@ constexpr int A_P_HALF = (AKB / 4) * AQ * 16;         // 8 slabs x 128 rows x 16
 constexpr int A_SMEM = 2 * (A_Q_HALF + 2 * A_K_HALF + A_V_HALF + A_P_HALF) + 64;
 constexpr int A_NLD = (AKB * (HD / 4) + AQ - 1) / AQ; // 16-byte pieces of a K (or V) block per thread: 320 / 128 -> 3
 constexpr float A_GROW = 8.0f;                        // lazy running maximum: raise it only beyond 2^8
+constexpr int A_THREADS = AQ + 32;                    // softmax warps + the MMA issuer warp
 
-__global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQh = smem;
   uint8_t* sQl = sQh + A_Q_HALF;
@@ -460,10 +572,13 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
   uint8_t* sPh = sVl + A_V_HALF;
   uint8_t* sPl = sPh + A_P_HALF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPl + A_P_HALF);
-  uint64_t* bar_s = bars;                              // [2]
-  uint64_t* bar_o = bars + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-  const int tid = threadIdx.x, warp = tid >> 5;
+  uint64_t* bar_s = bars;                              // [2] S block (i & 1) computed
+  uint64_t* bar_o = bars + 2;                          // P V(i) retired
+  uint64_t* bar_k = bars + 3;                          // [2] K image of block i written, S block (i & 1) read out (4 warp arrivals)
+  uint64_t* bar_p = bars + 5;                          // V and P images of block i written, O rescaled (4 warp arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool issuer = warp == AQ / 32;
   const int b = blockIdx.z, h = blockIdx.y;
   const int q0 = blockIdx.x * AQ;
   const int qi = q0 + tid;
@@ -474,6 +589,9 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     mbar_init(bar_s, 1);
     mbar_init(bar_s + 1, 1);
     mbar_init(bar_o, 1);
+    mbar_init(bar_k, AQ / 32);
+    mbar_init(bar_k + 1, AQ / 32);
+    mbar_init(bar_p, AQ / 32);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<128>(tmem_slot);
@@ -482,7 +600,7 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     *reinterpret_cast<float4*>(sVh + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(sVl + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  {                                                    // this thread's query row, pre-scaled by scale * log2(e)
+  if (!issuer) {                                       // this thread's query row, pre-scaled by scale * log2(e)
     const float qs = a.scale * 1.4426950408889634f;
     const float* qp = a.q + ((int64_t)b * a.Tq + (active ? qi : 0)) * a.q_stride + h * HD;
     float4 t[HD / 4];
@@ -549,41 +667,61 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     }
   };
 
-  // ---- prologue: K(0) staged, S(0) issued ----
-  fetch(kbase, klo, kreg);
-  stash_k(0);
-  if (nblk > 1) fetch(kbase, klo + AKB, kreg);
-  fetch(vbase, klo, vreg);
-  fence_proxy_async();
+  // ---- prologue: K(0) staged ----
+  if (!issuer) {
+    fetch(kbase, klo, kreg);
+    stash_k(0);
+    if (nblk > 1) fetch(kbase, klo + AKB, kreg);
+    fetch(vbase, klo, vreg);
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
   const uint32_t tO = 2 * AKB;                         // columns: S0 (32) | S1 (32) | O (48)
-  if (tid == 0) {
-    issue_chunk(tmem, smem_u32(sQh), smem_u32(sQl), smem_u32(sK), smem_u32(sK) + A_K_HALF, HD / 8, AKB, false);
-    umma_commit(bar_s);
+
+  // ================= MMA issuer: warp 4, one elected lane =================
+  if (issuer) {
+    if (lane == 0) {
+      auto issue_s = [&](int i) {
+        mbar_wait(bar_k + (i & 1), (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t kh = smem_u32(sK + (i & 1) * 2 * A_K_HALF);
+        issue_chunk(tmem + (i & 1) * AKB, smem_u32(sQh), smem_u32(sQl), kh, kh + A_K_HALF, HD / 8, AKB, false);
+        umma_commit(bar_s + (i & 1));
+      };
+      issue_s(0);
+      for (int blk = 0; blk < nblk; ++blk) {
+        if (blk + 1 < nblk) issue_s(blk + 1);
+        mbar_wait(bar_p, blk & 1);
+        tc_fence_after();
+        issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, blk > 0);
+        umma_commit(bar_o);
+      }
+    }
+    return;
   }
+
+  // ================= softmax warps 0-3 =================
+  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar_k);                   // K(0) (and Q, the V padding) written
 
   float m = -INFINITY, l = 0.f;
   const int r0w = q0 + warp * 32;                      // first query row of this warp
 
   for (int blk = 0; blk < nblk; ++blk) {
     const int kc = klo + blk * AKB;
-    // ---- A / B: K(blk+1) -> second K buffer (S(blk-1), its last reader, retired: this thread waited for it), S(blk+1) issued ----
+    // ---- A: K(blk+1) -> the other K buffer (S(blk-1), its last reader, retired: this thread waited for it); this warp has read
+    // S(blk-1) out of the tensor-memory block that S(blk+1) will overwrite ----
     if (blk + 1 < nblk) {
       stash_k((blk + 1) & 1);
       if (blk + 2 < nblk) fetch(kbase, kc + 2 * AKB, kreg);
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0 && blk + 1 < nblk) {
-      tc_fence_after();
-      const uint32_t kh = smem_u32(sK + ((blk + 1) & 1) * 2 * A_K_HALF);
-      issue_chunk(tmem + ((blk + 1) & 1) * AKB, smem_u32(sQh), smem_u32(sQl), kh, kh + A_K_HALF, HD / 8, AKB, false);
-      umma_commit(bar_s + ((blk + 1) & 1));
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_k + ((blk + 1) & 1));
     }
     // ---- C: S(blk) -> registers, softmax ----
     mbar_wait(bar_s + (blk & 1), (blk >> 1) & 1);
@@ -653,15 +791,11 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     if (blk + 1 < nblk) fetch(vbase, kc + AKB, vreg);
 #pragma unroll
     for (int q4 = 0; q4 < AKB / 4; ++q4) split_store(sPh, sPl, q4, tid, s + 4 * q4);
-    // ---- E: O (+)= P(blk) V(blk) ----
+    // ---- E: hand P(blk), V(blk) to the issuer ----
     fence_proxy_async();
     tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, blk > 0);
-      umma_commit(bar_o);
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_p);
   }
   mbar_wait(bar_o, (nblk - 1) & 1);
   tc_fence_after();
@@ -677,7 +811,7 @@ __global__ void __launch_bounds__(AQ, 2) t3_attn_kernel(const AttnArgs a) {
     }
   }
   tc_fence_before();
-  __syncthreads();
+  named_bar_sync(1, AQ);
   if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
@@ -691,7 +825,7 @@ int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st) {
   }
   dim3 grid((a.Tq + AQ - 1) / AQ, NH, B);
   LaunchScope ls(a.window >= 0 ? KC_T3_ATTN_WINDOW : KC_T3_ATTN_CROSS, st);
-  t3_attn_kernel<<<grid, AQ, A_SMEM, st>>>(a);
+  t3_attn_kernel<<<grid, A_THREADS, A_SMEM, st>>>(a);
   return check_launch("t3_attn");
 }
 
