@@ -97,7 +97,7 @@ SIGNATURES = {
     "edtts_test_attention": (C.c_int, [_p, _i32, _p, _p, _i32, _p, _i32, _i32, _i32, _i32, _i32, _p]),
     "edtts_test_gemm": (C.c_int, [_p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, C.c_float, _p, _i32, _p, _p, _i32, _i32,
                                   _p, _i64, _p]),
-    "edtts_test_gemm_workspace_bytes": (_i64, [_i32, _i32, _i32]),
+    "edtts_test_gemm_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "edtts_test_hidden": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32,
                                     _i32, _p]),
 }

@@ -226,10 +226,10 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
   return launch_attn_simt(a, B, as_stream(stream));
 }
 
-extern "C" int64_t edtts_test_gemm_workspace_bytes(int32_t K, int32_t N, int32_t epi) {
+extern "C" int64_t edtts_test_gemm_workspace_bytes(int64_t rows, int32_t K, int32_t N, int32_t epi) {
   const bool swi = epi == EPI_SWIGLU;
   const int NB = (N % 160 == 0 || swi) ? 160 : 80;
-  return t3::t3_gemm_image_floats(K, N, NB, swi) * 4;
+  return align_up(t3::t3_gemm_image_floats(K, N, NB, swi) * 4, 256) + rows * 8;   // weight images | row statistics
 }
 
 extern "C" int edtts_test_gemm(const float* x, const float* w, const float* bias, float* y, int64_t rows, int32_t K, int32_t N,
@@ -246,7 +246,7 @@ extern "C" int edtts_test_gemm(const float* x, const float* w, const float* bias
   const bool swi = epi == EPI_SWIGLU;
   EDTTS_REQUIRE(N % 80 == 0, EDTTS_ENOTSUP, "test_gemm: N=%d (multiple of 80)", N);
   const int NB = (N % 160 == 0 || swi) ? 160 : 80;
-  EDTTS_REQUIRE(workspace && workspace_bytes >= edtts_test_gemm_workspace_bytes(K, N, epi), EDTTS_ENOSPC, "test_gemm: workspace");
+  EDTTS_REQUIRE(workspace && workspace_bytes >= edtts_test_gemm_workspace_bytes(rows, K, N, epi), EDTTS_ENOSPC, "test_gemm: workspace");
   if (epi == EPI_RESID) {   // the tensor-core GEMM accumulates the residual in place (resid == out), as the decoder step uses it
     EDTTS_REQUIRE(resid, EDTTS_EINVAL, "test_gemm: resid is null");
     if (cudaMemcpyAsync(y, resid, (size_t)rows * N * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)) != cudaSuccess)
@@ -255,7 +255,8 @@ extern "C" int edtts_test_gemm(const float* x, const float* w, const float* bias
   }
   int rc = t3::pack_w_blocks(w, reinterpret_cast<float*>(workspace), K, N, NB, swi, as_stream(stream));
   if (rc) return rc;
-  return t3::launch_t3_gemm(g, reinterpret_cast<const float*>(workspace), t3::t3_gemm_block_stride(K, NB), NB, as_stream(stream));
+  float* stats = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align_up(t3::t3_gemm_image_floats(K, N, NB, swi) * 4, 256));
+  return t3::launch_t3_gemm(g, reinterpret_cast<const float*>(workspace), t3::t3_gemm_block_stride(K, NB), NB, stats, as_stream(stream));
 }
 
 extern "C" int edtts_test_hidden(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv,

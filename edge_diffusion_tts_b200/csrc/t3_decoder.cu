@@ -103,9 +103,51 @@ struct T3GemmArgs {
   GemmArgs g;
   const float* wimg;
   int64_t img_stride;
+  const float* stats;                                 // normalisation prologue: (rstd, mean) per row, written by t3_rowstats_kernel
   int NB, nchunk, main_bytes;
   int ahead;                                          // CTAs resident on the device at a time: the tile `ahead` positions on is prefetched into L2
 };
+// Row statistics of the normalisation prologues, once per row (every NB-column block of a GEMM needs them, and inside the GEMM
+// they cost a pass over the tile before the first MMA can be fed: 14 k of a CTA's ~45 k cycles).  A warp per row, four rows in
+// flight per warp; stats[row] = (rstd, mean).
+__global__ void __launch_bounds__(256) t3_rowstats_kernel(const float* __restrict__ A, int64_t rows, int K, int lda, int pro, float eps,
+                                                          float2* __restrict__ stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int RB = 4;
+  for (int64_t r0 = ((int64_t)blockIdx.x * 8 + warp) * RB; r0 < rows; r0 += (int64_t)gridDim.x * 8 * RB) {
+    float v[RB][6];
+#pragma unroll
+    for (int u = 0; u < RB; ++u)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int k = lane + 32 * i;
+        v[u][i] = (r0 + u < rows && k < K) ? __ldg(A + (r0 + u) * lda + k) : 0.f;
+      }
+#pragma unroll
+    for (int u = 0; u < RB; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) s += (pro == PRO_LN) ? v[u][i] : v[u][i] * v[u][i];
+      s = warp_sum(s);
+      float mean = 0.f, var;
+      if (pro == PRO_LN) {
+        mean = s / (float)K;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int k = lane + 32 * i;
+          const float d = (k < K) ? v[u][i] - mean : 0.f;
+          q += d * d;
+        }
+        var = warp_sum(q) / (float)K;
+      } else {
+        var = s / (float)K;
+      }
+      if (lane == 0 && r0 + u < rows) stats[r0 + u] = make_float2(1.0f / sqrtf(var + eps), mean);
+    }
+  }
+}
+
 constexpr int GK = 16;                                // contraction elements per pipeline chunk
 constexpr int G_A_BUF = 2 * (GK / 4) * TM * 16;       // hi | lo operand image of one chunk: 16,384 B
 constexpr int G_NW = 3;                               // weight chunk buffers
@@ -123,16 +165,11 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
   uint64_t* bar_w = reinterpret_cast<uint64_t*>(s_bias + 160);    // [G_NW] weight chunk landed (bulk-copy bytes)
   uint64_t* bar_mma = bar_w + G_NW;                               // [2] MMAs of chunk c retired (tcgen05.commit)
   uint64_t* bar_a = bar_mma + 2;                                  // [2] operand image of chunk c written (one arrival per compute warp)
-  uint64_t* bar_t = bar_a + 2;                                    // raw tile landed (statistics pass)
-  uint64_t* bar_go = bar_t + 1;                                   // statistics done: the pipeline buffers may be filled
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_go + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 2);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t row0 = (int64_t)blockIdx.x * TM;
   const float* wimg = a.wimg + (int64_t)blockIdx.y * a.img_stride;
   const int K = g.K, nchunk = a.nchunk;
-  // normalisation prologue with contiguous rows: the raw tile is pulled into shared memory by ONE bulk copy (over the still unused
-  // pipeline buffers) for the row statistics -- which also leaves it in L2 for the chunk loads of the main loop
-  const bool staged = g.pro != PRO_NONE && g.lda == K && (int64_t)TM * K * 4 <= a.main_bytes;
 #ifdef T3_CLOCKS   // development: cycle counts of one CTA's phases (thread 0), printed
   long long ck0 = clock64(), ck_m = 0, ck_split = 0, ck1 = 0, ck2 = 0, ck3 = 0, ck4 = 0;
 #define T3_CK(var, stmt) { const long long t_ = clock64(); stmt; var += clock64() - t_; }
@@ -146,14 +183,12 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
     mbar_init(bar_mma + 1, 1);
     mbar_init(bar_a, GT / 32);
     mbar_init(bar_a + 1, GT / 32);
-    mbar_init(bar_t, 1);
-    mbar_init(bar_go, 1);
     mbar_fence_init();
-    if (staged) {
-      const uint32_t nbytes = (uint32_t)(min((int64_t)TM, g.rows - row0) * K * 4);
-      mbar_expect_tx(bar_t, nbytes);
-      bulk_g2s(smem, g.A + row0 * g.lda, nbytes, bar_t);
-    }
+  }
+  if (g.pro != PRO_NONE && tid < TM) {                 // row statistics of the tile (t3_rowstats_kernel)
+    const float2 st = row0 + tid < g.rows ? __ldg(reinterpret_cast<const float2*>(a.stats) + row0 + tid) : make_float2(0.f, 0.f);
+    s_rstd[tid] = st.x;
+    s_mean[tid] = st.y;
   }
   if (warp == 0) tmem_alloc<256>(tmem_slot);
   if (tid < NB) {                                      // image row j of the block <-> bias index (SwiGLU: x rows, then their gates)
@@ -180,15 +215,14 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
         bulk_g2s(dst, src, w_half, bar);
         bulk_g2s(dst + w_half, src + 32 * NB, w_half, bar);
       };
-      if (g.lda == K) {                                // L2 prefetch (fire and forget) of the tile a later CTA of this SM will work on
-        const int64_t r0 = row0 + (int64_t)a.ahead * TM;
+      for (int w = 0; w < 2 && g.lda == K; ++w) {      // L2 prefetch (fire and forget) of this tile's rows and of the tile a later
+        const int64_t r0 = row0 + (int64_t)w * a.ahead * TM;   // CTA of this SM will work on
         if (r0 < g.rows) {
           const int64_t nbytes = (min((int64_t)TM, g.rows - r0)) * K * 4;
           const char* src = reinterpret_cast<const char*>(g.A + r0 * g.lda);
           for (int64_t o = 0; o < nbytes; o += 16384) bulk_prefetch_l2(src + o, (uint32_t)min((int64_t)16384, nbytes - o));
         }
       }
-      if (staged) mbar_wait(bar_go, 0);                // the raw tile overlays the pipeline buffers until the statistics are done
       for (int c = 0; c < G_NW && c < nchunk; ++c) request_w(c);
       for (int c = 0; c < nchunk; ++c) {
         mbar_wait(bar_a + (c & 1), (c >> 1) & 1);
@@ -226,84 +260,6 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
   };
   float4 cur[2], nx1[2], nx2[2], nx3[2];
 
-  // ---- row statistics of the normalisation prologues (K <= 192), a warp per row ----
-  if (g.pro != PRO_NONE) {
-    constexpr int RPW = TM / (GT / 32);                // 16 rows per warp
-    if (staged) {
-      mbar_wait(bar_t, 0);
-      const float* raw = reinterpret_cast<const float*>(smem);
-      for (int r = warp * RPW; r < (warp + 1) * RPW; ++r) {
-        float v[6];
-        float s = 0.f;
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          const int k = lane + 32 * i;
-          v[i] = (row0 + r < g.rows && k < K) ? raw[r * K + k] : 0.f;
-          s += (g.pro == PRO_LN) ? v[i] : v[i] * v[i];
-        }
-        s = warp_sum(s);
-        float mean = 0.f, var;
-        if (g.pro == PRO_LN) {
-          mean = s / (float)K;
-          float q = 0.f;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int k = lane + 32 * i;
-            const float d = (k < K) ? v[i] - mean : 0.f;
-            q += d * d;
-          }
-          var = warp_sum(q) / (float)K;
-        } else {
-          var = s / (float)K;
-        }
-        if (lane == 0) {
-          s_rstd[r] = 1.0f / sqrtf(var + g.norm_eps);
-          s_mean[r] = mean;
-        }
-      }
-    } else {                                           // strided rows: four rows per pass straight from global memory
-      constexpr int RB = 4;
-      for (int rb = warp * RPW; rb < (warp + 1) * RPW; rb += RB) {
-        float v[RB][6];
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          const int64_t row = row0 + rb + u;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) {
-            const int k = lane + 32 * i;
-            v[u][i] = (row < g.rows && k < K) ? __ldg(g.A + row * g.lda + k) : 0.f;
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < RB; ++u) {
-          float s = 0.f;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) s += (g.pro == PRO_LN) ? v[u][i] : v[u][i] * v[u][i];
-          s = warp_sum(s);
-          float mean = 0.f, var;
-          if (g.pro == PRO_LN) {
-            mean = s / (float)K;
-            float q = 0.f;
-#pragma unroll
-            for (int i = 0; i < 6; ++i) {
-              const int k = lane + 32 * i;
-              const float d = (k < K) ? v[u][i] - mean : 0.f;
-              q += d * d;
-            }
-            var = warp_sum(q) / (float)K;
-          } else {
-            var = s / (float)K;
-          }
-          if (lane == 0) {
-            s_rstd[rb + u] = 1.0f / sqrtf(var + g.norm_eps);
-            s_mean[rb + u] = mean;
-          }
-        }
-      }
-    }
-    named_bar_sync(1, GT);                             // statistics visible to every compute thread, the raw tile is dead
-    if (staged && tid == 0) mbar_arrive(bar_go);
-  }
   fetch(0, cur);
   fetch(1, nx1);
   fetch(2, nx2);
@@ -503,15 +459,15 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
   }
 }
 
-// pipeline buffers, overlaid by the epilogue tile and (normalisation prologue with contiguous rows) by the raw tile of the statistics pass
-static int gemm_main_bytes(int NB, bool swi, int raw_bytes) {
+// pipeline buffers, overlaid by the epilogue tile
+static int gemm_main_bytes(int NB, bool swi) {
   const int nout = swi ? NB / 2 : NB;
   const int pipe = 2 * G_A_BUF + G_NW * 2 * (GK / 4) * NB * 16, stage = TM * (nout + 4) * 4;
-  return (int)align_up(std::max(std::max(pipe, stage), raw_bytes), 128);
+  return (int)align_up(std::max(pipe, stage), 128);
 }
-static int gemm_smem(int NB, bool swi, int raw_bytes) { return gemm_main_bytes(NB, swi, raw_bytes) + 2 * TM * 4 + 160 * 4 + (G_NW + 6) * 8 + 16; }
+static int gemm_smem(int NB, bool swi) { return gemm_main_bytes(NB, swi) + 2 * TM * 4 + 160 * 4 + (G_NW + 6) * 8 + 16; }
 
-int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st) {
+int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, float* stats, cudaStream_t st) {
   const bool swi = g.epi == EPI_SWIGLU;
   const int nout = swi ? NB / 2 : NB;
   EDTTS_REQUIRE(g.rows > 0 && g.K % GK == 0 && g.lda % 4 == 0 && g.ldo % 4 == 0 && NB % 16 == 0 && NB <= 160 && nout % 16 == 0 &&
@@ -524,17 +480,25 @@ int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int
                 EDTTS_EINVAL, "t3_gemm: operands must be 16-byte aligned");
   EDTTS_REQUIRE(g.epi != EPI_RESID || g.resid == g.out, EDTTS_EINVAL, "t3_gemm: the residual epilogue accumulates in place (resid == out)");
   T3GemmArgs a;
-  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; const int raw_bytes = (g.pro != PRO_NONE && g.lda == g.K) ? TM * g.K * 4 : 0;
-  a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi, raw_bytes);
+  a.g = g; a.wimg = wimg; a.img_stride = img_stride; a.NB = NB; 
+  a.nchunk = g.K / GK; a.main_bytes = gemm_main_bytes(NB, swi); a.stats = stats;
+  if (g.pro != PRO_NONE) {
+    EDTTS_REQUIRE(stats && (reinterpret_cast<uintptr_t>(stats) & 7) == 0, EDTTS_EINVAL, "t3_gemm: the normalisation prologue needs a statistics buffer");
+    LaunchScope ls(KC_TC_MISC, st);
+    const int64_t blocks = std::min<int64_t>((g.rows + 31) / 32, stream_grid_cap(8));
+    t3_rowstats_kernel<<<(unsigned)blocks, 256, 0, st>>>(g.A, g.rows, g.K, g.lda, g.pro, g.norm_eps, reinterpret_cast<float2*>(stats));
+    int rc = check_launch("t3_rowstats");
+    if (rc) return rc;
+  }
   a.ahead = 2 * sm_count();
   static PerDeviceOnce configured;
   if (configured.need()) {
-    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160, false, TM * 192 * 4)) != cudaSuccess)
+    if (cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem(160, false)) != cudaSuccess)
       return check_launch("t3_gemm smem attribute");
     configured.set();
   }
   LaunchScope ls(KC_T3_GEMM, st);
-  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT_ALL, gemm_smem(NB, swi, raw_bytes), st>>>(a);
+  t3_gemm_kernel<<<dim3((unsigned)((g.rows + TM - 1) / TM), g.N / nout), GT_ALL, gemm_smem(NB, swi), st>>>(a);
   return check_launch("t3_gemm");
 }
 
@@ -855,7 +819,7 @@ static ImgLayout img_layout() {
 int64_t t3_decoder_workspace_bytes(int B, int T, int S) {
   (void)S;
   const int64_t R = (int64_t)B * T;
-  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256);
+  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256);
 }
 
 int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
@@ -866,6 +830,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
   float* a = reinterpret_cast<float*>(ws + align_up(R * H * 4, 256));
   float* big = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256));
   float* img = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256));
+  float* stats = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256));
   const ImgLayout IL = img_layout();
   const float scale = 1.0f / sqrtf((float)HD);
   const int64_t s160 = t3_gemm_block_stride(H, 160), s80 = t3_gemm_block_stride(H, 80), s_in = t3_gemm_block_stride(M, 160),
@@ -892,7 +857,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     GemmArgs g;
     g.A = x_t; g.rows = R; g.K = M; g.lda = M; g.W = w->in_proj_w; g.N = H; g.bias = w->in_proj_b;
     g.out = h; g.ldo = H; g.epi = EPI_PE; g.pe = w->pos_pe; g.pe_period = T;
-    if ((rc = launch_t3_gemm(g, img + IL.in_proj, s_in, 160, st))) return rc;
+    if ((rc = launch_t3_gemm(g, img + IL.in_proj, s_in, 160, stats, st))) return rc;
   }
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
@@ -902,7 +867,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = L.attn_qkv_w; g.N = 3 * H; g.out = big; g.ldo = 3 * H;
       g.pro = PRO_ADARMS; g.norm_w = L.norm1_norm_w; g.mod = mod + (int64_t)(2 * l) * 2 * H;
       g.mod_stride = 2 * NL * 2 * H; g.rows_per_batch = T;
-      if ((rc = launch_t3_gemm(g, li + IL.qkv, s160, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.qkv, s160, 160, stats, st))) return rc;
     }
     {  // banded self-attention (attention.py:94-111)
       AttnArgs at{big, 3 * H, big + H, big + 2 * H, 3 * H, a, H, T, T, WIN, scale};
@@ -912,13 +877,13 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       GemmArgs g;
       g.A = a; g.rows = R; g.K = H; g.lda = H; g.W = L.attn_proj_w; g.N = H; g.bias = L.attn_proj_b;
       g.out = h; g.ldo = H; g.epi = EPI_RESID; g.resid = h;
-      if ((rc = launch_t3_gemm(g, li + IL.proj, s160, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.proj, s160, 160, stats, st))) return rc;
     }
     {  // q = q_proj(norm2(h))   (transformer.py:151, mla.py:139)
       GemmArgs g;
       g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = L.q_proj_w; g.N = H; g.out = big; g.ldo = H;
       g.pro = PRO_RMS; g.norm_w = L.norm2_w;
-      if ((rc = launch_t3_gemm(g, li + IL.q, s160, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.q, s160, 160, stats, st))) return rc;
     }
     {  // full cross-attention over the S context tokens (mla.py:176-180)
       const float* kvl = kv + (int64_t)l * B * S * 2 * H;
@@ -929,7 +894,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       GemmArgs g;
       g.A = a; g.rows = R; g.K = H; g.lda = H; g.W = L.cross_out_w; g.N = H; g.out = h; g.ldo = H;
       g.epi = EPI_RESID; g.resid = h;
-      if ((rc = launch_t3_gemm(g, li + IL.out, s160, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.out, s160, 160, stats, st))) return rc;
     }
     {  // u = swiglu(ffn.net.0(norm3(h, cond)))   (transformer.py:155, :13-23)
       GemmArgs g;
@@ -937,13 +902,13 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
       g.out = big; g.ldo = FFN; g.epi = EPI_SWIGLU;
       g.pro = PRO_ADARMS; g.norm_w = L.norm3_norm_w; g.mod = mod + (int64_t)(2 * l + 1) * 2 * H;
       g.mod_stride = 2 * NL * 2 * H; g.rows_per_batch = T;
-      if ((rc = launch_t3_gemm(g, li + IL.f0, s160, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.f0, s160, 160, stats, st))) return rc;
     }
     {  // h += ffn.net.3(u)
       GemmArgs g;
       g.A = big; g.rows = R; g.K = FFN; g.lda = FFN; g.W = L.ffn3_w; g.N = H; g.bias = L.ffn3_b;
       g.out = h; g.ldo = H; g.epi = EPI_RESID; g.resid = h;
-      if ((rc = launch_t3_gemm(g, li + IL.f3, s320, 160, st))) return rc;
+      if ((rc = launch_t3_gemm(g, li + IL.f3, s320, 160, stats, st))) return rc;
     }
   }
   {  // eps = out_proj(final_norm(h)) + fused update   (decoder.py:108-109, schedule.py)
@@ -951,7 +916,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     g.A = h; g.rows = R; g.K = H; g.lda = H; g.W = w->out_proj_w; g.N = M; g.bias = w->out_proj_b;
     g.out = nullptr; g.ldo = M; g.epi = EPI_STEP; g.pro = PRO_LN; g.norm_w = w->final_norm_w;
     g.norm_b = w->final_norm_b; g.norm_eps = 1e-5f; g.rows_per_batch = T; g.x_t = x_t; g.step = *args;
-    if ((rc = launch_t3_gemm(g, img + IL.out_proj, s80, 80, st))) return rc;
+    if ((rc = launch_t3_gemm(g, img + IL.out_proj, s80, 80, stats, st))) return rc;
   }
   return EDTTS_OK;
 }

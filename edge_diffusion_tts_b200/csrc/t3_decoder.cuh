@@ -11,7 +11,8 @@ namespace t3 {
 // y = epi(pro(A) W^T + bias) with the semantics of launch_gemm_simt (g.W is only read by the packer): the weight matrix comes
 // as operand images of NB-row blocks (pack_w_blocks), block j at wimg + j * img_stride floats.  EPI_SWIGLU: block j holds the x
 // rows 80 j .. 80 j + 79 followed by their gate rows (NB = 160) and produces output columns 80 j .. 80 j + 79.
-int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, cudaStream_t st);
+// stats: rows * 2 floats of scratch (normalisation prologues: the row statistics are computed by a small launch in front)
+int launch_t3_gemm(const GemmArgs& g, const float* wimg, int64_t img_stride, int NB, float* stats, cudaStream_t st);
 // weight images of W [N or 2N][K] for launch_t3_gemm into img (t3_gemm_image_floats(K, N, swiglu) floats), one launch
 int pack_w_blocks(const float* W, float* img, int K, int N, int NB, bool swiglu, cudaStream_t st);
 int64_t t3_gemm_image_floats(int K, int N, int NB, bool swiglu);

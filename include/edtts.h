@@ -337,7 +337,7 @@ int edtts_test_gemm(const float* x, const float* w, const float* bias, float* y,
                     int32_t pro, int32_t epi, const float* norm_w, const float* norm_b, float norm_eps, const float* mod,
                     int32_t rows_per_batch, const float* resid, const float* pe, int32_t pe_period, int32_t use_tc,
                     void* workspace, int64_t workspace_bytes, void* stream);
-int64_t edtts_test_gemm_workspace_bytes(int32_t K, int32_t N, int32_t epi);
+int64_t edtts_test_gemm_workspace_bytes(int64_t rows, int32_t K, int32_t N, int32_t epi);
 
 /* Residual stream h [B*T,160] of the bf16 path after in_proj and `n_layers` transformer blocks, the last block
  * optionally stopped early: stop_phase 1 = after x + attn(norm1(x)) (transformer.py:146), 2 = after the

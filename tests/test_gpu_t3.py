@@ -20,7 +20,7 @@ def _gemm(lib, x, w, b, N, pro, epi, norm_w, norm_b, eps, mod, rpb, resid, pe, p
     from edge_diffusion_tts_b200 import _lib
     rows, K = x.shape
     y = torch.full((rows, N), float("nan"), device=DEV)
-    nbytes = int(lib.edtts_test_gemm_workspace_bytes(K, N, epi))
+    nbytes = int(lib.edtts_test_gemm_workspace_bytes(rows, K, N, epi))
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV)
     p = lambda t: None if t is None else t.data_ptr()
     _lib.check(lib.edtts_test_gemm(p(x), p(w), p(b), p(y), rows, K, N, pro, epi, p(norm_w), p(norm_b), eps, p(mod), rpb, p(resid),
