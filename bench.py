@@ -321,13 +321,17 @@ def other_configs(E, synth, cfg, dec, sched, inf, dev) -> dict:
         del idx, xT
         inf2._plans.clear()
         torch.cuda.empty_cache()
-    # cfg3 on the fp32 (1e-4) path
+    # cfg3 on the fp32-grade (max-abs 1e-4) paths: precision="fp32" = tf32 x 3 split products on the tensor cores (the class default),
+    # precision="fp32_simt" = the CUDA-core kernels it is tested against
     keep = dec.precision
-    dec.precision = "fp32"
     idx = synth.synth_sem_idx(100, B_GLOBAL, S_TOK).to(dev)
     xT = torch.randn(B_GLOBAL, T_MEL, cfg.n_mels, device=dev)
-    ms = cuda_time(lambda: inf2.generate_mel(idx, 4, x_T=xT), 1, 3)
-    put("cfg3_fp32_path", B_GLOBAL * T_MEL, ms, workload="cfg3 with precision='fp32' (the max-abs 1e-4 parity path)")
+    for prec, key, what in (("fp32", "cfg3_fp32_path", "tf32 x 3 tensor-core GEMMs and attention (the class default; max-abs 1e-4 parity path)"),
+                            ("fp32_simt", "cfg3_fp32_simt_path", "CUDA-core FFMA kernels (the checker of the fp32 path)")):
+        dec.precision = prec
+        ms = cuda_time(lambda: inf2.generate_mel(idx, 4, x_T=xT), 1, 3)
+        put(key, B_GLOBAL * T_MEL, ms, workload=f"cfg3 with precision='{prec}': {what}")
+        inf2._plans.clear()
     dec.precision = keep
     inf2._plans.clear()
     torch.cuda.empty_cache()
