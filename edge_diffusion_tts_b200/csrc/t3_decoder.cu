@@ -3,19 +3,22 @@
 // The CUDA-core parity path (decoder.cu: gemm_simt_kernel + attn_simt_kernel) spends 115 ms in its GEMMs and 55 ms in its
 // attentions per cfg3 generate.  Here the same sequence of launches (models/decoder.py:96-109, layers/transformer.py:141-160)
 // runs on tcgen05 with every operand split into a tf32 head and tail (tf32x3.cuh: three kind::tf32 MMAs per k-step, fp32
-// accumulator in tensor memory, ~2^-21 relative per product -- as good as an FFMA chain):
+// accumulator in tensor memory, ~2^-22 relative per operand: measured 4 - 5 x the rounding error of the FFMA chain, 5.8e-6 on eps):
 //
-//   t3_gemm_kernel   y = epi(pro(A) W^T + b) for 128 rows x one NB-column block of W.  A rows stream in 32 columns at a time
-//                    (16-byte cp.async, double-buffered); the RMSNorm / AdaRMSNorm / LayerNorm prologue of gemm_simt.cuh is
-//                    applied on the way into the operand image (row statistics from a pre-pass over the tile); weight chunks
-//                    arrive by one bulk copy each from images packed per step (t3_pack_jobs_kernel: one launch for all 62
-//                    blocks); epilogues: bias, residual, positional table, SwiGLU (x 80 | gate 80 per block), and the fused
-//                    DDIM / DDPM / DPM update rule of the last GEMM.
-//   t3_attn_kernel   one CTA = (utterance, head, 128 queries), 128 threads (thread <-> query <-> tensor-memory lane), keys in
-//                    blocks of 32: S = Q K^T (15 MMAs) -> online softmax in registers (exp2, fp32) -> P split hi / lo into a
-//                    shared-memory operand image -> O_blk = P V (12 MMAs, V staged transposed) -> acc = acc * corr + O_blk in
-//                    registers.  Band (|i - j| <= 64, attention.py:94-111) or full context (mla.py:176-180) by a per-element
-//                    mask; only the key blocks a tile can see are visited.  Two CTAs per SM overlap each other's round trips.
+//   t3_gemm_kernel   y = epi(pro(A) W^T + b) for 128 rows x one NB-column block of W, 288 threads, two CTAs per SM.  Warps 0-7
+//                    fetch the A values of a 16-element chunk (three chunks ahead), apply the RMSNorm / AdaRMSNorm / LayerNorm
+//                    prologue of gemm_simt.cuh (row statistics: t3_rowstats_kernel, a small launch in front), split hi / lo into
+//                    one of two operand-image buffers and hand it over by per-warp mbarrier arrivals; warp 8 streams the weight
+//                    chunks (bulk copies into three buffers, from images packed per step by ONE launch of t3_pack_jobs_kernel)
+//                    and issues the MMAs.  Epilogues: bias, GELU, SwiGLU (x 80 | gate 80 per block) -> a shared-memory tile ->
+//                    the TMA engine (bulk copy per row; the residual GEMMs as bulk ADD in L2), or coalesced walks for the
+//                    positional table and the fused DDIM / DDPM / DPM update rule of the last GEMM.
+//   t3_attn_kernel   one CTA = (utterance, head, 128 queries), 160 threads (thread <-> query <-> tensor-memory lane; warp 4 issues
+//                    the MMAs), keys in blocks of 32: S = Q K^T (15 MMAs, one block ahead in a second tensor-memory block) ->
+//                    online softmax in registers (exp2, fp32) -> P split hi / lo into a shared-memory operand image -> O += P V
+//                    (12 MMAs, V staged transposed) accumulating in tensor memory with a lazily raised running maximum.  Band
+//                    (|i - j| <= 64, attention.py:94-111) or full context (mla.py:176-180) by a per-element mask with
+//                    warp-uniform fast paths; only the key blocks a tile can see are visited.  Two CTAs per SM.
 //
 // A row's result does not depend on the other rows of a launch (batch invariance).
 #define EDTTS_DECL_ONLY
