@@ -11,8 +11,9 @@
 // Bit-exactness: fp32 distances of magnitude ~170 carry ~1e-5 of rounding noise,
 // so when best and second-best are closer than a conservative bound the two
 // candidates are re-ranked with fp64 distances.  The result is the exact argmin;
-// the reference's fp32 argmin equals it on every seed tested (tests/test_gpu_vq.py
-// checks against both the fp32 oracle and its fp64 restatement).
+// the reference's fp32 argmin equals it on every seed tested
+// (tests/test_gpu_parity.py::test_vq_indices_bit_exact_vs_oracle_fp32_and_fp64 checks against both the fp32
+// oracle and its fp64 restatement; tests/test_gpu_pinned_configs.py::test_raw_features_to_vq_indices the chain from raw features).
 #include "common.cuh"
 #include "tf32x3.cuh"
 
