@@ -148,7 +148,7 @@ extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t*
 
 extern "C" int64_t edtts_context_workspace_bytes(int32_t B, int32_t S) {
   const int64_t rows = (int64_t)B * S;
-  return align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) + align_up(rows * 2 * H * 4, 256);
+  return align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) + align_up(rows * 2 * H * 4, 256) + t3::t3_context_scratch_bytes(rows);
 }
 
 extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64_t* sem_idx, const float* sem_features,
@@ -185,6 +185,11 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
   }
   if (precision == EDTTS_PREC_BF16)   // kv_down -> kv_norm -> kv_up on the tensor cores, stored as the attention operand image
     return tc_context_kv(w, ctx, nullptr, S, craw, kv_out, rows, st);
+  if (precision == EDTTS_PREC_TF32X3)   // the same projections as tf32 x 3 GEMMs, fp32 rows out
+    return t3::t3_context_kv(w, ctx, craw, kv_out,
+                             reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) +
+                                 align_up(rows * 2 * H * 4, 256),
+                             rows, st);
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     GemmArgs d;   // kv_down_proj (mla.py:146)

@@ -32,6 +32,15 @@ namespace t3 {
 constexpr int GT = 256;                               // compute threads of the GEMM kernel
 constexpr int GT_ALL = GT + 32;                       // + the MMA issuer warp
 
+// mbarrier wait of an MMA-issuer lane: a short sleep between probes, so that the issuer's spin does not take issue slots from the
+// compute warp sharing its scheduler (12.8 % of the attention kernel's issued instructions were this loop)
+__device__ __forceinline__ void mbar_wait_issuer(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    __nanosleep(32);
+    if (spin > (1u << 22)) __trap();
+  }
+}
+
 // ---- weight images ------------------------------------------------------------------------------------------------------
 struct PackJob {
   const float* W;        // first source row
@@ -228,14 +237,14 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
       }
       for (int c = 0; c < G_NW && c < nchunk; ++c) request_w(c);
       for (int c = 0; c < nchunk; ++c) {
-        mbar_wait(bar_a + (c & 1), (c >> 1) & 1);
-        mbar_wait(bar_w + c % G_NW, (c / G_NW) & 1);
+        mbar_wait_issuer(bar_a + (c & 1), (c >> 1) & 1);
+        mbar_wait_issuer(bar_w + c % G_NW, (c / G_NW) & 1);
         tc_fence_after();
         const uint32_t ah = smem_u32(sA + (c & 1) * G_A_BUF), wh = smem_u32(sW + (c % G_NW) * 2 * w_half);
         issue_chunk(tmem, ah, ah + G_A_BUF / 2, wh, wh + w_half, GK / 8, NB, c > 0);
         umma_commit(bar_mma + (c & 1));
         if (c >= 1 && c + 2 < nchunk) {                // buffer (c + 2) % 3 was chunk c - 1's
-          mbar_wait(bar_mma + ((c - 1) & 1), ((c - 1) >> 1) & 1);
+          mbar_wait_issuer(bar_mma + ((c - 1) & 1), ((c - 1) >> 1) & 1);
           request_w(c + 2);
         }
       }
@@ -359,7 +368,10 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float x = v[j] + s_bias[cc + j];
-        if (swi) x = x * silu(gt[j] + s_bias[NOUT + cc + j]);
+        if (swi) {                                      // x * silu(gate) with ex2.approx and the approximate reciprocal (2 ulp each)
+          const float gate = gt[j] + s_bias[NOUT + cc + j];
+          x = x * __fdividef(gate, 1.0f + __expf(-gate));
+        }
         if (g.epi == EPI_GELU) x = gelu_erf(x);
         v[j] = x;
       }
@@ -378,10 +390,11 @@ __global__ void __launch_bounds__(GT_ALL, 2) t3_gemm_kernel(const __grid_constan
   // ---- phase 2a: plain / residual outputs leave by the TMA engine, one bulk copy (or bulk add: global += shared, performed in
   // L2 -- the residual never travels to the SM) per row --------------------------------------------------------------------------
   if (g.epi == EPI_STORE || g.epi == EPI_GELU || g.epi == EPI_SWIGLU || g.epi == EPI_RESID) {
-    if (tid < TM && row0 + tid < g.rows) {
-      float* dst = g.out + (row0 + tid) * g.ldo + n_out0;
-      if (g.epi == EPI_RESID) bulk_reduce_add_f32(dst, stage + tid * LD, NOUT * 4);
-      else bulk_s2g(dst, stage + tid * LD, NOUT * 4);
+    const int r = warp * (TM / (GT / 32)) + lane;     // 16 rows per warp: the bulk instructions of a warp's lanes are serialised
+    if (lane < TM / (GT / 32) && row0 + r < g.rows) {
+      float* dst = g.out + (row0 + r) * g.ldo + n_out0;
+      if (g.epi == EPI_RESID) bulk_reduce_add_f32(dst, stage + r * LD, NOUT * 4);
+      else bulk_s2g(dst, stage + r * LD, NOUT * 4);
       bulk_commit();
       bulk_wait_all();                                 // shared memory must outlive the engine's reads; writes performed
     }
@@ -652,7 +665,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
   if (issuer) {
     if (lane == 0) {
       auto issue_s = [&](int i) {
-        mbar_wait(bar_k + (i & 1), (i >> 1) & 1);
+        mbar_wait_issuer(bar_k + (i & 1), (i >> 1) & 1);
         tc_fence_after();
         const uint32_t kh = smem_u32(sK + (i & 1) * 2 * A_K_HALF);
         issue_chunk(tmem + (i & 1) * AKB, smem_u32(sQh), smem_u32(sQl), kh, kh + A_K_HALF, HD / 8, AKB, false);
@@ -661,7 +674,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
       issue_s(0);
       for (int blk = 0; blk < nblk; ++blk) {
         if (blk + 1 < nblk) issue_s(blk + 1);
-        mbar_wait(bar_p, blk & 1);
+        mbar_wait_issuer(bar_p, blk & 1);
         tc_fence_after();
         issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, blk > 0);
         umma_commit(bar_o);
@@ -794,6 +807,40 @@ int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st) {
   LaunchScope ls(a.window >= 0 ? KC_T3_ATTN_WINDOW : KC_T3_ATTN_CROSS, st);
   t3_attn_kernel<<<grid, A_THREADS, A_SMEM, st>>>(a);
   return check_launch("t3_attn");
+}
+
+// ---- context K | V (once per utterance) ----------------------------------------------------------------------------------------
+static int64_t ctx_img_floats() { return t3_gemm_image_floats(H, RANK, 80, false) + t3_gemm_image_floats(RANK, 2 * H, 160, false); }
+int64_t t3_context_scratch_bytes(int64_t rows) { return align_up(NL * ctx_img_floats() * 4, 256) + align_up(rows * 8, 256); }
+
+int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, cudaStream_t st) {
+  float* img = reinterpret_cast<float*>(scratch);
+  float* stats = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + align_up(NL * ctx_img_floats() * 4, 256));
+  const int64_t o_up = t3_gemm_image_floats(H, RANK, 80, false);
+  int rc;
+  {
+    PackJobs pj;
+    int n = 0, k;
+    for (int l = 0; l < NL; ++l) {
+      const edtts_layer_weights& L = w->layers[l];
+      if ((k = add_jobs(pj, n, L.kv_down_w, img + l * ctx_img_floats(), H, RANK, 80, false)) < 0) return EDTTS_EINVAL; n += k;
+      if ((k = add_jobs(pj, n, L.kv_up_w, img + l * ctx_img_floats() + o_up, RANK, 2 * H, 160, false)) < 0) return EDTTS_EINVAL; n += k;
+    }
+    if ((rc = launch_pack(pj, n, st))) return rc;
+  }
+  for (int l = 0; l < NL; ++l) {
+    const edtts_layer_weights& L = w->layers[l];
+    const float* li = img + l * ctx_img_floats();
+    GemmArgs d;   // kv_down_proj (mla.py:146)
+    d.A = ctx; d.rows = rows; d.K = H; d.lda = H; d.W = L.kv_down_w; d.N = RANK; d.out = craw; d.ldo = RANK;
+    if ((rc = launch_t3_gemm(d, li, t3_gemm_block_stride(H, 80), 80, stats, st))) return rc;
+    GemmArgs u;   // kv_norm + kv_up_proj (mla.py:147-153)
+    u.A = craw; u.rows = rows; u.K = RANK; u.lda = RANK; u.W = L.kv_up_w; u.N = 2 * H;
+    u.out = kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
+    u.pro = PRO_RMS; u.norm_w = L.kv_norm_w; u.norm_eps = 1e-6f;
+    if ((rc = launch_t3_gemm(u, li + o_up, t3_gemm_block_stride(RANK, 160), 160, stats, st))) return rc;
+  }
+  return EDTTS_OK;
 }
 
 // ---- one decoder evaluation ---------------------------------------------------------------------------------------------------

@@ -21,6 +21,11 @@ int64_t t3_gemm_block_stride(int K, int NB);
 // attention with the semantics of launch_attn_simt
 int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st);
 
+// context K | V of all layers (mla.py:144-153): kv_down -> kv_norm -> kv_up as tf32 x 3 GEMMs; ctx [rows,160] in, craw [rows,80]
+// scratch, kv_out [4][rows][320]; scratch: t3_context_scratch_bytes(rows) bytes (weight images + row statistics)
+int64_t t3_context_scratch_bytes(int64_t rows);
+int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, cudaStream_t st);
+
 // one decoder evaluation (decoder.cu: decoder_step_fp32 with the kernels above); workspace as sized below
 int64_t t3_decoder_workspace_bytes(int B, int T, int S);
 int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
