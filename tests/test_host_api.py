@@ -113,3 +113,29 @@ def test_timesteps_and_cfg():
     assert inf._timesteps(4) == O.ddim_timesteps(4) and inf._timesteps(1) == [(999, 0)]
     assert inf._timesteps(16) == O.ddim_timesteps(16)
     assert E.CFG.from_dict(cfg.to_dict()) == cfg
+
+
+def test_precision_names_and_workspace_sizes(lib):
+    """precision="fp32" (the class default) selects the tf32 x 3 tensor-core path, "fp32_simt" the CUDA-core checker, "bf16" the fused
+    kernel; anything else raises.  Workspace sizes are pure host arithmetic (no GPU needed): the tensor-core fp32 path adds its weight
+    images and row statistics to the CUDA-core path's buffers; the context workspace covers its scratch for every precision."""
+    import pytest
+    import edge_diffusion_tts_b200 as E
+    from edge_diffusion_tts_b200 import _lib
+    dec = E.EdgeDiffusionDecoder(E.CFG(device="cpu"))
+    assert dec.precision == "fp32"
+    want = {"fp32": _lib.PREC_TF32X3, "fp32_simt": _lib.PREC_FP32, "bf16": _lib.PREC_BF16}
+    for name, code in want.items():
+        dec.precision = name
+        assert dec._prec() == code
+    dec.precision = "fp16"
+    with pytest.raises(ValueError):
+        dec._prec()
+    B, T, S = 3, 200, 100
+    simt = lib.edtts_decoder_workspace_bytes(B, T, S, _lib.PREC_FP32)
+    t3 = lib.edtts_decoder_workspace_bytes(B, T, S, _lib.PREC_TF32X3)
+    assert simt == 2 * B * T * 160 * 4 + B * T * 480 * 4
+    assert t3 >= simt + B * T * 8 + 4 * 2_400_000          # + row statistics + ~10 MB of hi | lo weight images
+    assert lib.edtts_context_workspace_bytes(B, S) >= B * S * (160 + 80 + 320) * 4 + B * S * 8
+    # one N-block image of a [160 -> 160] matrix: 5 chunks x (hi | lo) x 8 slabs x 160 rows x 16 B, + the statistics of `rows` rows
+    assert lib.edtts_test_gemm_workspace_bytes(1000, 160, 160, 0) == 5 * 2 * 8 * 160 * 16 + 1000 * 8
