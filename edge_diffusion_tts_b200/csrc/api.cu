@@ -222,7 +222,16 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
   if (precision == EDTTS_PREC_BF16)
     return tc_test_attention(q, q_stride, k, v, kv_stride, o, B, Tq, Tk, window, as_stream(stream));
   AttnArgs a{q, q_stride, k, v, kv_stride, o, H, Tq, Tk, window, 1.0f / sqrtf((float)HD)};
-  if (precision == EDTTS_PREC_TF32X3) return t3::launch_t3_attn(a, B, as_stream(stream));
+  if (precision == EDTTS_PREC_TF32X3) {   // full-context attention: with the K | V operand images the decoder step uses (this unit-test
+    void* img = nullptr;                  // hook owns the scratch: allocate, run, synchronise, free)
+    if (window < 0 && cudaMalloc(&img, (size_t)t3::t3_kvimg_bytes(B, Tk)) != cudaSuccess) return check_launch("test_attention scratch");
+    int rc = t3::launch_t3_attn(a, B, img, as_stream(stream));
+    if (img) {
+      cudaStreamSynchronize(as_stream(stream));
+      cudaFree(img);
+    }
+    return rc;
+  }
   return launch_attn_simt(a, B, as_stream(stream));
 }
 

@@ -537,12 +537,70 @@ constexpr int A_K_HALF = (HD / 4) * AKB * 16;         // 10 slabs x 32 keys x 16
 constexpr int A_VN = 48;                              // head_dim padded to an MMA N (rows 40..47 of the V^T image stay zero)
 constexpr int A_V_HALF = (AKB / 4) * A_VN * 16;       // 8 slabs x 48 rows x 16 B
 constexpr int A_P_HALF = (AKB / 4) * AQ * 16;         // 8 slabs x 128 rows x 16 B
-constexpr int A_SMEM = 2 * (A_Q_HALF + 2 * A_K_HALF + A_V_HALF + A_P_HALF) + 64;
+constexpr int A_SMEM = 2 * (A_Q_HALF + 2 * A_K_HALF + A_V_HALF + A_P_HALF) + 128;
 constexpr int A_NLD = (AKB * (HD / 4) + AQ - 1) / AQ; // 16-byte pieces of a K (or V) block per thread: 320 / 128 -> 3
 constexpr float A_GROW = 8.0f;                        // lazy running maximum: raise it only beyond 2^8
 constexpr int A_THREADS = AQ + 32;                    // softmax warps + the MMA issuer warp
 
-__global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a) {
+// Operand images of context K | V (cross-attention): per (utterance, head, 32-key block) [K hi | K lo | V^T hi | V^T lo], exactly the
+// shared-memory layout of the attention kernel, so that its issuer lane streams a block in with one bulk copy each for K and V
+// and the softmax warps issue no global load at all (their proxy fences / arrivals wait for every outstanding load of a thread).
+constexpr int A_IMG_K = 2 * A_K_HALF, A_IMG_V = 2 * A_V_HALF, A_IMG_BLK = A_IMG_K + A_IMG_V;   // 10,240 + 12,288 bytes
+
+__global__ void __launch_bounds__(AQ) t3_kvimg_kernel(const float* __restrict__ k, const float* __restrict__ v, int kv_stride, int Tk,
+                                                      uint8_t* __restrict__ img) {
+  __shared__ __align__(16) uint8_t blk[A_IMG_BLK];
+  const int tid = threadIdx.x, i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int nb = gridDim.x, kc = i * AKB;
+  uint8_t* sKh = blk;
+  uint8_t* sKl = blk + A_K_HALF;
+  uint8_t* sVh = blk + A_IMG_K;
+  uint8_t* sVl = sVh + A_V_HALF;
+  if (tid < 64) {                                      // padding rows 40..47 of the V^T images
+    const int slab = tid >> 3, row = HD + (tid & 7);
+    *reinterpret_cast<float4*>(sVh + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sVl + slab * (A_VN * 16) + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float* kbase = k + (int64_t)b * Tk * kv_stride + h * HD;
+  const float* vbase = v + (int64_t)b * Tk * kv_stride + h * HD;
+#pragma unroll
+  for (int it = 0; it < A_NLD; ++it) {
+    const int idx = tid + it * AQ;
+    if (idx >= AKB * (HD / 4)) continue;
+    const int key = idx / (HD / 4), c4 = idx % (HD / 4);
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if (kc + key < Tk) {
+      kk = *reinterpret_cast<const float4*>(kbase + (int64_t)(kc + key) * kv_stride + 4 * c4);
+      vv = *reinterpret_cast<const float4*>(vbase + (int64_t)(kc + key) * kv_stride + 4 * c4);
+    }
+    {
+      const float x[4] = {kk.x, kk.y, kk.z, kk.w};
+      float4 hi, lo;
+      hi.x = tf32_rna(x[0]); hi.y = tf32_rna(x[1]); hi.z = tf32_rna(x[2]); hi.w = tf32_rna(x[3]);
+      lo.x = x[0] - hi.x; lo.y = x[1] - hi.y; lo.z = x[2] - hi.z; lo.w = x[3] - hi.w;
+      *reinterpret_cast<float4*>(sKh + c4 * (AKB * 16) + key * 16) = hi;
+      *reinterpret_cast<float4*>(sKl + c4 * (AKB * 16) + key * 16) = lo;
+    }
+    {
+      const float x[4] = {vv.x, vv.y, vv.z, vv.w};
+      const int off = (key >> 2) * (A_VN * 16) + (key & 3) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float hi = tf32_rna(x[j]);
+        *reinterpret_cast<float*>(sVh + off + (4 * c4 + j) * 16) = hi;
+        *reinterpret_cast<float*>(sVl + off + (4 * c4 + j) * 16) = x[j] - hi;
+      }
+    }
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(img + (((int64_t)b * NH + h) * nb + i) * A_IMG_BLK);
+  for (int j = tid; j < A_IMG_BLK / 16; j += AQ) dst[j] = reinterpret_cast<const float4*>(blk)[j];
+}
+
+// IMG: the K / V blocks come as ready-made operand images (t3_kvimg_kernel) by bulk copies of the issuer lane; K double-buffered,
+// V single-buffered (requested when P V of the previous block has retired); the softmax warps neither load nor convert K / V.
+template <bool IMG>
+__global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a, const uint8_t* __restrict__ kvimg) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* sQh = smem;
   uint8_t* sQl = sQh + A_Q_HALF;
@@ -556,7 +614,9 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
   uint64_t* bar_o = bars + 2;                          // P V(i) retired
   uint64_t* bar_k = bars + 3;                          // [2] K image of block i written, S block (i & 1) read out (4 warp arrivals)
   uint64_t* bar_p = bars + 5;                          // V and P images of block i written, O rescaled (4 warp arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* bar_kl = bars + 6;                         // [2] IMG: K image of block i landed in buffer i & 1
+  uint64_t* bar_vl = bars + 8;                         // IMG: V image of block i landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool issuer = warp == AQ / 32;
   const int b = blockIdx.z, h = blockIdx.y;
@@ -572,6 +632,9 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
     mbar_init(bar_k, AQ / 32);
     mbar_init(bar_k + 1, AQ / 32);
     mbar_init(bar_p, AQ / 32);
+    mbar_init(bar_kl, 1);
+    mbar_init(bar_kl + 1, 1);
+    mbar_init(bar_vl, 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<128>(tmem_slot);
@@ -649,10 +712,12 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
 
   // ---- prologue: K(0) staged ----
   if (!issuer) {
-    fetch(kbase, klo, kreg);
-    stash_k(0);
-    if (nblk > 1) fetch(kbase, klo + AKB, kreg);
-    fetch(vbase, klo, vreg);
+    if (!IMG) {
+      fetch(kbase, klo, kreg);
+      stash_k(0);
+      if (nblk > 1) fetch(kbase, klo + AKB, kreg);
+      fetch(vbase, klo, vreg);
+    }
     fence_proxy_async();
   }
   tc_fence_before();
@@ -664,8 +729,23 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
   // ================= MMA issuer: warp 4, one elected lane =================
   if (issuer) {
     if (lane == 0) {
+      const uint8_t* img = IMG ? kvimg + ((int64_t)b * NH + h) * nblk * A_IMG_BLK : nullptr;   // klo = 0: block i <-> image block i
+      auto req_k = [&](int i) {
+        mbar_expect_tx(bar_kl + (i & 1), A_IMG_K);
+        bulk_g2s(sK + (i & 1) * A_IMG_K, img + (int64_t)i * A_IMG_BLK, A_IMG_K, bar_kl + (i & 1));
+      };
+      auto req_v = [&](int i) {
+        mbar_expect_tx(bar_vl, A_IMG_V);
+        bulk_g2s(sVh, img + (int64_t)i * A_IMG_BLK + A_IMG_K, A_IMG_V, bar_vl);
+      };
+      if (IMG) {
+        req_k(0);
+        if (nblk > 1) req_k(1);
+        req_v(0);
+      }
       auto issue_s = [&](int i) {
         mbar_wait_issuer(bar_k + (i & 1), (i >> 1) & 1);
+        if (IMG) mbar_wait_issuer(bar_kl + (i & 1), (i >> 1) & 1);
         tc_fence_after();
         const uint32_t kh = smem_u32(sK + (i & 1) * 2 * A_K_HALF);
         issue_chunk(tmem + (i & 1) * AKB, smem_u32(sQh), smem_u32(sQl), kh, kh + A_K_HALF, HD / 8, AKB, false);
@@ -674,10 +754,19 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
       issue_s(0);
       for (int blk = 0; blk < nblk; ++blk) {
         if (blk + 1 < nblk) issue_s(blk + 1);
+        if (IMG && blk + 2 < nblk) {                   // K buffer blk & 1 is free once S(blk) has retired
+          mbar_wait_issuer(bar_s + (blk & 1), (blk >> 1) & 1);
+          req_k(blk + 2);
+        }
         mbar_wait_issuer(bar_p, blk & 1);
+        if (IMG) mbar_wait_issuer(bar_vl, blk & 1);
         tc_fence_after();
         issue_chunk(tmem + tO, smem_u32(sPh), smem_u32(sPl), smem_u32(sVh), smem_u32(sVl), AKB / 8, A_VN, blk > 0);
         umma_commit(bar_o);
+        if (IMG && blk + 1 < nblk) {                   // the single V buffer is free once P V(blk) has retired
+          mbar_wait_issuer(bar_o, blk & 1);
+          req_v(blk + 1);
+        }
       }
     }
     return;
@@ -696,8 +785,10 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
     // ---- A: K(blk+1) -> the other K buffer (S(blk-1), its last reader, retired: this thread waited for it); this warp has read
     // S(blk-1) out of the tensor-memory block that S(blk+1) will overwrite ----
     if (blk + 1 < nblk) {
-      stash_k((blk + 1) & 1);
-      if (blk + 2 < nblk) fetch(kbase, kc + 2 * AKB, kreg);
+      if (!IMG) {
+        stash_k((blk + 1) & 1);
+        if (blk + 2 < nblk) fetch(kbase, kc + 2 * AKB, kreg);
+      }
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
@@ -767,8 +858,10 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
         tmem_st_wait();
       }
     }
-    stash_v();
-    if (blk + 1 < nblk) fetch(vbase, kc + AKB, vreg);
+    if (!IMG) {
+      stash_v();
+      if (blk + 1 < nblk) fetch(vbase, kc + AKB, vreg);
+    }
 #pragma unroll
     for (int q4 = 0; q4 < AKB / 4; ++q4) split_store(sPh, sPl, q4, tid, s + 4 * q4);
     // ---- E: hand P(blk), V(blk) to the issuer ----
@@ -795,17 +888,33 @@ __global__ void __launch_bounds__(A_THREADS, 2) t3_attn_kernel(const AttnArgs a)
   if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
-int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st) {
+int64_t t3_kvimg_bytes(int B, int Tk) { return (int64_t)B * NH * ((Tk + AKB - 1) / AKB) * A_IMG_BLK; }
+
+// kvimg: scratch of t3_kvimg_bytes(B, Tk) bytes for the operand images of a full-context (window < 0) attention, or null: the softmax
+// warps then stage K / V themselves (always for the band attention, whose k | v change with every layer and step)
+int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st) {
   EDTTS_REQUIRE(a.q_stride % 4 == 0 && a.kv_stride % 4 == 0 && a.o_stride % 4 == 0, EDTTS_EINVAL, "t3_attn: strides must be multiples of 4");
   static PerDeviceOnce configured;
   if (configured.need()) {
-    if (cudaFuncSetAttribute(t3_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(t3_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(t3_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM) != cudaSuccess)
       return check_launch("t3_attn smem attribute");
     configured.set();
   }
   dim3 grid((a.Tq + AQ - 1) / AQ, NH, B);
+  if (kvimg && a.window < 0) {
+    {
+      LaunchScope ls(KC_TC_MISC, st);
+      t3_kvimg_kernel<<<dim3((a.Tk + AKB - 1) / AKB, NH, B), AQ, 0, st>>>(a.k, a.v, a.kv_stride, a.Tk, reinterpret_cast<uint8_t*>(kvimg));
+      int rc = check_launch("t3_kvimg");
+      if (rc) return rc;
+    }
+    LaunchScope ls(KC_T3_ATTN_CROSS, st);
+    t3_attn_kernel<true><<<grid, A_THREADS, A_SMEM, st>>>(a, reinterpret_cast<const uint8_t*>(kvimg));
+    return check_launch("t3_attn");
+  }
   LaunchScope ls(a.window >= 0 ? KC_T3_ATTN_WINDOW : KC_T3_ATTN_CROSS, st);
-  t3_attn_kernel<<<grid, A_THREADS, A_SMEM, st>>>(a);
+  t3_attn_kernel<false><<<grid, A_THREADS, A_SMEM, st>>>(a, nullptr);
   return check_launch("t3_attn");
 }
 
@@ -869,7 +978,8 @@ static ImgLayout img_layout() {
 int64_t t3_decoder_workspace_bytes(int B, int T, int S) {
   (void)S;
   const int64_t R = (int64_t)B * T;
-  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256);
+  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256) +
+         align_up(t3_kvimg_bytes(B, S), 256);
 }
 
 int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
@@ -881,6 +991,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
   float* big = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256));
   float* img = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256));
   float* stats = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256));
+  void* kvimg = ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256);
   const ImgLayout IL = img_layout();
   const float scale = 1.0f / sqrtf((float)HD);
   const int64_t s160 = t3_gemm_block_stride(H, 160), s80 = t3_gemm_block_stride(H, 80), s_in = t3_gemm_block_stride(M, 160),
@@ -921,7 +1032,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     }
     {  // banded self-attention (attention.py:94-111)
       AttnArgs at{big, 3 * H, big + H, big + 2 * H, 3 * H, a, H, T, T, WIN, scale};
-      if ((rc = launch_t3_attn(at, B, st))) return rc;
+      if ((rc = launch_t3_attn(at, B, nullptr, st))) return rc;
     }
     {  // h += attn.proj(o)   (attention.py:123, transformer.py:146)
       GemmArgs g;
@@ -938,7 +1049,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     {  // full cross-attention over the S context tokens (mla.py:176-180)
       const float* kvl = kv + (int64_t)l * B * S * 2 * H;
       AttnArgs at{big, H, kvl, kvl + H, 2 * H, a, H, T, S, -1, scale};
-      if ((rc = launch_t3_attn(at, B, st))) return rc;
+      if ((rc = launch_t3_attn(at, B, kvimg, st))) return rc;
     }
     {  // h += out_proj(o)   (mla.py:194)
       GemmArgs g;

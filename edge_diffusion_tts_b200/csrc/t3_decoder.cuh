@@ -18,8 +18,10 @@ int pack_w_blocks(const float* W, float* img, int K, int N, int NB, bool swiglu,
 int64_t t3_gemm_image_floats(int K, int N, int NB, bool swiglu);
 int64_t t3_gemm_block_stride(int K, int NB);
 
-// attention with the semantics of launch_attn_simt
-int launch_t3_attn(const AttnArgs& a, int B, cudaStream_t st);
+// attention with the semantics of launch_attn_simt; kvimg (full-context attention only): t3_kvimg_bytes(B, Tk) bytes of scratch for
+// the K | V operand images the issuer then streams in by bulk copies, or null
+int64_t t3_kvimg_bytes(int B, int Tk);
+int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st);
 
 // context K | V of all layers (mla.py:144-153): kv_down -> kv_norm -> kv_up as tf32 x 3 GEMMs; ctx [rows,160] in, craw [rows,80]
 // scratch, kv_out [4][rows][320]; scratch: t3_context_scratch_bytes(rows) bytes (weight images + row statistics)
