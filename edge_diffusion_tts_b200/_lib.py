@@ -71,6 +71,7 @@ SIGNATURES = {
     "edtts_cond_prepare": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _i32, _p]),
     "edtts_context_prepare": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, _p, _i64, _i32, _i32, _i32, _p]),
     "edtts_context_workspace_bytes": (_i64, [_i32, _i32]),
+    "edtts_context_kv_bytes": (_i64, [_i32, _i32, _i32]),
     "edtts_decoder_step": (C.c_int, [C.POINTER(DecoderWeights), _p, _p, _p, C.POINTER(StepArgs), _p, _i64, _i32,
                                       _i32, _i32, _i32, _p]),
     "edtts_decoder_workspace_bytes": (_i64, [_i32, _i32, _i32, _i32]),

@@ -225,7 +225,7 @@ extern "C" int edtts_test_attention(const float* q, int32_t q_stride, const floa
   if (precision == EDTTS_PREC_TF32X3) {   // full-context attention: with the K | V operand images the decoder step uses (this unit-test
     void* img = nullptr;                  // hook owns the scratch: allocate, run, synchronise, free)
     if (window < 0 && cudaMalloc(&img, (size_t)t3::t3_kvimg_bytes(B, Tk)) != cudaSuccess) return check_launch("test_attention scratch");
-    int rc = t3::launch_t3_attn(a, B, img, as_stream(stream));
+    int rc = t3::launch_t3_attn(a, B, img, true, as_stream(stream));
     if (img) {
       cudaStreamSynchronize(as_stream(stream));
       cudaFree(img);

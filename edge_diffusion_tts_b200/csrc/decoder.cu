@@ -146,6 +146,11 @@ extern "C" int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t*
   return check_launch("cond_kernel");
 }
 
+extern "C" int64_t edtts_context_kv_bytes(int32_t B, int32_t S, int32_t precision) {
+  if (precision == EDTTS_PREC_TF32X3) return t3::t3_kv_total_bytes(B, S);   // fp32 rows + the cross-attention operand images
+  return (int64_t)NL * B * S * 2 * H * 4;
+}
+
 extern "C" int64_t edtts_context_workspace_bytes(int32_t B, int32_t S) {
   const int64_t rows = (int64_t)B * S;
   return align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) + align_up(rows * 2 * H * 4, 256) + t3::t3_context_scratch_bytes(rows);
@@ -189,7 +194,7 @@ extern "C" int edtts_context_prepare(const edtts_decoder_weights* w, const int64
     return t3::t3_context_kv(w, ctx, craw, kv_out,
                              reinterpret_cast<char*>(workspace) + align_up(rows * H * 4, 256) + align_up(rows * RANK * 4, 256) +
                                  align_up(rows * 2 * H * 4, 256),
-                             rows, st);
+                             rows, B, S, st);
   for (int l = 0; l < NL; ++l) {
     const edtts_layer_weights& L = w->layers[l];
     GemmArgs d;   // kv_down_proj (mla.py:146)

@@ -892,7 +892,16 @@ int64_t t3_kvimg_bytes(int B, int Tk) { return (int64_t)B * NH * ((Tk + AKB - 1)
 
 // kvimg: scratch of t3_kvimg_bytes(B, Tk) bytes for the operand images of a full-context (window < 0) attention, or null: the softmax
 // warps then stage K / V themselves (always for the band attention, whose k | v change with every layer and step)
-int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st) {
+int64_t t3_kv_rows_bytes(int B, int S) { return align_up((int64_t)NL * B * S * 2 * H * 4, 256); }
+int64_t t3_kv_total_bytes(int B, int S) { return t3_kv_rows_bytes(B, S) + NL * align_up(t3_kvimg_bytes(B, S), 256); }
+
+int launch_t3_kvimg(const float* k, const float* v, int kv_stride, int Tk, int B, void* kvimg, cudaStream_t st) {
+  LaunchScope ls(KC_TC_MISC, st);
+  t3_kvimg_kernel<<<dim3((Tk + AKB - 1) / AKB, NH, B), AQ, 0, st>>>(k, v, kv_stride, Tk, reinterpret_cast<uint8_t*>(kvimg));
+  return check_launch("t3_kvimg");
+}
+
+int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, bool build, cudaStream_t st) {
   EDTTS_REQUIRE(a.q_stride % 4 == 0 && a.kv_stride % 4 == 0 && a.o_stride % 4 == 0, EDTTS_EINVAL, "t3_attn: strides must be multiples of 4");
   static PerDeviceOnce configured;
   if (configured.need()) {
@@ -903,10 +912,8 @@ int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st) {
   }
   dim3 grid((a.Tq + AQ - 1) / AQ, NH, B);
   if (kvimg && a.window < 0) {
-    {
-      LaunchScope ls(KC_TC_MISC, st);
-      t3_kvimg_kernel<<<dim3((a.Tk + AKB - 1) / AKB, NH, B), AQ, 0, st>>>(a.k, a.v, a.kv_stride, a.Tk, reinterpret_cast<uint8_t*>(kvimg));
-      int rc = check_launch("t3_kvimg");
+    if (build) {
+      int rc = launch_t3_kvimg(a.k, a.v, a.kv_stride, a.Tk, B, kvimg, st);
       if (rc) return rc;
     }
     LaunchScope ls(KC_T3_ATTN_CROSS, st);
@@ -922,7 +929,8 @@ int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st) {
 static int64_t ctx_img_floats() { return t3_gemm_image_floats(H, RANK, 80, false) + t3_gemm_image_floats(RANK, 2 * H, 160, false); }
 int64_t t3_context_scratch_bytes(int64_t rows) { return align_up(NL * ctx_img_floats() * 4, 256) + align_up(rows * 8, 256); }
 
-int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, cudaStream_t st) {
+int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, int B, int S,
+                  cudaStream_t st) {
   float* img = reinterpret_cast<float*>(scratch);
   float* stats = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + align_up(NL * ctx_img_floats() * 4, 256));
   const int64_t o_up = t3_gemm_image_floats(H, RANK, 80, false);
@@ -948,6 +956,9 @@ int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw,
     u.out = kv_out + (int64_t)l * rows * 2 * H; u.ldo = 2 * H;
     u.pro = PRO_RMS; u.norm_w = L.kv_norm_w; u.norm_eps = 1e-6f;
     if ((rc = launch_t3_gemm(u, li + o_up, t3_gemm_block_stride(RANK, 160), 160, stats, st))) return rc;
+    // the layer's operand images for the cross-attention of every decoder step of this generate, behind the fp32 rows
+    char* img_l = reinterpret_cast<char*>(kv_out) + t3_kv_rows_bytes(B, S) + l * align_up(t3_kvimg_bytes(B, S), 256);
+    if ((rc = launch_t3_kvimg(u.out, u.out + H, 2 * H, S, B, img_l, st))) return rc;
   }
   return EDTTS_OK;
 }
@@ -978,8 +989,7 @@ static ImgLayout img_layout() {
 int64_t t3_decoder_workspace_bytes(int B, int T, int S) {
   (void)S;
   const int64_t R = (int64_t)B * T;
-  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256) +
-         align_up(t3_kvimg_bytes(B, S), 256);
+  return align_up(R * H * 4, 256) * 2 + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256);
 }
 
 int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const float* mod, const float* kv, const edtts_step_args* args,
@@ -991,7 +1001,6 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
   float* big = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256));
   float* img = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256));
   float* stats = reinterpret_cast<float*>(ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256));
-  void* kvimg = ws + 2 * align_up(R * H * 4, 256) + align_up(R * 3 * H * 4, 256) + align_up(img_layout().total * 4, 256) + align_up(R * 8, 256);
   const ImgLayout IL = img_layout();
   const float scale = 1.0f / sqrtf((float)HD);
   const int64_t s160 = t3_gemm_block_stride(H, 160), s80 = t3_gemm_block_stride(H, 80), s_in = t3_gemm_block_stride(M, 160),
@@ -1032,7 +1041,7 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     }
     {  // banded self-attention (attention.py:94-111)
       AttnArgs at{big, 3 * H, big + H, big + 2 * H, 3 * H, a, H, T, T, WIN, scale};
-      if ((rc = launch_t3_attn(at, B, nullptr, st))) return rc;
+      if ((rc = launch_t3_attn(at, B, nullptr, false, st))) return rc;
     }
     {  // h += attn.proj(o)   (attention.py:123, transformer.py:146)
       GemmArgs g;
@@ -1049,7 +1058,9 @@ int t3_decoder_step(const edtts_decoder_weights* w, const float* x_t, const floa
     {  // full cross-attention over the S context tokens (mla.py:176-180)
       const float* kvl = kv + (int64_t)l * B * S * 2 * H;
       AttnArgs at{big, H, kvl, kvl + H, 2 * H, a, H, T, S, -1, scale};
-      if ((rc = launch_t3_attn(at, B, kvimg, st))) return rc;
+      // operand images of this layer's context k | v, written once per generate by edtts_context_prepare behind the fp32 rows of kv
+      void* kvimg = const_cast<char*>(reinterpret_cast<const char*>(kv)) + t3_kv_rows_bytes(B, S) + l * align_up(t3_kvimg_bytes(B, S), 256);
+      if ((rc = launch_t3_attn(at, B, kvimg, false, st))) return rc;
     }
     {  // h += out_proj(o)   (mla.py:194)
       GemmArgs g;

@@ -21,12 +21,18 @@ int64_t t3_gemm_block_stride(int K, int NB);
 // attention with the semantics of launch_attn_simt; kvimg (full-context attention only): t3_kvimg_bytes(B, Tk) bytes of scratch for
 // the K | V operand images the issuer then streams in by bulk copies, or null
 int64_t t3_kvimg_bytes(int B, int Tk);
-int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, cudaStream_t st);
+// build = true: the images are built from a.k / a.v in front of the attention; false: kvimg already holds them (launch_t3_kvimg)
+int launch_t3_attn(const AttnArgs& a, int B, void* kvimg, bool build, cudaStream_t st);
+int launch_t3_kvimg(const float* k, const float* v, int kv_stride, int Tk, int B, void* kvimg, cudaStream_t st);
+// layout of the kv buffer of EDTTS_PREC_TF32X3: [NL][B S][320] fp32 rows (k | v), then per layer the operand images
+int64_t t3_kv_rows_bytes(int B, int S);              // offset of the first image
+int64_t t3_kv_total_bytes(int B, int S);
 
 // context K | V of all layers (mla.py:144-153): kv_down -> kv_norm -> kv_up as tf32 x 3 GEMMs; ctx [rows,160] in, craw [rows,80]
 // scratch, kv_out [4][rows][320]; scratch: t3_context_scratch_bytes(rows) bytes (weight images + row statistics)
 int64_t t3_context_scratch_bytes(int64_t rows);
-int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, cudaStream_t st);
+int t3_context_kv(const edtts_decoder_weights* w, const float* ctx, float* craw, float* kv_out, void* scratch, int64_t rows, int B, int S,
+                  cudaStream_t st);
 
 // one decoder evaluation (decoder.cu: decoder_step_fp32 with the kernels above); workspace as sized below
 int64_t t3_decoder_workspace_bytes(int B, int T, int S);

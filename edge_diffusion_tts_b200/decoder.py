@@ -204,6 +204,15 @@ class EdgeDiffusionDecoder(nn.Module):
         except KeyError:
             raise ValueError(f"precision must be 'fp32', 'bf16' or 'fp32_simt', got {self.precision!r}") from None
 
+    def alloc_kv(self, B: int, S: int, device) -> torch.Tensor:
+        """The buffer prepare_context() fills and step() reads: [layers, B*S, 320] fp32 rows (k | v); for precision="fp32" a flat
+        fp32 tensor that holds those rows followed by the operand images of the cross-attention (edtts_context_kv_bytes)."""
+        lib = _lib.load()
+        n = int(lib.edtts_context_kv_bytes(B, S, self._prec())) // 4
+        if n == self.cfg.layers * B * S * 2 * self.cfg.hidden:
+            return torch.empty(self.cfg.layers, B * S, 2 * self.cfg.hidden, dtype=torch.float32, device=device)
+        return torch.empty(n, dtype=torch.float32, device=device)
+
     def workspace_bytes(self, B: int, T: int, S: int):
         """(context bytes, step bytes) a caller must provide to own the scratch itself."""
         lib = _lib.load()
@@ -244,8 +253,9 @@ class EdgeDiffusionDecoder(nn.Module):
             sem_features, sem_idx = _lib.f32(sem_features), None
         else:
             sem_idx = _lib.i64(sem_idx)
-        kv = out if out is not None else torch.empty(self.cfg.layers, B * S, 2 * self.cfg.hidden,
-                                                     dtype=torch.float32, device=src.device)
+        kv = out if out is not None else self.alloc_kv(B, S, src.device)
+        if kv.numel() * 4 < int(lib.edtts_context_kv_bytes(B, S, self._prec())) or kv.dtype != torch.float32:
+            raise ValueError("context buffer too small for this precision: allocate it with alloc_kv()")
         nbytes = lib.edtts_context_workspace_bytes(B, S)
         if ws is None:
             ws = self._ws_ctx.get(nbytes, src.device)

@@ -87,7 +87,7 @@ class EdgeInference:
         p.sem_idx = torch.zeros(B, S, dtype=torch.int64, device=device)
         p.x = torch.empty(B, T, cfg.n_mels, dtype=torch.float32, device=device)
         p.x0 = torch.empty_like(p.x)
-        p.kv = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, dtype=torch.float32, device=device)
+        p.kv = self.decoder.alloc_kv(B, S, device)
         nb_ctx, nb_step = self.decoder.workspace_bytes(B, T, S)       # plan-private scratch: a captured graph
         p.ws_ctx = torch.empty(max(nb_ctx, 256), dtype=torch.uint8, device=device)    # must never see its
         p.ws_step = torch.empty(max(nb_step, 256), dtype=torch.uint8, device=device)  # buffers reallocated
@@ -224,7 +224,7 @@ class EdgeInference:
         p.known = torch.empty(B, max(L, 1), cfg.n_mels, **f)
         p.known_noise = torch.empty(max(steps, 1), B, max(L, 1), cfg.n_mels, **f)
         p.L = L
-        p.kv = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, **f)
+        p.kv = self.decoder.alloc_kv(B, S, device)
         p.kv0 = torch.empty_like(p.kv) if guided else None
         nb_ctx, nb_step = self.decoder.workspace_bytes(B, T, S)
         p.ws_ctx = torch.empty(max(nb_ctx, 256), dtype=torch.uint8, device=device)

@@ -273,7 +273,7 @@ class DPMSolverPP:
             p["feats"] = torch.empty(B, S, sem_features.shape[2], dtype=torch.float32, device=dev)
             p["x0"] = [torch.empty_like(p["x"]) for _ in range(n if return_intermediates else min(n, 3))]
             cfg = dec.cfg
-            p["kv"] = torch.empty(cfg.layers, B * S, 2 * cfg.hidden, dtype=torch.float32, device=dev)
+            p["kv"] = dec.alloc_kv(B, S, dev)
             p["mod_all"] = torch.empty(n * B, 2 * cfg.layers, 2 * cfg.hidden, dtype=torch.float32, device=dev)
             p["mods"] = [p["mod_all"][i * B:(i + 1) * B] for i in range(n)]
             nb_ctx, nb_step = dec.workspace_bytes(B, T, S)

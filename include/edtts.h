@@ -173,11 +173,15 @@ int edtts_cond_prepare(const edtts_decoder_weights* w, const int64_t* t, const i
                        float* mod_out, int32_t B, void* stream);
 /* decoder.py:83-93 + mla.py:144-153 for all layers (step-invariant):
  *   kv_out[LAYERS][B*S][320] = (k | v), head-major inside each half.
- * Exactly one of sem_idx (int64[B,S]) / sem_features (fp32[B,S,128]) is non-NULL. */
+ * Exactly one of sem_idx (int64[B,S]) / sem_features (fp32[B,S,128]) is non-NULL.
+ * kv_out holds edtts_context_kv_bytes(B, S, precision) bytes: for EDTTS_PREC_TF32X3 the rows are followed by the tf32 hi | lo
+ * operand images of every layer's k | v, which the cross-attention of every edtts_decoder_step of that precision streams in;
+ * the same buffer goes to edtts_decoder_step as `kv`. */
 int edtts_context_prepare(const edtts_decoder_weights* w, const int64_t* sem_idx, const float* sem_features,
                           float* kv_out, void* workspace, int64_t workspace_bytes, int32_t B, int32_t S,
                           int32_t precision, void* stream);
 int64_t edtts_context_workspace_bytes(int32_t B, int32_t S);
+int64_t edtts_context_kv_bytes(int32_t B, int32_t S, int32_t precision);
 
 /* Coefficients of the fused update, gathered on the device from the schedule
  * tables (so the call stays graph-capturable): t, t_prev int64[B]. */

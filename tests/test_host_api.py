@@ -137,5 +137,9 @@ def test_precision_names_and_workspace_sizes(lib):
     assert simt == 2 * B * T * 160 * 4 + B * T * 480 * 4
     assert t3 >= simt + B * T * 8 + 4 * 2_400_000          # + row statistics + ~10 MB of hi | lo weight images
     assert lib.edtts_context_workspace_bytes(B, S) >= B * S * (160 + 80 + 320) * 4 + B * S * 8
+    rows_bytes = 4 * B * S * 320 * 4
+    assert lib.edtts_context_kv_bytes(B, S, _lib.PREC_FP32) == rows_bytes == lib.edtts_context_kv_bytes(B, S, _lib.PREC_BF16)
+    # + per layer, utterance, head and 32-key block the hi | lo operand images of K (10,240 B) and V^T (12,288 B)
+    assert lib.edtts_context_kv_bytes(B, S, _lib.PREC_TF32X3) >= rows_bytes + 4 * B * 4 * ((S + 31) // 32) * 22528
     # one N-block image of a [160 -> 160] matrix: 5 chunks x (hi | lo) x 8 slabs x 160 rows x 16 B, + the statistics of `rows` rows
     assert lib.edtts_test_gemm_workspace_bytes(1000, 160, 160, 0) == 5 * 2 * 8 * 160 * 16 + 1000 * 8

@@ -108,7 +108,7 @@ def decoder(prec="fp32"):
     ref_mod = torch.stack([torch.nn.functional.linear(cond, sd[f"layers.{l}.norm{n}.proj.weight"], sd[f"layers.{l}.norm{n}.proj.bias"])
                            for l in range(4) for n in (1, 3)], dim=1)
     stats("cond mod", mod, ref_mod)
-    kv = dec.prepare_context(idx.to(DEV)).view(4, B, S, 320)
+    kv = dec.prepare_context(idx.to(DEV)).flatten()[:4 * B * S * 320].view(4, B, S, 320)   # (fp32: the operand images follow the rows)
     ctx = sd["token_emb.weight"][idx] + sd["context_pos_emb.pe"][:S]
     for l in range(4):
         k, v = O.cross_kv(ctx, sd, f"layers.{l}.cross_attn.")
