@@ -18,7 +18,9 @@
 //                    online softmax in registers (exp2, fp32) -> P split hi / lo into a shared-memory operand image -> O += P V
 //                    (12 MMAs, V staged transposed) accumulating in tensor memory with a lazily raised running maximum.  Band
 //                    (|i - j| <= 64, attention.py:94-111) or full context (mla.py:176-180) by a per-element mask with
-//                    warp-uniform fast paths; only the key blocks a tile can see are visited.  Two CTAs per SM.
+//                    warp-uniform fast paths; only the key blocks a tile can see are visited.  Two CTAs per SM.  Cross-attention:
+//                    K | V blocks arrive as ready-made operand images (t3_kvimg_kernel, built once per generate by
+//                    edtts_context_prepare) by bulk copies of the issuer lane -- the softmax warps issue no global load.
 //
 // A row's result does not depend on the other rows of a launch (batch invariance).
 #define EDTTS_DECL_ONLY
