@@ -12,13 +12,15 @@ h = rows[0]
 ik, im, iv, ig, igrid = h.index("Kernel Name"), h.index("Metric Name"), h.index("Metric Value"), h.index("ID"), h.index("Grid Size")
 d = OrderedDict()
 for r in rows[1:]:
-    d.setdefault((int(r[ig]), r[ik].split("(")[0], r[igrid]), {})[r[im]] = float(r[iv].replace(",", ""))
+    name = r[ik].split("(")[0].replace("void ", "").strip()
+    d.setdefault((int(r[ig]), name, r[igrid]), {})[r[im]] = float(r[iv].replace(",", ""))
 H, FFN, M = 160, 320, 80
 # name by (kernel, grid): the launches of one layer in order
 names = {("t3_gemm_kernel", "(1600, 3, 1)"): ("qkv GEMM  (AdaRMSNorm prologue, K 160 -> N 480)", 2 * H * 3 * H),
          ("t3_gemm_kernel", "(1600, 4, 1)"): ("ffn0 GEMM (AdaRMSNorm prologue, SwiGLU epilogue, 160 -> 640 -> 320)", 2 * H * 2 * FFN),
          ("t3_attn_kernel", "(7, 4, 256)"): None,
          ("t3_rowstats_kernel", None): ("row statistics of a norm prologue", 0),
+         ("t3_kvimg_kernel", None): ("context K | V operand images of one layer (once per generate)", 0),
          ("t3_pack_jobs_kernel", None): ("weight images of the step (62 blocks)", 0)}
 print(f"{'kernel':74s} {'us':>8s} {'tensor %':>8s} {'issue %':>8s} {'DRAM MB':>9s} {'GB/s':>7s} {'% HBM':>6s} {'TFLOP/s':>8s}")
 seen = {}
@@ -26,9 +28,9 @@ for (kid, kname, grid), v in d.items():
     t_us = v["gpu__time_duration.sum"] / 1e3
     mb = (v["dram__bytes_read.sum"] + v["dram__bytes_write.sum"]) / 1e6
     label, flop_row = None, 0
-    if kname == "t3_attn_kernel":
-        # window launches read q | k | v of the qkv buffer (393 MB), cross launches q and the context k | v (262 MB)
-        win = v["dram__bytes_read.sum"] > 330e6
+    if kname.startswith("t3_attn_kernel"):
+        # <0>: the softmax warps stage k | v themselves (band attention); <1>: ready-made context K | V operand images (cross-attention)
+        win = "<1>" not in kname
         label = "window attention (band +-64, 4 heads)" if win else "cross attention (400 context tokens, 4 heads)"
         flop_row = (4 * 129 * 40 * 2 * 2) if win else (4 * 400 * 40 * 2 * 2)
     elif kname == "t3_gemm_kernel" and grid == "(1600, 1, 1)":
