@@ -141,5 +141,11 @@ def test_precision_names_and_workspace_sizes(lib):
     assert lib.edtts_context_kv_bytes(B, S, _lib.PREC_FP32) == rows_bytes == lib.edtts_context_kv_bytes(B, S, _lib.PREC_BF16)
     # + per layer, utterance, head and 32-key block the hi | lo operand images of K (10,240 B) and V^T (12,288 B)
     assert lib.edtts_context_kv_bytes(B, S, _lib.PREC_TF32X3) >= rows_bytes + 4 * B * 4 * ((S + 31) // 32) * 22528
+    # the allocator of the Python class follows it: the reference's [layers, B*S, 320] rows, or a flat buffer with the images behind
+    dec.precision = "bf16"
+    assert tuple(dec.alloc_kv(B, S, "cpu").shape) == (4, B * S, 320)
+    dec.precision = "fp32"
+    kv = dec.alloc_kv(B, S, "cpu")
+    assert kv.dim() == 1 and kv.numel() * 4 == lib.edtts_context_kv_bytes(B, S, _lib.PREC_TF32X3) and kv.dtype == torch.float32
     # one N-block image of a [160 -> 160] matrix: 5 chunks x (hi | lo) x 8 slabs x 160 rows x 16 B, + the statistics of `rows` rows
     assert lib.edtts_test_gemm_workspace_bytes(1000, 160, 160, 0) == 5 * 2 * 8 * 160 * 16 + 1000 * 8
