@@ -19,8 +19,9 @@ One JSON line on stdout (rank 0).  Keys beyond the base contract:
                 in ``e2e.path`` / ``config.parallelism``)
   weak          (N > 1) the same step with 256 utterances PER GPU
   cfg5          (N > 1) BASELINE config 5, batch 128 x 3000 frames sharded over the N GPUs
-  configs       (N = 1) the other BASELINE configurations and the fp32 path, each with ms / frames per second / fraction of the
-                BASELINE.md section 3 ideal
+  configs       (N = 1) the other BASELINE configurations and cfg3 on both fp32-grade paths (cfg3_fp32_path: precision="fp32", tf32 x 3
+                on the tensor cores, the class default; cfg3_fp32_simt_path: the CUDA-core checker), each with ms / frames per
+                second / fraction of the BASELINE.md section 3 ideal
   cpu_baseline  (N = 1) the UNMODIFIED reference (baseline/_ref) on the host cores: all threads and one thread, cfg1 in full,
                 the same modules eager on cuda:0 with TF32 off as a labelled context number, and the free-running parity of
                 this package's fp32 / bf16 paths against it (oracle/parity.py criterion)
